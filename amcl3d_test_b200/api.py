@@ -1,0 +1,276 @@
+"""Python mirror of the reference's Grid3d / ParticleFilter interface over the C-ABI.
+
+Names, argument meaning and error behaviour follow amcl3d/src/Grid3d.h and ParticleFilter.h
+(open -> bool, computeCloudWeight -> 0 before a map is open, isIntoMap -> False without a map ...),
+so the parity tests read like the reference's own tests.  Every method is one C-ABI call; arrays are
+numpy float32 on the host or raw device pointers (ints) for resident data.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import capi
+from .capi import GRID_GAUSSIAN, GRID_QUIRK, GRID_SPLAT, TRIG_F32, TRIG_F64, check  # noqa: F401
+
+
+def device_info(device: int = 0) -> dict:
+    L = capi.load()
+    cnt, sm, maj, mnr = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    l2, mem = C.c_uint64(), C.c_uint64()
+    check(L.amcl3d_b200_device_info(device, C.byref(cnt), C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(l2), C.byref(mem)))
+    return dict(device_count=cnt.value, sm_count=sm.value, cc=(maj.value, mnr.value), l2_bytes=l2.value, mem_bytes=mem.value)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Grid3d:
+    """amcl3d::Grid3d (amcl3d/src/Grid3d.h:33-147)."""
+
+    def __init__(self, device: int = 0):
+        self._L = capi.load()
+        self._h = C.c_void_p()
+        check(self._L.amcl3d_b200_grid_create(device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.amcl3d_b200_grid_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- map / grid set-up ------------------------------------------------------------------
+    def info(self) -> dict:
+        gi = capi.GridInfo()
+        check(self._L.amcl3d_b200_grid_get_info(self._h, C.byref(gi)))
+        return dict(min=np.array(list(gi.min)), max=np.array(list(gi.max)), resol=gi.resol, sensor_dev=gi.sensor_dev,
+                    size=tuple(int(v) for v in gi.size), n_cells=int(gi.n_cells), has_map=bool(gi.has_map),
+                    has_grid=bool(gi.has_grid), device=gi.device)
+
+    def computePointCloud(self, xyz, resolution):
+        """computePointCloud (PointCloudTools.cpp:84-109): bounds of the map cloud; raises on <= 1 point."""
+        xyz = _f32(xyz)
+        mn, mx = (C.c_double * 3)(), (C.c_double * 3)()
+        rc = self._L.amcl3d_b200_grid_compute_bounds(self._h, xyz.ctypes.data, xyz.shape[1], xyz.shape[0], float(resolution), mn, mx)
+        if rc == capi.ERR_EMPTY:
+            raise RuntimeError("OcTree is empty")
+        check(rc)
+        return np.array(list(mn)), np.array(list(mx))
+
+    def setMap(self, mn, mx, resol):
+        a, b = (C.c_double * 3)(*[float(v) for v in mn]), (C.c_double * 3)(*[float(v) for v in mx])
+        check(self._L.amcl3d_b200_grid_set_map(self._h, a, b, float(resol)))
+
+    def computeGrid(self, xyz, sensor_dev, mode=GRID_QUIRK, sub=2, keep_edt=False):
+        """computeGrid / computeGrid2 (PointCloudTools.cpp:111-254) on the device."""
+        xyz = _f32(xyz)
+        check(self._L.amcl3d_b200_grid_build(self._h, xyz.ctypes.data, xyz.shape[1], xyz.shape[0], float(sensor_dev), mode, sub, int(keep_edt)))
+
+    def edt(self) -> np.ndarray:
+        n = self.info()["n_cells"]
+        out = np.empty(n, np.int32)
+        check(self._L.amcl3d_b200_grid_download_edt(self._h, out.ctypes.data, n))
+        return out
+
+    def uploadGrid(self, prob, size, sensor_dev):
+        prob = _f32(prob).reshape(-1)
+        assert prob.size == int(size[0]) * int(size[1]) * int(size[2])
+        check(self._L.amcl3d_b200_grid_upload(self._h, prob.ctypes.data, (C.c_uint32 * 3)(*[int(v) for v in size]), float(sensor_dev)))
+
+    def downloadGrid(self) -> np.ndarray:
+        n = self.info()["n_cells"]
+        out = np.empty(n, np.float32)
+        check(self._L.amcl3d_b200_grid_download(self._h, out.ctypes.data, n))
+        return out
+
+    def saveGrid(self, path) -> bool:
+        return self._L.amcl3d_b200_grid_save_file(self._h, os.fspath(path).encode()) == capi.OK
+
+    def loadGrid(self, path, sensor_dev) -> bool:
+        return self._L.amcl3d_b200_grid_load_file(self._h, os.fspath(path).encode(), float(sensor_dev)) == capi.OK
+
+    def open_points(self, xyz, sensor_dev, resolution, grid_path=None, mode=GRID_SPLAT, sub=2) -> bool:
+        """The body of Grid3d::open after the PCDs are loaded (Grid3d.cpp:155-197): bounds, cached
+        .grid if present and matching, else build (the fork builds with computeGrid2) and save."""
+        try:
+            self.computePointCloud(xyz, resolution)
+        except Exception:
+            return False
+        if grid_path is not None and os.path.exists(grid_path) and self.loadGrid(grid_path, sensor_dev):
+            return True
+        self.computeGrid(xyz, sensor_dev, mode=mode, sub=sub)
+        if grid_path is not None:
+            self.saveGrid(grid_path)
+        return True
+
+    # ---- queries ----------------------------------------------------------------------------
+    def isIntoMap(self, x, y, z) -> bool:
+        out = C.c_int(0)
+        check(self._L.amcl3d_b200_grid_is_into_map(self._h, float(np.float32(x)), float(np.float32(y)), float(np.float32(z)), C.byref(out)))
+        return bool(out.value)
+
+    def computeCloudWeight(self, cloud, tx, ty, tz, roll, pitch, yaw, trig_mode=TRIG_F64) -> np.float32:
+        cloud = _f32(cloud)
+        stride = cloud.shape[1] if cloud.ndim == 2 else 3
+        npts = cloud.shape[0] if cloud.ndim == 2 else 0
+        w = C.c_float(0)
+        pose = [float(np.float32(v)) for v in (tx, ty, tz, roll, pitch, yaw)]
+        check(self._L.amcl3d_b200_grid_cloud_weight(self._h, cloud.ctypes.data if npts else None, stride, npts, *pose, trig_mode, C.byref(w)))
+        return np.float32(w.value)
+
+    def device_ptr(self) -> int:
+        p = C.c_void_p()
+        check(self._L.amcl3d_b200_grid_device_ptr(self._h, C.byref(p)))
+        return p.value or 0
+
+    def bench_gather(self, window_cells=0, blocks=148 * 8, iters=64, coherent=False):
+        ms, loads = C.c_float(0), C.c_uint64(0)
+        check(self._L.amcl3d_b200_bench_gather(self._h, int(window_cells), blocks, iters, int(coherent), C.byref(ms), C.byref(loads)))
+        return ms.value, loads.value
+
+
+class ParticleFilter:
+    """amcl3d::ParticleFilter (amcl3d/src/ParticleFilter.h:104-252) bound to a Grid3d."""
+
+    def __init__(self, grid3d: Grid3d):
+        self._L = capi.load()
+        self.grid3d_ = grid3d
+        self._h = C.c_void_p()
+        check(self._L.amcl3d_b200_pf_create(grid3d._h, C.byref(self._h)))
+        self._keep = None  # keeps a bound torch tensor alive
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.amcl3d_b200_pf_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- p_ -----------------------------------------------------------------------------------
+    @property
+    def p_(self) -> np.ndarray:
+        n = self.size()
+        out = np.empty((n, 7), np.float32)
+        got = C.c_uint64(0)
+        check(self._L.amcl3d_b200_pf_get_particles(self._h, out.ctypes.data, n, C.byref(got)))
+        return out
+
+    @p_.setter
+    def p_(self, aos7):
+        aos7 = _f32(aos7)
+        assert aos7.ndim == 2 and aos7.shape[1] == 7
+        check(self._L.amcl3d_b200_pf_set_particles(self._h, aos7.ctypes.data, aos7.shape[0]))
+
+    def size(self) -> int:
+        n = C.c_uint64(0)
+        check(self._L.amcl3d_b200_pf_size(self._h, C.byref(n)))
+        return int(n.value)
+
+    def bind_device(self, ptr: int, n: int, capacity: int, keep=None):
+        check(self._L.amcl3d_b200_pf_bind_device(self._h, C.c_void_p(ptr), n, capacity))
+        self._keep = keep
+
+    def device_ptr(self):
+        p, n = C.c_void_p(), C.c_uint64(0)
+        check(self._L.amcl3d_b200_pf_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return p.value or 0, int(n.value)
+
+    def set_stream(self, cuda_stream: int | None):
+        check(self._L.amcl3d_b200_pf_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def set_trig_mode(self, mode):
+        check(self._L.amcl3d_b200_pf_set_trig_mode(self._h, mode))
+
+    # ---- the path -----------------------------------------------------------------------------
+    def set_cloud(self, cloud):
+        cloud = _f32(cloud)
+        npts = cloud.shape[0]
+        check(self._L.amcl3d_b200_pf_set_cloud(self._h, cloud.ctypes.data if npts else None, cloud.shape[1] if cloud.ndim == 2 else 3, npts))
+
+    def set_cloud_device(self, ptr: int, stride: int, npts: int):
+        check(self._L.amcl3d_b200_pf_set_cloud_device(self._h, C.c_void_p(ptr), stride, npts))
+
+    def update(self, cloud=None, beacons=None, alpha=1.0, sigma=1.0, count=False):
+        """ParticleFilter::update(cloud) (ParticleFilter.cpp:114-139).  cloud=None reuses the resident one."""
+        if cloud is not None:
+            self.set_cloud(cloud)
+        nb = 0
+        arr = None
+        if beacons is not None:
+            pos, rng = beacons
+            nb = len(rng)
+            arr = (capi.Beacon * nb)()
+            for k in range(nb):
+                for a in range(3):
+                    arr[k].position[a] = float(pos[k][a])
+                arr[k].range = float(rng[k])
+        c = C.c_uint64(0)
+        check(self._L.amcl3d_b200_pf_update(self._h, arr, nb, float(alpha), float(sigma), C.byref(c) if count else None))
+        return int(c.value) if count else None
+
+    def particleNormalize(self) -> np.float32:
+        wtp = C.c_float(0)
+        check(self._L.amcl3d_b200_pf_normalize(self._h, C.byref(wtp)))
+        return np.float32(wtp.value)
+
+    def addParticleWeight(self):
+        check(self._L.amcl3d_b200_pf_scale_by_max(self._h))
+
+    def resample(self, u01, m0=0, m1=0, d_out=0, want_idx=False):
+        """ParticleFilter::resample (ParticleFilter.cpp:230-254) with r = u01 / N."""
+        n = self.size()
+        cnt = (m1 or n) - m0
+        idx = np.empty(cnt, np.int32) if want_idx else None
+        check(self._L.amcl3d_b200_pf_resample(self._h, float(np.float32(u01)), m0, m1, C.c_void_p(d_out or 0), idx.ctypes.data if want_idx else None))
+        return idx
+
+    def uniformSample(self, sample_num, k0=0, k1=0, d_out=0, want_idx=False):
+        """ParticleFilter::uniformSample (ParticleFilter.cpp:256-280).  Returns (idx | None, emitted)."""
+        cnt = (k1 or sample_num) - k0
+        idx = np.empty(cnt, np.int32) if want_idx else None
+        em = C.c_int(0)
+        check(self._L.amcl3d_b200_pf_uniform_sample(self._h, int(sample_num), k0, k1, C.c_void_p(d_out or 0), idx.ctypes.data if want_idx else None, C.byref(em)))
+        return idx, em.value
+
+    def getMean(self, exact=False) -> np.ndarray:
+        out = np.zeros(7, np.float32)
+        check(self._L.amcl3d_b200_pf_mean(self._h, int(exact), out.ctypes.data))
+        return out
+
+    def getBestParticle(self) -> np.ndarray:
+        out = np.zeros(7, np.float32)
+        check(self._L.amcl3d_b200_pf_best(self._h, out.ctypes.data))
+        return out
+
+    def predict(self, delta6, noise6):
+        d = np.ascontiguousarray(delta6, np.float64)
+        nz = _f32(noise6)
+        check(self._L.amcl3d_b200_pf_predict(self._h, d.ctypes.data_as(C.POINTER(C.c_double)), nz.ctypes.data))
+
+    def prefix(self) -> np.ndarray:
+        n = self.size()
+        out = np.empty(n, np.float32)
+        check(self._L.amcl3d_b200_pf_prefix(self._h, None, out.ctypes.data, n))
+        return out
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        check(self._L.amcl3d_b200_pf_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = C.c_uint64(0)
+        check(self._L.amcl3d_b200_pf_launch_count(self._h, C.byref(n)))
+        return int(n.value)

@@ -1,0 +1,1132 @@
+// capi.cu -- the C-ABI (include/amcl3d_b200.h): opaque handles that own device memory and launch the
+// sm_100a kernels of update.cu / pfops.cu / gridbuild.cu.  No CPU fallback: without a usable CUDA
+// device every compute entry point returns AMCL3D_B200_ERR_CUDA.
+#include "common.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace a3d;
+
+namespace
+{
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+  g_err = msg;
+  return code;
+}
+int fail_cuda(cudaError_t e, const char* where)
+{
+  g_err = std::string(where) + ": " + cudaGetErrorString(e);
+  (void)cudaGetLastError();
+  return AMCL3D_B200_ERR_CUDA;
+}
+#define CU(expr)                         \
+  do                                     \
+  {                                      \
+    cudaError_t e__ = (expr);            \
+    if (e__ != cudaSuccess)              \
+      return fail_cuda(e__, #expr);      \
+  } while (0)
+
+template <typename T>
+cudaError_t ensure(T*& ptr, uint64_t& cap, uint64_t need)
+{
+  if (need <= cap && ptr != nullptr)
+    return cudaSuccess;
+  if (ptr)
+    cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+  const uint64_t want = std::max<uint64_t>(need, 1);
+  cudaError_t e = cudaMalloc(&ptr, sizeof(T) * want);
+  if (e == cudaSuccess)
+    cap = want;
+  return e;
+}
+// particle buffers: capacity counted in particles, 7 floats each
+cudaError_t ensure_particles(float*& ptr, uint64_t& cap, uint64_t need)
+{
+  if (need <= cap && ptr != nullptr)
+    return cudaSuccess;
+  if (ptr)
+    cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+  const uint64_t want = std::max<uint64_t>(need, 1);
+  cudaError_t e = cudaMalloc(&ptr, sizeof(float) * 7 * want);
+  if (e == cudaSuccess)
+    cap = want;
+  return e;
+}
+}  // namespace
+
+struct amcl3d_b200_grid_s
+{
+  int device = 0;
+  MapDev map{};
+  double sensor_dev = 0;
+  float* d_prob = nullptr;
+  uint64_t prob_cap = 0;
+  int32_t* d_edt = nullptr;
+  uint64_t edt_cells = 0;
+  cudaStream_t stream = nullptr;
+  amcl3d_b200_pf_t scratch_pf = nullptr;  // for the single-pose computeCloudWeight
+};
+
+struct amcl3d_b200_pf_s
+{
+  amcl3d_b200_grid_t grid = nullptr;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  int trig_mode = AMCL3D_B200_TRIG_F64;
+  // p_
+  float* d_p = nullptr;
+  uint64_t n = 0, cap = 0;
+  bool external = false;
+  float* d_alt = nullptr;
+  uint64_t alt_cap = 0;
+  // cloud
+  float4* d_cloud = nullptr;
+  uint64_t cloud_cap = 0;
+  uint32_t npts = 0, npad = 0;
+  float* d_stage = nullptr;
+  uint64_t stage_cap = 0;
+  // scratch
+  float* d_prefix = nullptr;
+  uint64_t prefix_cap = 0;
+  float* d_thr = nullptr;
+  uint64_t thr_cap = 0;
+  float* d_wr = nullptr;
+  uint64_t wr_cap = 0;
+  int32_t* d_idx = nullptr;
+  uint64_t idx_cap = 0;
+  float* d_noise = nullptr;
+  uint64_t noise_cap = 0;
+  float* d_scalars = nullptr;  // [0] total [1] total_r [2] max [8..14] out7
+  unsigned long long* d_u64 = nullptr;  // [0] counter [1] argmax
+  int* d_int = nullptr;
+  double* d_delta = nullptr;
+  BeaconSet* d_beacons = nullptr;
+  void* d_scratch = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  uint64_t launches = 0;
+};
+
+namespace
+{
+void refresh_map(amcl3d_b200_grid_t g)
+{
+  MapDev& m = g->map;
+  m.rinv = 1.0 / m.resol;
+  m.rinv_f = (float)(1.0 / m.resol);
+  for (int a = 0; a < 3; ++a)
+  {
+    const double S = m.max[a] - m.min[a];  // Grid3d.cpp:252-254
+    float f = (float)S;
+    if ((double)f < S)
+      f = nextafterf(f, INFINITY);
+    m.size_up[a] = f;
+    // |fl32(v*rinv_f) - v/resol| <= (v/resol) * 2^-23 (1 + 2^-24); v/resol < size + 1
+    float eps = ((float)m.size[a] + 2.f) * 1.25e-7f + 2e-7f;
+    if (!(eps < 0.5f))
+      eps = 0.5f;
+    m.eps[a] = eps;
+  }
+  m.step_z = (uint64_t)m.size[0] * (uint64_t)m.size[1];
+  m.n_cells = (uint64_t)m.size[0] * (uint64_t)m.size[1] * (uint64_t)m.size[2];
+  m.prob = g->d_prob;
+}
+
+// PointCloudTools.cpp:120-125
+void size_from_bounds(amcl3d_b200_grid_t g)
+{
+  MapDev& m = g->map;
+  for (int a = 0; a < 3; ++a)
+    m.size[a] = static_cast<uint32_t>(ceil((m.max[a] - m.min[a]) / m.resol));
+}
+
+int use_device(int device)
+{
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess)
+    return fail_cuda(e, "cudaSetDevice");
+  return AMCL3D_B200_OK;
+}
+
+struct Timed
+{
+  amcl3d_b200_pf_t pf;
+  explicit Timed(amcl3d_b200_pf_t p) : pf(p)
+  {
+    cudaEventRecord(pf->ev0, pf->stream);
+  }
+  ~Timed()
+  {
+    cudaEventRecord(pf->ev1, pf->stream);
+    pf->timed = true;
+  }
+};
+}  // namespace
+
+extern "C" {
+
+int amcl3d_b200_abi_version(void)
+{
+  return AMCL3D_B200_ABI_VERSION;
+}
+
+const char* amcl3d_b200_last_error(void)
+{
+  return g_err.c_str();
+}
+
+int amcl3d_b200_device_info(int device, int* device_count, int* sm_count, int* cc_major, int* cc_minor,
+                            uint64_t* l2_bytes, uint64_t* mem_bytes)
+{
+  int cnt = 0;
+  CU(cudaGetDeviceCount(&cnt));
+  if (device_count)
+    *device_count = cnt;
+  if (device < 0 || device >= cnt)
+    return fail(AMCL3D_B200_ERR_ARG, "device index out of range");
+  cudaDeviceProp p;
+  CU(cudaGetDeviceProperties(&p, device));
+  if (sm_count)
+    *sm_count = p.multiProcessorCount;
+  if (cc_major)
+    *cc_major = p.major;
+  if (cc_minor)
+    *cc_minor = p.minor;
+  if (l2_bytes)
+    *l2_bytes = (uint64_t)p.l2CacheSize;
+  if (mem_bytes)
+    *mem_bytes = (uint64_t)p.totalGlobalMem;
+  return AMCL3D_B200_OK;
+}
+
+/* ============================================ Grid3d ============================================ */
+
+int amcl3d_b200_grid_create(int device, amcl3d_b200_grid_t* out)
+{
+  if (!out)
+    return fail(AMCL3D_B200_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  int cnt = 0;
+  CU(cudaGetDeviceCount(&cnt));
+  if (device < 0 || device >= cnt)
+    return fail(AMCL3D_B200_ERR_ARG, "device index out of range");
+  if (int rc = use_device(device))
+    return rc;
+  amcl3d_b200_grid_t g = new (std::nothrow) amcl3d_b200_grid_s();
+  if (!g)
+    return fail(AMCL3D_B200_ERR_ARG, "out of host memory");
+  g->device = device;
+  cudaError_t e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess)
+  {
+    delete g;
+    return fail_cuda(e, "cudaStreamCreate");
+  }
+  *out = g;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_grid_destroy(amcl3d_b200_grid_t g)
+{
+  if (!g)
+    return AMCL3D_B200_OK;
+  cudaSetDevice(g->device);
+  if (g->scratch_pf)
+    amcl3d_b200_pf_destroy(g->scratch_pf);
+  cudaFree(g->d_prob);
+  cudaFree(g->d_edt);
+  if (g->stream)
+    cudaStreamDestroy(g->stream);
+  delete g;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_grid_get_info(amcl3d_b200_grid_t g, amcl3d_b200_grid_info_t* info)
+{
+  if (!g || !info)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  for (int a = 0; a < 3; ++a)
+  {
+    info->min[a] = g->map.min[a];
+    info->max[a] = g->map.max[a];
+    info->size[a] = g->map.size[a];
+  }
+  info->resol = g->map.resol;
+  info->sensor_dev = g->sensor_dev;
+  info->n_cells = g->map.n_cells;
+  info->has_map = g->map.has_map;
+  info->has_grid = g->map.has_grid;
+  info->device = g->device;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_grid_set_map(amcl3d_b200_grid_t g, const double mn[3], const double mx[3], double resol)
+{
+  if (!g || !mn || !mx || !(resol > 0))
+    return fail(AMCL3D_B200_ERR_ARG, "bad map bounds / resolution");
+  for (int a = 0; a < 3; ++a)
+  {
+    g->map.min[a] = mn[a];
+    g->map.max[a] = mx[a];
+  }
+  g->map.resol = resol;
+  g->map.has_map = 1;
+  if (!g->map.has_grid)
+    size_from_bounds(g);
+  refresh_map(g);
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_grid_compute_bounds(amcl3d_b200_grid_t g, const float* xyz, uint32_t stride, uint64_t n, double resol,
+                                    double mn[3], double mx[3])
+{
+  if (!g || !xyz || stride < 3 || !(resol > 0))
+    return fail(AMCL3D_B200_ERR_ARG, "bad cloud");
+  if (n <= 1)
+    return fail(AMCL3D_B200_ERR_EMPTY, "OcTree is empty");  // PointCloudTools.cpp:89-91
+  if (int rc = use_device(g->device))
+    return rc;
+  float* d_xyz = nullptr;
+  float* d_keys = nullptr;
+  CU(cudaMalloc(&d_xyz, sizeof(float) * n * stride));
+  cudaError_t e = cudaMalloc(&d_keys, 6 * sizeof(float));
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(d_xyz, xyz, sizeof(float) * n * stride, cudaMemcpyHostToDevice, g->stream);
+  if (e == cudaSuccess)
+    e = launch_bounds(d_xyz, stride, n, d_keys, g->stream);
+  uint32_t keys[6];
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(keys, d_keys, sizeof(keys), cudaMemcpyDeviceToHost, g->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(g->stream);
+  cudaFree(d_xyz);
+  cudaFree(d_keys);
+  if (e != cudaSuccess)
+    return fail_cuda(e, "bounds reduction");
+  double lo[3], hi[3];
+  for (int a = 0; a < 6; ++a)
+  {
+    const uint32_t k = keys[a];
+    const uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    float f;
+    memcpy(&f, &b, 4);
+    if (a < 3)
+      lo[a] = f;
+    else
+      hi[a - 3] = f;
+  }
+  g->map.has_grid = 0;
+  int rc = amcl3d_b200_grid_set_map(g, lo, hi, resol);
+  if (rc)
+    return rc;
+  for (int a = 0; a < 3; ++a)
+  {
+    if (mn)
+      mn[a] = lo[a];
+    if (mx)
+      mx[a] = hi[a];
+  }
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_grid_upload(amcl3d_b200_grid_t g, const float* prob, const uint32_t size[3], double sensor_dev)
+{
+  if (!g || !prob || !size)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  if (int rc = use_device(g->device))
+    return rc;
+  const uint64_t cells = (uint64_t)size[0] * size[1] * size[2];
+  CU(ensure(g->d_prob, g->prob_cap, cells));
+  CU(cudaMemcpyAsync(g->d_prob, prob, sizeof(float) * cells, cudaMemcpyHostToDevice, g->stream));
+  CU(cudaStreamSynchronize(g->stream));
+  for (int a = 0; a < 3; ++a)
+    g->map.size[a] = size[a];
+  g->sensor_dev = sensor_dev;
+  g->map.has_grid = 1;
+  refresh_map(g);
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_grid_download(amcl3d_b200_grid_t g, float* prob, uint64_t cap)
+{
+  if (!g || !prob)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  if (!g->map.has_grid)
+    return fail(AMCL3D_B200_ERR_STATE, "no grid");
+  if (cap < g->map.n_cells)
+    return fail(AMCL3D_B200_ERR_ARG, "output too small");
+  if (int rc = use_device(g->device))
+    return rc;
+  CU(cudaMemcpy(prob, g->d_prob, sizeof(float) * g->map.n_cells, cudaMemcpyDeviceToHost));
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_grid_device_ptr(amcl3d_b200_grid_t g, void** d_prob)
+{
+  if (!g || !d_prob)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  *d_prob = g->d_prob;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_grid_build(amcl3d_b200_grid_t g, const float* xyz, uint32_t stride, uint64_t n, double sensor_dev,
+                           int mode, int sub, int keep_edt)
+{
+  if (!g || !xyz || stride < 3)
+    return fail(AMCL3D_B200_ERR_ARG, "bad cloud");
+  if (!g->map.has_map)
+    return fail(AMCL3D_B200_ERR_STATE, "PointCloudInfo is NULL");  // PointCloudTools.cpp:113-114
+  if (mode != AMCL3D_B200_GRID_QUIRK && mode != AMCL3D_B200_GRID_GAUSSIAN && mode != AMCL3D_B200_GRID_SPLAT)
+    return fail(AMCL3D_B200_ERR_ARG, "unknown grid mode");
+  if (mode != AMCL3D_B200_GRID_SPLAT && sub != 1 && sub != 2)
+    return fail(AMCL3D_B200_ERR_ARG, "sub must be 1 or 2");
+  if (int rc = use_device(g->device))
+    return rc;
+  g->map.has_grid = 0;
+  size_from_bounds(g);
+  refresh_map(g);
+  const uint64_t cells = g->map.n_cells;
+  if (mode == AMCL3D_B200_GRID_SPLAT && cells >= (1ull << 32))
+    return fail(AMCL3D_B200_ERR_ARG, "computeGrid2 indexes cells with uint32_t");
+  CU(ensure(g->d_prob, g->prob_cap, cells));
+  refresh_map(g);
+  cudaFree(g->d_edt);
+  g->d_edt = nullptr;
+  g->edt_cells = 0;
+
+  float* d_xyz = nullptr;
+  CU(cudaMalloc(&d_xyz, sizeof(float) * std::max<uint64_t>(n, 1) * stride));
+  cudaError_t e = cudaMemcpyAsync(d_xyz, xyz, sizeof(float) * n * stride, cudaMemcpyHostToDevice, g->stream);
+  char msg[256] = { 0 };
+  if (e == cudaSuccess)
+  {
+    if (mode == AMCL3D_B200_GRID_SPLAT)
+      e = build_grid_splat(g->map, d_xyz, stride, n, sensor_dev, g->d_prob, g->stream);
+    else
+      e = build_grid_edt(g->map, d_xyz, stride, n, sensor_dev, mode, sub, g->d_prob, keep_edt ? &g->d_edt : nullptr,
+                         g->stream, msg, sizeof(msg));
+  }
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(g->stream);
+  cudaFree(d_xyz);
+  if (e != cudaSuccess)
+  {
+    if (msg[0])
+    {
+      (void)cudaGetLastError();
+      return fail(e == cudaErrorInvalidValue ? AMCL3D_B200_ERR_ARG : AMCL3D_B200_ERR_CUDA, msg);
+    }
+    return fail_cuda(e, "grid build");
+  }
+  if (g->d_edt)
+    g->edt_cells = cells;
+  g->sensor_dev = sensor_dev;
+  g->map.has_grid = 1;
+  refresh_map(g);
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_grid_download_edt(amcl3d_b200_grid_t g, int32_t* d2, uint64_t cap)
+{
+  if (!g || !d2)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  if (!g->d_edt)
+    return fail(AMCL3D_B200_ERR_STATE, "no distance transform kept (keep_edt = 0?)");
+  if (cap < g->edt_cells)
+    return fail(AMCL3D_B200_ERR_ARG, "output too small");
+  if (int rc = use_device(g->device))
+    return rc;
+  CU(cudaMemcpy(d2, g->d_edt, sizeof(int32_t) * g->edt_cells, cudaMemcpyDeviceToHost));
+  return AMCL3D_B200_OK;
+}
+
+// Grid3d.cpp:374-402
+int amcl3d_b200_grid_save_file(amcl3d_b200_grid_t g, const char* path)
+{
+  if (!g || !path)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  if (!g->map.has_grid)
+    return fail(AMCL3D_B200_ERR_STATE, "no grid");  // Grid3d.cpp:376-377
+  if (g->map.n_cells >= (1ull << 32))
+    return fail(AMCL3D_B200_ERR_ARG, "the .grid header stores u32 sizes whose product must fit u32");
+  std::vector<float> host(g->map.n_cells);
+  int rc = amcl3d_b200_grid_download(g, host.data(), host.size());
+  if (rc)
+    return rc;
+  FILE* pf = fopen(path, "wb");
+  if (!pf)
+    return fail(AMCL3D_B200_ERR_IO, std::string("Error opening file ") + path + " for writing");
+  bool ok = fwrite(&g->map.size[0], sizeof(uint32_t), 1, pf) == 1 && fwrite(&g->map.size[1], sizeof(uint32_t), 1, pf) == 1 &&
+            fwrite(&g->map.size[2], sizeof(uint32_t), 1, pf) == 1 && fwrite(&g->sensor_dev, sizeof(double), 1, pf) == 1;
+  ok = ok && fwrite(host.data(), sizeof(float), host.size(), pf) == host.size();
+  fclose(pf);
+  if (!ok)
+    return fail(AMCL3D_B200_ERR_IO, "short write");
+  return AMCL3D_B200_OK;
+}
+
+// Grid3d.cpp:404-442
+int amcl3d_b200_grid_load_file(amcl3d_b200_grid_t g, const char* path, double sensor_dev)
+{
+  if (!g || !path)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  FILE* pf = fopen(path, "rb");
+  if (!pf)
+    return fail(AMCL3D_B200_ERR_IO, std::string("Error opening file ") + path + " for reading");
+  uint32_t size[3];
+  double dev = 0;
+  if (fread(&size[0], sizeof(uint32_t), 1, pf) != 1 || fread(&size[1], sizeof(uint32_t), 1, pf) != 1 ||
+      fread(&size[2], sizeof(uint32_t), 1, pf) != 1 || fread(&dev, sizeof(double), 1, pf) != 1)
+  {
+    fclose(pf);
+    return fail(AMCL3D_B200_ERR_IO, "short header");
+  }
+  if (fabs(dev - sensor_dev) >= 2.220446049250313e-16)  // Grid3d.cpp:422
+  {
+    fclose(pf);
+    return fail(AMCL3D_B200_ERR_MISMATCH, "Loaded sensorDev is different");
+  }
+  const uint64_t cells = (uint64_t)size[0] * size[1] * size[2];
+  std::vector<float> host;
+  try
+  {
+    host.resize(cells);
+  }
+  catch (...)
+  {
+    fclose(pf);
+    return fail(AMCL3D_B200_ERR_IO, "grid too large for host staging");
+  }
+  const size_t got = fread(host.data(), sizeof(float), cells, pf);
+  fclose(pf);
+  if (got != cells)
+    return fail(AMCL3D_B200_ERR_IO, "short read");
+  return amcl3d_b200_grid_upload(g, host.data(), size, dev);
+}
+
+// Grid3d.cpp:365-372
+int amcl3d_b200_grid_is_into_map(amcl3d_b200_grid_t g, float x, float y, float z, int* inside)
+{
+  if (!g || !inside)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  const MapDev& m = g->map;
+  *inside = (m.has_map && x >= m.min[0] && x < m.max[0] && y >= m.min[1] && y < m.max[1] && z >= m.min[2] && z < m.max[2])
+                ? 1
+                : 0;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_grid_cloud_weight(amcl3d_b200_grid_t g, const float* cloud, uint32_t stride, uint32_t npts, float tx,
+                                  float ty, float tz, float roll, float pitch, float yaw, int trig_mode, float* weight)
+{
+  if (!g || !weight || (npts && !cloud) || stride < 3)
+    return fail(AMCL3D_B200_ERR_ARG, "bad argument");
+  *weight = 0.f;
+  if (!g->map.has_grid || !g->map.has_map)
+    return AMCL3D_B200_OK;  // Grid3d.cpp:237-238 returns 0
+  if (!g->scratch_pf)
+  {
+    int rc = amcl3d_b200_pf_create(g, &g->scratch_pf);
+    if (rc)
+      return rc;
+  }
+  amcl3d_b200_pf_t pf = g->scratch_pf;
+  pf->trig_mode = trig_mode;
+  // computeCloudWeight itself has no isIntoMap gate: evaluate the pose even when it lies outside the map
+  // by running the kernel on a map copy whose particle gate is opened (bounds for points are unchanged)
+  const float p7[7] = { tx, ty, tz, roll, pitch, yaw, 0.f };
+  int rc = amcl3d_b200_pf_set_particles(pf, p7, 1);
+  if (!rc)
+    rc = amcl3d_b200_pf_set_cloud(pf, cloud, stride, npts);
+  if (rc)
+    return rc;
+  if (int rc2 = use_device(g->device))
+    return rc2;
+  MapDev open = g->map;
+  // the per-particle gate compares (double)p >= min && < max; widen it without touching the offsets
+  // (offsets use map.min, so pass the true min through and lift only the gate via has_map semantics):
+  // the kernel gates on min/max, so use a dedicated flag value 2 = "do not gate"
+  open.has_map = 2;
+  CU(launch_update(open, pf->d_p, 1, pf->d_cloud, pf->npts, pf->npad, pf->d_beacons, nullptr, trig_mode, nullptr,
+                   pf->stream));
+  pf->launches++;
+  float out7[7];
+  CU(cudaMemcpyAsync(out7, pf->d_p, sizeof(out7), cudaMemcpyDeviceToHost, pf->stream));
+  CU(cudaStreamSynchronize(pf->stream));
+  *weight = out7[6];
+  return AMCL3D_B200_OK;
+}
+
+/* ========================================= ParticleFilter ======================================= */
+
+int amcl3d_b200_pf_create(amcl3d_b200_grid_t g, amcl3d_b200_pf_t* out)
+{
+  if (!g || !out)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  if (int rc = use_device(g->device))
+    return rc;
+  amcl3d_b200_pf_t pf = new (std::nothrow) amcl3d_b200_pf_s();
+  if (!pf)
+    return fail(AMCL3D_B200_ERR_ARG, "out of host memory");
+  pf->grid = g;
+  cudaError_t e = cudaStreamCreateWithFlags(&pf->own_stream, cudaStreamNonBlocking);
+  pf->stream = pf->own_stream;
+  if (e == cudaSuccess)
+    e = cudaEventCreate(&pf->ev0);
+  if (e == cudaSuccess)
+    e = cudaEventCreate(&pf->ev1);
+  if (e == cudaSuccess)
+    e = cudaMalloc(&pf->d_scalars, 64 * sizeof(float));
+  if (e == cudaSuccess)
+    e = cudaMalloc(&pf->d_u64, 8 * sizeof(unsigned long long));
+  if (e == cudaSuccess)
+    e = cudaMalloc(&pf->d_int, 8 * sizeof(int));
+  if (e == cudaSuccess)
+    e = cudaMalloc(&pf->d_delta, 8 * sizeof(double));
+  if (e == cudaSuccess)
+    e = cudaMalloc(&pf->d_beacons, sizeof(BeaconSet));
+  if (e == cudaSuccess)
+    e = cudaMemset(pf->d_beacons, 0, sizeof(BeaconSet));
+  if (e == cudaSuccess)
+    e = cudaMalloc(&pf->d_scratch, reduce_scratch_bytes());
+  if (e != cudaSuccess)
+  {
+    amcl3d_b200_pf_destroy(pf);
+    return fail_cuda(e, "pf_create");
+  }
+  *out = pf;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_destroy(amcl3d_b200_pf_t pf)
+{
+  if (!pf)
+    return AMCL3D_B200_OK;
+  cudaSetDevice(pf->grid->device);
+  if (!pf->external)
+    cudaFree(pf->d_p);
+  cudaFree(pf->d_alt);
+  cudaFree(pf->d_cloud);
+  cudaFree(pf->d_stage);
+  cudaFree(pf->d_prefix);
+  cudaFree(pf->d_thr);
+  cudaFree(pf->d_wr);
+  cudaFree(pf->d_idx);
+  cudaFree(pf->d_noise);
+  cudaFree(pf->d_scalars);
+  cudaFree(pf->d_u64);
+  cudaFree(pf->d_int);
+  cudaFree(pf->d_delta);
+  cudaFree(pf->d_beacons);
+  cudaFree(pf->d_scratch);
+  if (pf->ev0)
+    cudaEventDestroy(pf->ev0);
+  if (pf->ev1)
+    cudaEventDestroy(pf->ev1);
+  if (pf->own_stream)
+    cudaStreamDestroy(pf->own_stream);
+  delete pf;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_set_trig_mode(amcl3d_b200_pf_t pf, int trig_mode)
+{
+  if (!pf || (trig_mode != AMCL3D_B200_TRIG_F64 && trig_mode != AMCL3D_B200_TRIG_F32))
+    return fail(AMCL3D_B200_ERR_ARG, "bad trig mode");
+  pf->trig_mode = trig_mode;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_set_stream(amcl3d_b200_pf_t pf, void* cuda_stream)
+{
+  if (!pf)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+  pf->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : pf->own_stream;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_set_particles(amcl3d_b200_pf_t pf, const float* aos7, uint64_t n)
+{
+  if (!pf || (n && !aos7))
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  if (n >= (1ull << 31))
+    return fail(AMCL3D_B200_ERR_ARG, "too many particles");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  if (pf->external)
+  {
+    if (n > pf->cap)
+      return fail(AMCL3D_B200_ERR_ARG, "bound device buffer too small");
+  }
+  else
+    CU(ensure_particles(pf->d_p, pf->cap, n));
+  if (n)
+    CU(cudaMemcpyAsync(pf->d_p, aos7, sizeof(float) * 7 * n, cudaMemcpyHostToDevice, pf->stream));
+  CU(cudaStreamSynchronize(pf->stream));
+  pf->n = n;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_get_particles(amcl3d_b200_pf_t pf, float* aos7, uint64_t cap, uint64_t* n)
+{
+  if (!pf || (!aos7 && cap))
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  if (n)
+    *n = pf->n;
+  if (cap < pf->n)
+    return fail(AMCL3D_B200_ERR_ARG, "output too small");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  if (pf->n)
+    CU(cudaMemcpyAsync(aos7, pf->d_p, sizeof(float) * 7 * pf->n, cudaMemcpyDeviceToHost, pf->stream));
+  CU(cudaStreamSynchronize(pf->stream));
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_size(amcl3d_b200_pf_t pf, uint64_t* n)
+{
+  if (!pf || !n)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  *n = pf->n;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_bind_device(amcl3d_b200_pf_t pf, void* d_aos7, uint64_t n, uint64_t capacity)
+{
+  if (!pf || !d_aos7 || n > capacity || capacity >= (1ull << 31))
+    return fail(AMCL3D_B200_ERR_ARG, "bad device buffer");
+  if (!pf->external)
+    cudaFree(pf->d_p);
+  pf->d_p = reinterpret_cast<float*>(d_aos7);
+  pf->n = n;
+  pf->cap = capacity;
+  pf->external = true;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_device_ptr(amcl3d_b200_pf_t pf, void** d_aos7, uint64_t* n)
+{
+  if (!pf || !d_aos7)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  *d_aos7 = pf->d_p;
+  if (n)
+    *n = pf->n;
+  return AMCL3D_B200_OK;
+}
+
+static int set_cloud_common(amcl3d_b200_pf_t pf, const float* d_src, uint32_t stride, uint32_t npts)
+{
+  const uint32_t npad = (npts + 31u) & ~31u;
+  CU(ensure(pf->d_cloud, pf->cloud_cap, npad));
+  CU(launch_pack_cloud(d_src, stride, npts, pf->d_cloud, npad, pf->stream));
+  pf->launches += npad ? 1 : 0;
+  pf->npts = npts;
+  pf->npad = npad;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_set_cloud(amcl3d_b200_pf_t pf, const float* cloud, uint32_t stride, uint32_t npts)
+{
+  if (!pf || (npts && !cloud) || stride < 3)
+    return fail(AMCL3D_B200_ERR_ARG, "bad cloud");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  const uint64_t floats = (uint64_t)npts * stride;
+  CU(ensure(pf->d_stage, pf->stage_cap, floats));
+  if (floats)
+    CU(cudaMemcpyAsync(pf->d_stage, cloud, sizeof(float) * floats, cudaMemcpyHostToDevice, pf->stream));
+  int rc = set_cloud_common(pf, pf->d_stage, stride, npts);
+  if (rc)
+    return rc;
+  CU(cudaStreamSynchronize(pf->stream));  // the host buffer may be reused by the caller
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_set_cloud_device(amcl3d_b200_pf_t pf, const void* d_cloud, uint32_t stride, uint32_t npts)
+{
+  if (!pf || (npts && !d_cloud) || stride < 3)
+    return fail(AMCL3D_B200_ERR_ARG, "bad cloud");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  return set_cloud_common(pf, reinterpret_cast<const float*>(d_cloud), stride, npts);
+}
+
+int amcl3d_b200_pf_update(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beacons, uint32_t nb, float alpha, float sigma,
+                          uint64_t* in_bounds)
+{
+  if (!pf || (nb && !beacons) || nb > (uint32_t)kMaxBeacons)
+    return fail(AMCL3D_B200_ERR_ARG, "bad beacons");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  const MapDev& map = pf->grid->map;
+  float* d_wr = nullptr;
+  if (nb)
+  {
+    BeaconSet bs{};
+    bs.n = nb;
+    bs.k1 = 1.f / (sigma * sqrt(2 * M_PI));
+    bs.k2 = 0.5f / (sigma * sigma);
+    for (uint32_t b = 0; b < nb; ++b)
+    {
+      bs.ax[b] = (float)beacons[b].position[0];
+      bs.ay[b] = (float)beacons[b].position[1];
+      bs.az[b] = (float)beacons[b].position[2];
+      bs.r[b] = (float)beacons[b].range;
+    }
+    CU(cudaMemcpyAsync(pf->d_beacons, &bs, sizeof(bs), cudaMemcpyHostToDevice, pf->stream));
+    CU(cudaStreamSynchronize(pf->stream));  // bs lives on this stack frame
+    CU(ensure(pf->d_wr, pf->wr_cap, pf->n));
+    d_wr = pf->d_wr;
+  }
+  unsigned long long* d_counter = nullptr;
+  if (in_bounds)
+  {
+    d_counter = pf->d_u64;
+    CU(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), pf->stream));
+  }
+  {
+    Timed t(pf);
+    CU(launch_update(map, pf->d_p, (uint32_t)pf->n, pf->d_cloud, pf->npts, pf->npad, pf->d_beacons, d_wr, pf->trig_mode,
+                     d_counter, pf->stream));
+    pf->launches += pf->n ? 1 : 0;
+    if (nb && pf->n)
+    {
+      // w = alpha*wp/sum(wp) + (1-alpha)*wr/sum(wr): both sums as sequential f32 chains
+      CU(launch_chain_prefix(pf->d_p, pf->n, 0, nullptr, pf->d_scalars + 0, pf->stream));
+      CU(launch_chain_sum_array(pf->d_wr, pf->n, pf->d_scalars + 1, pf->stream));
+      CU(launch_fuse_range(pf->d_p, pf->d_wr, pf->n, pf->d_scalars + 0, pf->d_scalars + 1, alpha, pf->stream));
+      pf->launches += 3;
+    }
+  }
+  if (in_bounds)
+  {
+    unsigned long long c = 0;
+    CU(cudaMemcpyAsync(&c, d_counter, sizeof(c), cudaMemcpyDeviceToHost, pf->stream));
+    CU(cudaStreamSynchronize(pf->stream));
+    *in_bounds = c;
+  }
+  else
+    CU(cudaStreamSynchronize(pf->stream));
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_update_cloud(amcl3d_b200_pf_t pf, const float* cloud, uint32_t stride, uint32_t npts)
+{
+  int rc = amcl3d_b200_pf_set_cloud(pf, cloud, stride, npts);
+  if (rc)
+    return rc;
+  return amcl3d_b200_pf_update(pf, nullptr, 0, 1.f, 1.f, nullptr);
+}
+
+static int normalize_async(amcl3d_b200_pf_t pf)
+{
+  CU(launch_chain_prefix(pf->d_p, pf->n, 1, nullptr, pf->d_scalars + 0, pf->stream));
+  CU(launch_normalize(pf->grid->map, pf->d_p, pf->n, pf->d_scalars + 0, pf->stream));
+  pf->launches += pf->n ? 2 : 1;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_normalize(amcl3d_b200_pf_t pf, float* wtp)
+{
+  if (!pf)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  {
+    Timed t(pf);
+    if (int rc = normalize_async(pf))
+      return rc;
+  }
+  float total = 0;
+  CU(cudaMemcpyAsync(&total, pf->d_scalars, sizeof(float), cudaMemcpyDeviceToHost, pf->stream));
+  CU(cudaStreamSynchronize(pf->stream));
+  if (wtp)
+    *wtp = total;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_scale_by_max(amcl3d_b200_pf_t pf)
+{
+  if (!pf)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  {
+    Timed t(pf);
+    CU(launch_max_weight(pf->d_p, pf->n, pf->d_scalars + 2, pf->d_u64 + 1, pf->d_scratch, pf->stream));
+    CU(launch_scale_by_max(pf->d_p, pf->n, pf->d_scalars + 2, pf->stream));
+    pf->launches += 3;
+  }
+  CU(cudaStreamSynchronize(pf->stream));
+  return AMCL3D_B200_OK;
+}
+
+// replaces p_ by the first `count` particles of d_alt
+static int adopt_alt(amcl3d_b200_pf_t pf, uint64_t count)
+{
+  if (pf->external)
+  {
+    if (count > pf->cap)
+      return fail(AMCL3D_B200_ERR_ARG, "bound device buffer too small for the resampled set");
+    if (count)
+      CU(cudaMemcpyAsync(pf->d_p, pf->d_alt, sizeof(float) * 7 * count, cudaMemcpyDeviceToDevice, pf->stream));
+  }
+  else
+  {
+    std::swap(pf->d_p, pf->d_alt);
+    std::swap(pf->cap, pf->alt_cap);
+  }
+  pf->n = count;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_resample(amcl3d_b200_pf_t pf, float u01, uint64_t m0, uint64_t m1, void* d_out, int32_t* idx)
+{
+  if (!pf)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+  const uint64_t n = pf->n;
+  if (m1 == 0)
+    m1 = n;
+  if (m0 > m1 || m1 > n)
+    return fail(AMCL3D_B200_ERR_ARG, "bad output range");
+  if (!d_out && (m0 != 0 || m1 != n))
+    return fail(AMCL3D_B200_ERR_ARG, "replacing p_ needs the full output range");
+  if (n == 0)
+    return AMCL3D_B200_OK;
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  const uint64_t cnt = m1 - m0;
+  CU(ensure(pf->d_prefix, pf->prefix_cap, n));
+  float* out = reinterpret_cast<float*>(d_out);
+  if (!out)
+  {
+    CU(ensure_particles(pf->d_alt, pf->alt_cap, n));
+    out = pf->d_alt;
+  }
+  int32_t* d_idx = nullptr;
+  if (idx)
+  {
+    CU(ensure(pf->d_idx, pf->idx_cap, cnt));
+    d_idx = pf->d_idx;
+  }
+  {
+    Timed t(pf);
+    CU(launch_chain_prefix(pf->d_p, n, 0, pf->d_prefix, nullptr, pf->stream));
+    CU(launch_resample_search(pf->d_p, pf->d_prefix, n, u01, m0, m1, out, d_idx, pf->stream));
+    pf->launches += 2;
+  }
+  if (!d_out)
+    if (int rc = adopt_alt(pf, n))
+      return rc;
+  if (idx && cnt)
+    CU(cudaMemcpyAsync(idx, d_idx, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, pf->stream));
+  CU(cudaStreamSynchronize(pf->stream));
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_uniform_sample(amcl3d_b200_pf_t pf, int sample_num, uint64_t k0, uint64_t k1, void* d_out,
+                                  int32_t* idx, int* emitted)
+{
+  if (!pf || sample_num < 0)
+    return fail(AMCL3D_B200_ERR_ARG, "bad sample_num");
+  const uint64_t S = (uint64_t)sample_num;
+  const uint64_t n = pf->n;
+  if (k1 == 0)
+    k1 = S;
+  if (k0 > k1 || k1 > S)
+    return fail(AMCL3D_B200_ERR_ARG, "bad output range");
+  if (!d_out && (k0 != 0 || k1 != S))
+    return fail(AMCL3D_B200_ERR_ARG, "replacing p_ needs the full output range");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  const uint64_t cnt = k1 - k0;
+  CU(ensure(pf->d_prefix, pf->prefix_cap, n));
+  CU(ensure(pf->d_thr, pf->thr_cap, S));
+  float* out = reinterpret_cast<float*>(d_out);
+  if (!out)
+  {
+    CU(ensure_particles(pf->d_alt, pf->alt_cap, S));
+    out = pf->d_alt;
+  }
+  int32_t* d_idx = nullptr;
+  if (idx)
+  {
+    CU(ensure(pf->d_idx, pf->idx_cap, cnt));
+    d_idx = pf->d_idx;
+  }
+  {
+    Timed t(pf);
+    if (int rc = normalize_async(pf))  // ParticleFilter.cpp:258
+      return rc;
+    CU(launch_chain_prefix(pf->d_p, n, 0, pf->d_prefix, nullptr, pf->stream));
+    CU(launch_chain_thresholds(sample_num, pf->d_thr, pf->stream));
+    CU(launch_uniform_search(pf->d_p, pf->d_prefix, n, pf->d_thr, sample_num, k0, k1, out, d_idx, pf->stream));
+    CU(launch_count_emitted(pf->d_thr, sample_num, pf->d_prefix, n, pf->d_int, pf->stream));
+    pf->launches += 4;
+  }
+  if (!d_out)
+    if (int rc = adopt_alt(pf, S))
+      return rc;
+  int em = 0;
+  CU(cudaMemcpyAsync(&em, pf->d_int, sizeof(int), cudaMemcpyDeviceToHost, pf->stream));
+  if (idx && cnt)
+    CU(cudaMemcpyAsync(idx, d_idx, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, pf->stream));
+  CU(cudaStreamSynchronize(pf->stream));
+  if (emitted)
+    *emitted = em;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_mean(amcl3d_b200_pf_t pf, int exact, float out7[7])
+{
+  if (!pf || !out7)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  {
+    Timed t(pf);
+    CU(launch_mean(pf->d_p, pf->n, exact, pf->d_scalars + 8, pf->d_scratch, pf->stream));
+    pf->launches += exact ? 1 : 2;
+  }
+  CU(cudaMemcpyAsync(out7, pf->d_scalars + 8, 7 * sizeof(float), cudaMemcpyDeviceToHost, pf->stream));
+  CU(cudaStreamSynchronize(pf->stream));
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_best(amcl3d_b200_pf_t pf, float out7[7])
+{
+  if (!pf || !out7)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  {
+    Timed t(pf);
+    CU(launch_max_weight(pf->d_p, pf->n, pf->d_scalars + 2, pf->d_u64 + 1, pf->d_scratch, pf->stream));
+    pf->launches += 2;
+  }
+  unsigned long long arg = ~0ull;
+  CU(cudaMemcpyAsync(&arg, pf->d_u64 + 1, sizeof(arg), cudaMemcpyDeviceToHost, pf->stream));
+  CU(cudaStreamSynchronize(pf->stream));
+  for (int k = 0; k < 7; ++k)
+    out7[k] = 0.f;  // best_p starts as the zero particle (ParticleFilter.cpp:220-221)
+  if (arg != ~0ull && arg < pf->n)
+    CU(cudaMemcpy(out7, pf->d_p + 7 * arg, 7 * sizeof(float), cudaMemcpyDeviceToHost));
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_predict(amcl3d_b200_pf_t pf, const double delta[6], const float* noise6)
+{
+  if (!pf || !delta || (pf->n && !noise6))
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  CU(ensure(pf->d_noise, pf->noise_cap, pf->n * 6));
+  CU(cudaMemcpyAsync(pf->d_delta, delta, 6 * sizeof(double), cudaMemcpyHostToDevice, pf->stream));
+  if (pf->n)
+    CU(cudaMemcpyAsync(pf->d_noise, noise6, sizeof(float) * 6 * pf->n, cudaMemcpyHostToDevice, pf->stream));
+  {
+    Timed t(pf);
+    CU(launch_predict(pf->d_p, pf->n, pf->d_delta, pf->d_noise, pf->stream));
+    pf->launches += pf->n ? 1 : 0;
+  }
+  CU(cudaStreamSynchronize(pf->stream));
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_prefix(amcl3d_b200_pf_t pf, void** d_prefix, float* host_out, uint64_t cap)
+{
+  if (!pf)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+  if (host_out && cap < pf->n)
+    return fail(AMCL3D_B200_ERR_ARG, "output too small");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  CU(ensure(pf->d_prefix, pf->prefix_cap, pf->n));
+  {
+    Timed t(pf);
+    CU(launch_chain_prefix(pf->d_p, pf->n, 0, pf->d_prefix, nullptr, pf->stream));
+    pf->launches += 1;
+  }
+  if (host_out && pf->n)
+    CU(cudaMemcpyAsync(host_out, pf->d_prefix, sizeof(float) * pf->n, cudaMemcpyDeviceToHost, pf->stream));
+  CU(cudaStreamSynchronize(pf->stream));
+  if (d_prefix)
+    *d_prefix = pf->d_prefix;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_last_kernel_ms(amcl3d_b200_pf_t pf, float* ms)
+{
+  if (!pf || !ms)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  *ms = 0.f;
+  if (!pf->timed)
+    return AMCL3D_B200_OK;
+  CU(cudaEventSynchronize(pf->ev1));
+  CU(cudaEventElapsedTime(ms, pf->ev0, pf->ev1));
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_launch_count(amcl3d_b200_pf_t pf, uint64_t* launches)
+{
+  if (!pf || !launches)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  *launches = pf->launches;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_bench_gather(amcl3d_b200_grid_t g, uint64_t window_cells, uint32_t blocks, uint32_t iters, int coherent,
+                             float* ms, uint64_t* loads)
+{
+  if (!g || !ms || !blocks || !iters)
+    return fail(AMCL3D_B200_ERR_ARG, "bad argument");
+  if (!g->map.has_grid)
+    return fail(AMCL3D_B200_ERR_STATE, "no grid");
+  if (int rc = use_device(g->device))
+    return rc;
+  if (window_cells == 0 || window_cells > g->map.n_cells)
+    window_cells = g->map.n_cells;
+  float* d_sink = nullptr;
+  CU(cudaMalloc(&d_sink, sizeof(float)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  // one untimed warm-up launch, then the timed one
+  cudaError_t e = launch_gather_bench(g->d_prob, window_cells, blocks, iters, coherent, d_sink, g->stream);
+  if (e == cudaSuccess)
+    e = cudaEventRecord(e0, g->stream);
+  if (e == cudaSuccess)
+    e = launch_gather_bench(g->d_prob, window_cells, blocks, iters, coherent, d_sink, g->stream);
+  if (e == cudaSuccess)
+    e = cudaEventRecord(e1, g->stream);
+  if (e == cudaSuccess)
+    e = cudaEventSynchronize(e1);
+  if (e == cudaSuccess)
+    e = cudaEventElapsedTime(ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_sink);
+  if (e != cudaSuccess)
+    return fail_cuda(e, "gather bench");
+  if (loads)
+    *loads = (uint64_t)blocks * 256ull * iters * 8ull;
+  return AMCL3D_B200_OK;
+}
+
+}  // extern "C"

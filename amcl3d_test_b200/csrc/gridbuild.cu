@@ -1,0 +1,697 @@
+// gridbuild.cu -- K1/K2: probability-grid build on the device (sm_100a)
+//
+// Stands behind computePointCloud   amcl3d/src/PointCloudTools.cpp:84-109   (bounds reduction)
+//               computeGrid         amcl3d/src/PointCloudTools.cpp:111-174  (kd-tree NN + Gaussian -> exact EDT)
+//               computeGrid2        amcl3d/src/PointCloudTools.cpp:176-254  (27-neighbour max splat)
+//
+// computeGrid asks, for every voxel corner min + i*resol, the squared distance to the nearest map
+// point.  For map points on the lattice of pitch resol/sub (octomap-derived maps sit on voxel centres,
+// i.e. the half-voxel lattice, sub = 2) that is an exact Euclidean distance transform in integer
+// arithmetic: sites h = sub*j + parity, queries x = sub*i.  Sites are split by the parity of their
+// coordinates (8 classes when sub = 2); every populated class is one voxel-resolution separable EDT
+//   x pass : nearest set bit left / right in an occupancy bit-row            -> uint16 |dx|
+//   y pass : lower envelope of parabolas per column (Meijster, integer Sep)  -> int32 dx^2+dy^2
+//   z pass : the same along z, min-combined across classes, and in the last class fused with the
+//            Gaussian writer  prob = c1*expf(-d^2*d^2*c2)  straight into the linear float grid.
+// Classes with only a handful of sites (e.g. the two extreme-corner points that pin the bounds) are
+// folded into that last epilogue by brute force instead of paying three passes.
+// The result is bit-exact in lattice units regardless of tie-breaking; the passes are HBM streaming
+// kernels (no reuse, no tensor-core work).
+#include "common.cuh"
+
+#include <float.h>
+#include <stdio.h>
+
+namespace a3d
+{
+namespace
+{
+constexpr int32_t kInf = INT32_MAX;
+constexpr uint16_t kInf16 = 0xFFFF;
+constexpr int kSparseMax = 256;  // classes with <= this many points are handled by brute force
+
+// ---- bounds ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2key(float f)
+{
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__global__ void bounds_kernel(const float* __restrict__ xyz, uint32_t stride, uint64_t n, uint32_t* __restrict__ keys)
+{
+  uint32_t lo[3] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, hi[3] = { 0, 0, 0 };
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+  {
+    const float* p = xyz + i * stride;
+    const float x = p[0], y = p[1], z = p[2];
+    if (!isfinite(x) || !isfinite(y) || !isfinite(z))
+      continue;
+    const uint32_t k[3] = { f2key(x), f2key(y), f2key(z) };
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+      lo[a] = min(lo[a], k[a]);
+      hi[a] = max(hi[a], k[a]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+      atomicMin(&keys[a], lo[a]);
+      atomicMax(&keys[3 + a], hi[a]);
+    }
+  }
+}
+
+// ---- voxelisation ---------------------------------------------------------------------------------
+struct Lattice
+{
+  double min[3];
+  double pitch;  // resol / sub
+  int sub;
+  int w[3];      // site nodes per axis = size + 1
+  uint32_t words_per_row;
+};
+
+__device__ __forceinline__ bool snap_point(const Lattice& L, const float* p, long long h[3])
+{
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    if (!isfinite(p[a]))
+      return false;
+    h[a] = __double2ll_rn(__ddiv_rn(__dsub_rn((double)p[a], L.min[a]), L.pitch));
+  }
+  return true;
+}
+__device__ __forceinline__ int class_of(const Lattice& L, const long long h[3])
+{
+  if (L.sub == 1)
+    return 0;
+  return (int)((h[0] & 1) | ((h[1] & 1) << 1) | ((h[2] & 1) << 2));
+}
+
+__global__ void class_count_kernel(const __grid_constant__ Lattice L, const float* __restrict__ xyz, uint32_t stride,
+                                   uint64_t n, unsigned long long* __restrict__ counts)
+{
+  __shared__ unsigned int sh[8];
+  if (threadIdx.x < 8)
+    sh[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+  {
+    long long h[3];
+    if (!snap_point(L, xyz + i * stride, h))
+      continue;
+    atomicAdd(&sh[class_of(L, h)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && sh[threadIdx.x])
+    atomicAdd(&counts[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+// dense class `cls`: set occupancy bits; sparse classes (mask bit set): append lattice coordinates
+__global__ void voxelize_kernel(const __grid_constant__ Lattice L, const float* __restrict__ xyz, uint32_t stride,
+                                uint64_t n, int cls, uint32_t* __restrict__ bits, uint32_t sparse_mask,
+                                int4* __restrict__ sparse, unsigned int* __restrict__ sparse_count)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+  {
+    long long h[3];
+    if (!snap_point(L, xyz + i * stride, h))
+      continue;
+    const int c = class_of(L, h);
+    const bool is_sparse = sparse != nullptr && ((sparse_mask >> c) & 1u);
+    if (!is_sparse && (bits == nullptr || c != cls))
+      continue;
+    // site node index along each axis; nodes outside [0, size] are dropped
+    long long j[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      j[a] = (L.sub == 2) ? ((h[a] - ((c >> a) & 1)) >> 1) : h[a];
+    if (j[0] < 0 || j[0] >= L.w[0] || j[1] < 0 || j[1] >= L.w[1] || j[2] < 0 || j[2] >= L.w[2])
+      continue;
+    if (is_sparse)
+    {
+      const unsigned int slot = atomicAdd(sparse_count, 1u);
+      if (slot < 8u * kSparseMax)
+        sparse[slot] = make_int4((int)h[0], (int)h[1], (int)h[2], 0);
+      continue;
+    }
+    const uint64_t row = (uint64_t)j[2] * L.w[1] + (uint64_t)j[1];
+    atomicOr(&bits[row * L.words_per_row + (uint32_t)(j[0] >> 5)], 1u << (j[0] & 31));
+  }
+}
+
+// ---- x pass ---------------------------------------------------------------------------------------
+// one thread per (row, query ix); a warp shares one occupancy word.  d1 = |sub*(ix - j) - par| of the
+// nearest site j in the row, kInf16 if the row is empty.
+__global__ void __launch_bounds__(256)
+    xpass_kernel(const uint32_t* __restrict__ bits, uint32_t words_per_row, uint64_t rows, int sx, int wx, int sub, int par,
+                 uint16_t* __restrict__ d1)
+{
+  const uint32_t chunks = (uint32_t)((sx + 31) / 32);
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows * chunks)
+    return;
+  const uint64_t row = warp / chunks;
+  const uint32_t wq = (uint32_t)(warp % chunks);
+  const uint32_t* r = bits + row * words_per_row;
+  const uint32_t W = r[wq];
+
+  // nearest site at or left of this lane
+  int left = -1;
+  {
+    const uint32_t m = W & (0xFFFFFFFFu >> (31 - lane));
+    if (m)
+      left = (int)(wq * 32u) + 31 - __clz(m);
+    else
+    {
+      for (int w = (int)wq - 1; w >= 0; --w)
+      {
+        const uint32_t v = r[w];
+        if (v)
+        {
+          left = w * 32 + 31 - __clz(v);
+          break;
+        }
+      }
+    }
+  }
+  int right = -1;
+  {
+    const uint32_t m = W & (0xFFFFFFFFu << lane);
+    if (m)
+      right = (int)(wq * 32u) + __ffs(m) - 1;
+    else
+    {
+      for (uint32_t w = wq + 1; w < words_per_row; ++w)
+      {
+        const uint32_t v = r[w];
+        if (v)
+        {
+          right = (int)(w * 32u) + __ffs(v) - 1;
+          break;
+        }
+      }
+    }
+  }
+  const int ix = (int)(wq * 32u) + lane;
+  if (ix >= sx)
+    return;
+  int best = 0x7FFFFFFF;
+  if (left >= 0)
+    best = abs(sub * (ix - left) - par);
+  if (right >= 0 && right < wx)
+    best = min(best, abs(sub * (ix - right) - par));
+  d1[row * (uint64_t)sx + ix] = (best >= 0xFFFF) ? kInf16 : (uint16_t)best;
+}
+
+// ---- lower-envelope passes --------------------------------------------------------------------------
+struct Gauss
+{
+  float c1, c2;
+  double unit;  // (resol/sub)^2 : lattice units^2 -> m^2
+  int mode;
+};
+
+__device__ __forceinline__ float prob_of(const Gauss& g, int32_t d2)
+{
+  if (d2 == kInf)
+    return 0.f;  // PointCloudTools.cpp:164-168
+  const float dist = __double2float_rn(__dmul_rn((double)d2, g.unit));  // squared NN distance in m^2
+  if (g.mode == AMCL3D_B200_GRID_GAUSSIAN)
+    return __fmul_rn(g.c1, expf(__fmul_rn(-dist, g.c2)));
+  return __fmul_rn(g.c1, expf(__fmul_rn(__fmul_rn(-dist, dist), g.c2)));  // PointCloudTools.cpp:160-162
+}
+
+__device__ __forceinline__ long long floor_div(long long num, long long den)  // den > 0
+{
+  long long q = (long long)floor((double)num / (double)den);
+  while (q * den > num)
+    --q;
+  while ((q + 1) * den <= num)
+    ++q;
+  return q;
+}
+
+struct PassArgs
+{
+  uint64_t ncol;     // contiguous (fast) extent
+  uint32_t nplane;   // outer extent
+  int len_in;        // sites along the pass axis (size + 1)
+  int len_out;       // queries along the pass axis (size)
+  int sub;
+  int par;
+  uint64_t nthreads; // total threads of the launch (stack stride)
+};
+
+struct FinalArgs
+{
+  int enabled;            // this is the last dense class: write prob
+  const int32_t* prev;    // d2 of earlier classes (nullable)
+  int32_t* d2_out;        // where to keep the combined d2 (nullable)
+  float* prob;
+  const int4* sparse;     // brute-force sites in lattice coordinates
+  int nsparse;
+  int sx, sy;             // to recover (ix, iy) from the column index in the z pass
+  Gauss g;
+};
+
+__device__ __forceinline__ int32_t load_g(const uint16_t* in, uint64_t idx)
+{
+  const uint16_t v = in[idx];
+  return v == kInf16 ? kInf : (int32_t)v * (int32_t)v;
+}
+__device__ __forceinline__ int32_t load_g(const int32_t* in, uint64_t idx)
+{
+  return in[idx];
+}
+
+// in : [plane][j][col]  (j < len_in),  out : [plane][i][col]  (i < len_out)
+// out[i] = min_j in[j] + (sub*i - (sub*j + par))^2
+template <typename TIn, bool kFinal>
+__global__ void __launch_bounds__(256) envelope_kernel(const TIn* __restrict__ in, int32_t* __restrict__ out,
+                                                       const __grid_constant__ PassArgs A, int2* __restrict__ stack,
+                                                       const __grid_constant__ FinalArgs F)
+{
+  const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t total = A.ncol * A.nplane;
+  for (uint64_t c = gtid; c < total; c += A.nthreads)
+  {
+    const uint64_t plane = c / A.ncol;
+    const uint64_t col = c % A.ncol;
+    const TIn* src = in + plane * (uint64_t)A.len_in * A.ncol + col;
+    int q = -1;
+    // cached top of stack
+    int top_s = 0, top_t = 0, top_g = 0;
+    for (int j = 0; j < A.len_in; ++j)
+    {
+      const int32_t g = load_g(src, (uint64_t)j * A.ncol);
+      if (g == kInf)
+        continue;
+      const long long sj = (long long)A.sub * j + A.par;
+      while (q >= 0)
+      {
+        const long long x = (long long)A.sub * top_t;
+        const long long st = (long long)A.sub * top_s + A.par;
+        const long long ft = (x - st) * (x - st) + top_g;
+        const long long fj = (x - sj) * (x - sj) + g;
+        if (ft > fj)
+        {
+          --q;
+          if (q >= 0)
+          {
+            const int2 e = stack[(uint64_t)q * A.nthreads + gtid];
+            top_s = e.x & 0xFFFF;
+            top_t = (e.x >> 16) & 0xFFFF;
+            top_g = e.y;
+          }
+        }
+        else
+          break;
+      }
+      if (q < 0)
+      {
+        q = 0;
+        top_s = j;
+        top_t = 0;
+        top_g = g;
+        stack[gtid] = make_int2(j, g);
+      }
+      else
+      {
+        const long long st = (long long)A.sub * top_s + A.par;
+        const long long num = sj * sj - st * st + (long long)g - (long long)top_g;
+        const long long den = 2ll * A.sub * (sj - st);
+        const long long w = floor_div(num, den) + 1;
+        if (w < A.len_out)
+        {
+          ++q;
+          top_s = j;
+          top_t = (int)w;
+          top_g = g;
+          stack[(uint64_t)q * A.nthreads + gtid] = make_int2(j | ((int)w << 16), g);
+        }
+      }
+    }
+    // backward scan
+    int32_t* dst = out ? out + plane * (uint64_t)A.len_out * A.ncol + col : nullptr;
+    for (int i = A.len_out - 1; i >= 0; --i)
+    {
+      int32_t d2 = kInf;
+      if (q >= 0)
+      {
+        const long long d = (long long)A.sub * i - ((long long)A.sub * top_s + A.par);
+        d2 = (int32_t)(d * d + top_g);
+        if (i == top_t)
+        {
+          --q;
+          if (q >= 0)
+          {
+            const int2 e = stack[(uint64_t)q * A.nthreads + gtid];
+            top_s = e.x & 0xFFFF;
+            top_t = (e.x >> 16) & 0xFFFF;
+            top_g = e.y;
+          }
+        }
+      }
+      const uint64_t o = plane * (uint64_t)A.len_out * A.ncol + (uint64_t)i * A.ncol + col;
+      if (kFinal)
+      {
+        if (F.prev != nullptr)
+          d2 = min(d2, F.prev[o]);
+        if (F.enabled)
+        {
+          if (F.nsparse > 0)
+          {
+            const long long qx = (long long)A.sub * (long long)(col % (uint64_t)F.sx);
+            const long long qy = (long long)A.sub * (long long)(col / (uint64_t)F.sx);
+            const long long qz = (long long)A.sub * i;
+            for (int s = 0; s < F.nsparse; ++s)
+            {
+              const int4 h = F.sparse[s];
+              const long long dx = qx - h.x, dy = qy - h.y, dz = qz - h.z;
+              const long long dd = dx * dx + dy * dy + dz * dz;
+              if (dd < (long long)d2)
+                d2 = (int32_t)dd;
+            }
+          }
+          F.prob[o] = prob_of(F.g, d2);
+          if (F.d2_out != nullptr)
+            F.d2_out[o] = d2;
+        }
+        else
+          F.d2_out[o] = d2;
+      }
+      else
+        dst[(uint64_t)i * A.ncol] = d2;
+    }
+  }
+}
+
+// no dense class at all: brute force over the sparse sites only
+__global__ void sparse_only_kernel(uint64_t cells, int sx, int sy, int sub, const int4* __restrict__ sparse, int nsparse,
+                                   const __grid_constant__ Gauss g, float* __restrict__ prob, int32_t* __restrict__ d2_out)
+{
+  const uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= cells)
+    return;
+  const long long qx = (long long)sub * (long long)(o % (uint64_t)sx);
+  const long long qy = (long long)sub * (long long)((o / (uint64_t)sx) % (uint64_t)sy);
+  const long long qz = (long long)sub * (long long)(o / ((uint64_t)sx * sy));
+  long long best = kInf;
+  for (int s = 0; s < nsparse; ++s)
+  {
+    const int4 h = sparse[s];
+    const long long dx = qx - h.x, dy = qy - h.y, dz = qz - h.z;
+    const long long dd = dx * dx + dy * dy + dz * dz;
+    best = dd < best ? dd : best;
+  }
+  prob[o] = prob_of(g, (int32_t)best);
+  if (d2_out)
+    d2_out[o] = (int32_t)best;
+}
+
+// ---- computeGrid2 splat -----------------------------------------------------------------------------
+struct SplatArgs
+{
+  double min[3];
+  double resol;
+  uint32_t size[3];
+  uint32_t step_y, step_z, grid_size;  // u32 arithmetic like PointCloudTools.cpp:192-195
+  float c1, c2;
+};
+__global__ void splat_kernel(const __grid_constant__ SplatArgs S, const float* __restrict__ xyz, uint32_t stride, uint64_t n,
+                             int* __restrict__ prob_bits)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * 27)
+    return;
+  const uint64_t pi = t / 27;
+  const int nb = (int)(t % 27);
+  const int i = nb / 9 - 1, j = (nb / 3) % 3 - 1, k = nb % 3 - 1;  // x, y, z offsets (PointCloudTools.cpp:225-233)
+  const float* pt = xyz + pi * stride;
+  // PointCloudTools.cpp:208-210: (f32 - f64) / f64 truncated to u32
+  const uint32_t ix = __double2uint_rz(__ddiv_rn(__dsub_rn((double)pt[0], S.min[0]), S.resol));
+  const uint32_t iy = __double2uint_rz(__ddiv_rn(__dsub_rn((double)pt[1], S.min[1]), S.resol));
+  const uint32_t iz = __double2uint_rz(__ddiv_rn(__dsub_rn((double)pt[2], S.min[2]), S.resol));
+  const int xx = (int)(ix + i), yy = (int)(iy + j), zz = (int)(iz + k);
+  if (xx < 0 || (uint32_t)xx >= S.size[0])
+    return;
+  if (yy < 0 || (uint32_t)yy >= S.size[1])
+    return;
+  if (zz < 0 || (uint32_t)zz > S.size[2])  // `>` as written (PointCloudTools.cpp:236)
+    return;
+  const uint32_t index = (uint32_t)xx + (uint32_t)yy * S.step_y + (uint32_t)zz * S.step_z;
+  if (index >= S.grid_size)  // PointCloudTools.cpp:238
+    return;
+  const float qx = __double2float_rn(__dadd_rn(S.min[0], __dmul_rn((double)xx, S.resol)));
+  const float qy = __double2float_rn(__dadd_rn(S.min[1], __dmul_rn((double)yy, S.resol)));
+  const float qz = __double2float_rn(__dadd_rn(S.min[2], __dmul_rn((double)zz, S.resol)));
+  const float dx = __fsub_rn(qx, pt[0]), dy = __fsub_rn(qy, pt[1]), dz = __fsub_rn(qz, pt[2]);
+  const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+  const float v = __fmul_rn(S.c1, expf(__fmul_rn(__fmul_rn(-dist, dist), S.c2)));
+  // values are >= 0, so the IEEE bit patterns order like ints: max is associative -> deterministic
+  atomicMax(&prob_bits[index], __float_as_int(v));
+}
+
+void gauss_consts(double sensor_dev, float* c1, float* c2)
+{
+  *c1 = static_cast<float>(1. / (sensor_dev * sqrt(2 * M_PI)));   // PointCloudTools.cpp:139
+  *c2 = static_cast<float>(1. / (2. * sensor_dev * sensor_dev));  // PointCloudTools.cpp:140
+}
+
+#define CK(expr)                     \
+  do                                 \
+  {                                  \
+    cudaError_t e__ = (expr);        \
+    if (e__ != cudaSuccess)          \
+    {                                \
+      rc = e__;                      \
+      goto done;                     \
+    }                                \
+  } while (0)
+
+}  // namespace
+
+cudaError_t launch_bounds(const float* xyz, uint32_t stride, uint64_t n, float* out6, cudaStream_t stream)
+{
+  // out6 is used as 6 ordered-uint keys on the device; the caller decodes them
+  uint32_t init[6] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u };
+  cudaError_t e = cudaMemcpyAsync(out6, init, sizeof(init), cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess)
+    return e;
+  uint64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8)
+    blocks = 148 * 8;
+  if (blocks == 0)
+    blocks = 1;
+  bounds_kernel<<<(unsigned)blocks, 256, 0, stream>>>(xyz, stride, n, reinterpret_cast<uint32_t*>(out6));
+  return cudaGetLastError();
+}
+
+cudaError_t build_grid_splat(const MapDev& map, const float* d_xyz, uint32_t stride, uint64_t n, double sensor_dev,
+                             float* prob, cudaStream_t stream)
+{
+  SplatArgs S;
+  for (int a = 0; a < 3; ++a)
+  {
+    S.min[a] = map.min[a];
+    S.size[a] = map.size[a];
+  }
+  S.resol = map.resol;
+  S.step_y = map.size[0];
+  S.step_z = map.size[0] * map.size[1];
+  S.grid_size = map.size[0] * map.size[1] * map.size[2];
+  gauss_consts(sensor_dev, &S.c1, &S.c2);
+  cudaError_t e = cudaMemsetAsync(prob, 0, sizeof(float) * map.n_cells, stream);
+  if (e != cudaSuccess)
+    return e;
+  if (n == 0)
+    return cudaSuccess;
+  const uint64_t threads = n * 27;
+  splat_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(S, d_xyz, stride, n, reinterpret_cast<int*>(prob));
+  return cudaGetLastError();
+}
+
+cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t stride, uint64_t n, double sensor_dev,
+                           int mode, int sub, float* prob, int32_t** keep_d2, cudaStream_t stream, char* err,
+                           size_t errlen)
+{
+  cudaError_t rc = cudaSuccess;
+  const int sx = (int)map.size[0], sy = (int)map.size[1], sz = (int)map.size[2];
+  const uint64_t cells = (uint64_t)sx * sy * sz;
+  const int maxdim = sx > sy ? (sx > sz ? sx : sz) : (sy > sz ? sy : sz);
+  if ((long long)sub * (maxdim + 1) > 26000 || maxdim + 1 > 65535)
+  {
+    snprintf(err, errlen, "grid axis too long for the int32 EDT (sub*size must stay below 26000)");
+    return cudaErrorInvalidValue;
+  }
+  Lattice L;
+  for (int a = 0; a < 3; ++a)
+  {
+    L.min[a] = map.min[a];
+    L.w[a] = (int)map.size[a] + 1;
+  }
+  L.pitch = map.resol / sub;
+  L.sub = sub;
+  L.words_per_row = (uint32_t)((L.w[0] + 31) / 32);
+  const uint64_t rows = (uint64_t)L.w[1] * L.w[2];
+  const int nclass = sub == 2 ? 8 : 1;
+
+  unsigned long long* d_counts = nullptr;
+  uint32_t* d_bits = nullptr;
+  int4* d_sparse = nullptr;
+  unsigned int* d_sparse_count = nullptr;
+  uint16_t* d_d1 = nullptr;
+  int32_t* d_dxy = nullptr;
+  int32_t* d_d2 = nullptr;
+  int2* d_stack = nullptr;
+  unsigned long long h_counts[8] = { 0 };
+  unsigned int h_nsparse = 0;
+  uint32_t sparse_mask = 0;
+  int dense[8], ndense = 0;
+  Gauss G;
+  gauss_consts(sensor_dev, &G.c1, &G.c2);
+  G.unit = L.pitch * L.pitch;
+  G.mode = mode;
+
+  uint64_t pblocks = (n + 255) / 256;
+  if (pblocks > 148 * 16)
+    pblocks = 148 * 16;
+  if (pblocks == 0)
+    pblocks = 1;
+
+  CK(cudaMalloc(&d_counts, 8 * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(d_counts, 0, 8 * sizeof(unsigned long long), stream));
+  class_count_kernel<<<(unsigned)pblocks, 256, 0, stream>>>(L, d_xyz, stride, n, d_counts);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h_counts, d_counts, sizeof(h_counts), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  for (int c = 0; c < nclass; ++c)
+  {
+    if (h_counts[c] == 0)
+      continue;
+    if (h_counts[c] <= (unsigned long long)kSparseMax)
+      sparse_mask |= 1u << c;
+    else
+      dense[ndense++] = c;
+  }
+  CK(cudaMalloc(&d_sparse, sizeof(int4) * 8 * kSparseMax));
+  CK(cudaMalloc(&d_sparse_count, sizeof(unsigned int)));
+  CK(cudaMemsetAsync(d_sparse_count, 0, sizeof(unsigned int), stream));
+  if (sparse_mask)
+  {
+    voxelize_kernel<<<(unsigned)pblocks, 256, 0, stream>>>(L, d_xyz, stride, n, -1, nullptr, sparse_mask, d_sparse,
+                                                           d_sparse_count);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&h_nsparse, d_sparse_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (h_nsparse > 8u * kSparseMax)
+      h_nsparse = 8u * kSparseMax;
+  }
+
+  {
+    const bool need_d2 = (keep_d2 != nullptr) || ndense > 1;
+    if (need_d2)
+      CK(cudaMalloc(&d_d2, sizeof(int32_t) * cells));
+
+    if (ndense == 0)
+    {
+      sparse_only_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(cells, sx, sy, sub, d_sparse, (int)h_nsparse,
+                                                                                G, prob, d_d2);
+      CK(cudaGetLastError());
+    }
+    else
+    {
+      const uint64_t bits_words = rows * L.words_per_row;
+      CK(cudaMalloc(&d_bits, sizeof(uint32_t) * bits_words));
+      CK(cudaMalloc(&d_d1, sizeof(uint16_t) * rows * (uint64_t)sx));
+      CK(cudaMalloc(&d_dxy, sizeof(int32_t) * (uint64_t)sx * sy * L.w[2]));
+      const uint64_t nthreads = 148ull * 1024ull;
+      const int maxlen = (L.w[1] > L.w[2] ? L.w[1] : L.w[2]);
+      CK(cudaMalloc(&d_stack, sizeof(int2) * nthreads * (uint64_t)maxlen));
+
+      for (int k = 0; k < ndense; ++k)
+      {
+        const int cls = dense[k];
+        const int px = cls & 1, py = (cls >> 1) & 1, pz = (cls >> 2) & 1;
+        const bool last = (k == ndense - 1);
+        CK(cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * bits_words, stream));
+        voxelize_kernel<<<(unsigned)pblocks, 256, 0, stream>>>(L, d_xyz, stride, n, cls, d_bits, 0u, nullptr, nullptr);
+        CK(cudaGetLastError());
+        {
+          const uint64_t warps = rows * (uint64_t)((sx + 31) / 32);
+          const uint64_t blocks = (warps * 32 + 255) / 256;
+          xpass_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_bits, L.words_per_row, rows, sx, L.w[0], sub, px, d_d1);
+          CK(cudaGetLastError());
+        }
+        FinalArgs F0{};
+        {
+          PassArgs A;
+          A.ncol = (uint64_t)sx;
+          A.nplane = (uint32_t)L.w[2];
+          A.len_in = L.w[1];
+          A.len_out = sy;
+          A.sub = sub;
+          A.par = py;
+          A.nthreads = nthreads;
+          envelope_kernel<uint16_t, false><<<(unsigned)(nthreads / 256), 256, 0, stream>>>(d_d1, d_dxy, A, d_stack, F0);
+          CK(cudaGetLastError());
+        }
+        {
+          PassArgs A;
+          A.ncol = (uint64_t)sx * sy;
+          A.nplane = 1;
+          A.len_in = L.w[2];
+          A.len_out = sz;
+          A.sub = sub;
+          A.par = pz;
+          A.nthreads = nthreads;
+          FinalArgs F{};
+          F.enabled = last ? 1 : 0;
+          F.prev = (k > 0) ? d_d2 : nullptr;
+          F.d2_out = d_d2;  // null only when single class and !keep
+          F.prob = prob;
+          F.sparse = d_sparse;
+          F.nsparse = last ? (int)h_nsparse : 0;
+          F.sx = sx;
+          F.sy = sy;
+          F.g = G;
+          envelope_kernel<int32_t, true><<<(unsigned)(nthreads / 256), 256, 0, stream>>>(d_dxy, nullptr, A, d_stack, F);
+          CK(cudaGetLastError());
+        }
+      }
+    }
+    CK(cudaStreamSynchronize(stream));
+    if (keep_d2 != nullptr)
+    {
+      *keep_d2 = d_d2;
+      d_d2 = nullptr;
+    }
+  }
+
+done:
+  if (rc != cudaSuccess && err)
+    snprintf(err, errlen, "grid build: %s", cudaGetErrorString(rc));
+  cudaFree(d_counts);
+  cudaFree(d_bits);
+  cudaFree(d_sparse);
+  cudaFree(d_sparse_count);
+  cudaFree(d_d1);
+  cudaFree(d_dxy);
+  cudaFree(d_d2);
+  cudaFree(d_stack);
+  return rc;
+}
+
+}  // namespace a3d

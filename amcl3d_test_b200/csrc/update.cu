@@ -1,0 +1,423 @@
+// update.cu -- K3: fused ParticleFilter::update  (sm_100a)
+//
+// Stands behind ParticleFilter::update(cloud)            amcl3d/src/ParticleFilter.cpp:114-139
+//               Grid3d::isIntoMap                        amcl3d/src/Grid3d.cpp:365-372
+//               Grid3d::computeCloudWeight (7-arg)       amcl3d/src/Grid3d.cpp:234-301
+// plus the range-only beacon weight of SURVEY 8(a) row R (not present in the reference tree).
+//
+// Mapping: one thread = one particle, so the f32 weight is accumulated in cloud order exactly like
+// the reference's serial loop (Grid3d.cpp:292) -- a shuffle/tree reduction would be *more* accurate
+// than the reference and miss the 1e-5 criterion at >= 10 k points.  A CTA streams the packed cloud
+// through a double-buffered shared-memory ring filled by TMA bulk copies (cp.async.bulk + mbarrier);
+// every lane reads the same point (smem broadcast), applies its particle's 3x3 rotation in registers
+// with the reference's rounding sequence (f32 mul/add, no FMA, f64 offset add), and issues kUnroll
+// independent voxel gathers before the in-order adds.  The kernel is a gather: one 32-byte sector per
+// in-bounds evaluation, no reuse across lanes, no tensor-core work.
+//
+// Exact arithmetic notes:
+//  * transform: ((x*r00 + y*r01) + z*r02) in f32, then + f64 offset, rounded to f32.  When the f64
+//    offset is exactly representable in f32 the f64 add is replaced by one f32 add (innocuous double
+//    rounding: 53 >= 2*24+2); otherwise the f64 path is taken.  Both are bit-identical to the reference.
+//  * bounds: f32 value against f64 size is done against size_up = smallest f32 >= size (equivalent).
+//  * voxel index floor(fl64(v / resol)): f32 quotient v*rinv with an error band; inside the band an
+//    f64 product with a 1e-9 band; inside that the real f64 division.  Result identical to the DDIV.
+#include "common.cuh"
+
+#include <math_constants.h>
+
+namespace a3d
+{
+namespace
+{
+constexpr int kThreads = 128;
+constexpr int kTile = 1024;  // points per stage: 16 KB
+constexpr int kStages = 2;
+constexpr int kUnroll = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  uint32_t done;
+  do
+  {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Grid3d.cpp:240-250
+__device__ __forceinline__ void rotation(float roll, float pitch, float yaw, int trig_mode, float r[9])
+{
+  if (trig_mode == AMCL3D_B200_TRIG_F64)
+  {
+    double sr, cr, sp, cp, sy, cy;
+    sincos((double)roll, &sr, &cr);
+    sincos((double)pitch, &sp, &cp);
+    sincos((double)yaw, &sy, &cy);
+    r[0] = __double2float_rn(__dmul_rn(cy, cp));
+    r[1] = __double2float_rn(__dsub_rn(__dmul_rn(__dmul_rn(cy, sp), sr), __dmul_rn(sy, cr)));
+    r[2] = __double2float_rn(__dadd_rn(__dmul_rn(__dmul_rn(cy, sp), cr), __dmul_rn(sy, sr)));
+    r[3] = __double2float_rn(__dmul_rn(sy, cp));
+    r[4] = __double2float_rn(__dadd_rn(__dmul_rn(__dmul_rn(sy, sp), sr), __dmul_rn(cy, cr)));
+    r[5] = __double2float_rn(__dsub_rn(__dmul_rn(__dmul_rn(sy, sp), cr), __dmul_rn(cy, sr)));
+    r[6] = __double2float_rn(-sp);
+    r[7] = __double2float_rn(__dmul_rn(cp, sr));
+    r[8] = __double2float_rn(__dmul_rn(cp, cr));
+  }
+  else
+  {
+    const float sr = sinf(roll), cr = cosf(roll);
+    const float sp = sinf(pitch), cp = cosf(pitch);
+    const float sy = sinf(yaw), cy = cosf(yaw);
+    r[0] = __fmul_rn(cy, cp);
+    r[1] = __fsub_rn(__fmul_rn(__fmul_rn(cy, sp), sr), __fmul_rn(sy, cr));
+    r[2] = __fadd_rn(__fmul_rn(__fmul_rn(cy, sp), cr), __fmul_rn(sy, sr));
+    r[3] = __fmul_rn(sy, cp);
+    r[4] = __fadd_rn(__fmul_rn(__fmul_rn(sy, sp), sr), __fmul_rn(cy, cr));
+    r[5] = __fsub_rn(__fmul_rn(__fmul_rn(sy, sp), cr), __fmul_rn(cy, sr));
+    r[6] = -sp;
+    r[7] = __fmul_rn(cp, sr);
+    r[8] = __fmul_rn(cp, cr);
+  }
+}
+
+// floor(fl64(v / resol)) for 0 <= v < size_up, three exact tiers (see header comment)
+__device__ __forceinline__ uint32_t voxel_of(float v, float rinv_f, float eps, double rinv, double resol)
+{
+  const float q = __fmul_rn(v, rinv_f);
+  const float kf = floorf(q);
+  const float fr = __fsub_rn(q, kf);
+  uint32_t k = (uint32_t)kf;
+  if (fr < eps || fr > __fsub_rn(1.0f, eps))
+  {
+    const double vd = (double)v;
+    const double qd = __dmul_rn(vd, rinv);
+    double kd = floor(qd);
+    const double frd = qd - kd;
+    if (frd < 1e-9 || frd > 1.0 - 1e-9)
+      kd = floor(__ddiv_rn(vd, resol));
+    k = (uint32_t)kd;
+  }
+  return k;
+}
+
+template <bool kF32Offset>
+__device__ __forceinline__ float add_offset(float s, float off_f, double off_d)
+{
+  if (kF32Offset)
+    return __fadd_rn(s, off_f);
+  return __double2float_rn(__dadd_rn((double)s, off_d));
+}
+
+// one tile of `count` points (multiple of kUnroll) for one particle
+template <bool kF32Offset>
+__device__ __forceinline__ void tile_loop(const MapDev& map, const float4* __restrict__ tile, uint32_t count,
+                                          const float r[9], const float off_f[3], const double off_d[3], float& weight,
+                                          int& cnt)
+{
+  const float* __restrict__ prob = map.prob;
+  const uint64_t step_y = map.size[0];
+  const uint64_t step_z = map.step_z;
+#pragma unroll 1
+  for (uint32_t base = 0; base < count; base += kUnroll)
+  {
+    uint64_t addr[kUnroll];
+    bool ok[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+    {
+      const float4 pt = tile[base + u];
+      // Grid3d.cpp:275-277
+      const float sx = __fadd_rn(__fadd_rn(__fmul_rn(pt.x, r[0]), __fmul_rn(pt.y, r[1])), __fmul_rn(pt.z, r[2]));
+      const float sy = __fadd_rn(__fadd_rn(__fmul_rn(pt.x, r[3]), __fmul_rn(pt.y, r[4])), __fmul_rn(pt.z, r[5]));
+      const float sz = __fadd_rn(__fadd_rn(__fmul_rn(pt.x, r[6]), __fmul_rn(pt.y, r[7])), __fmul_rn(pt.z, r[8]));
+      const float nx = add_offset<kF32Offset>(sx, off_f[0], off_d[0]);
+      const float ny = add_offset<kF32Offset>(sy, off_f[1], off_d[1]);
+      const float nz = add_offset<kF32Offset>(sz, off_f[2], off_d[2]);
+      // Grid3d.cpp:279-280 (NaN fails every comparison, like the reference)
+      bool in = (nx >= 0.f) & (nx < map.size_up[0]) & (ny >= 0.f) & (ny < map.size_up[1]) & (nz >= 0.f) &
+                (nz < map.size_up[2]);
+      uint64_t a = 0;
+      if (in)
+      {
+        // Grid3d.cpp:282-288
+        const uint32_t ix = voxel_of(nx, map.rinv_f, map.eps[0], map.rinv, map.resol);
+        const uint32_t iy = voxel_of(ny, map.rinv_f, map.eps[1], map.rinv, map.resol);
+        const uint32_t iz = voxel_of(nz, map.rinv_f, map.eps[2], map.rinv, map.resol);
+        in = (ix < map.size[0]) & (iy < map.size[1]) & (iz < map.size[2]);
+        a = (uint64_t)ix + (uint64_t)iy * step_y + (uint64_t)iz * step_z;
+        in = in & (a < map.n_cells);  // Grid3d.cpp:290
+      }
+      ok[u] = in;
+      addr[u] = a;
+    }
+    float v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      v[u] = ok[u] ? __ldg(prob + addr[u]) : 0.f;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+    {
+      if (ok[u])
+      {
+        weight = __fadd_rn(weight, v[u]);  // Grid3d.cpp:292, cloud order
+        ++cnt;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+    update_kernel(const __grid_constant__ MapDev map, float* __restrict__ particles, uint32_t n,
+                  const float4* __restrict__ cloud, uint32_t npts, uint32_t npad, const BeaconSet* __restrict__ beacons,
+                  float* __restrict__ wr_out, int trig_mode, unsigned long long* __restrict__ counter)
+{
+  __shared__ __align__(128) float4 tile[kStages][kTile];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+
+  const uint32_t tid = threadIdx.x;
+  const uint32_t i = blockIdx.x * kThreads + tid;
+  const bool live = i < n;
+
+  float px = 0, py = 0, pz = 0, roll = 0, pitch = 0, yaw = 0;
+  if (live)
+  {
+    const float* p = particles + (size_t)7 * i;
+    px = p[0];
+    py = p[1];
+    pz = p[2];
+    roll = p[3];
+    pitch = p[4];
+    yaw = p[5];
+  }
+  // Grid3d.cpp:365-372 -- f32 promoted against the f64 bounds; update() skips particles outside
+  // (has_map == 2: Grid3d::computeCloudWeight called directly, which has no such gate)
+  const bool gate = (map.has_map == 2) ||
+                    (((double)px >= map.min[0]) && ((double)px < map.max[0]) && ((double)py >= map.min[1]) &&
+                     ((double)py < map.max[1]) && ((double)pz >= map.min[2]) && ((double)pz < map.max[2]));
+  const bool inmap = live && map.has_map && map.has_grid && gate;
+
+  float r[9];
+  rotation(roll, pitch, yaw, trig_mode, r);
+  // Grid3d.cpp:256-258
+  double off_d[3];
+  off_d[0] = __dsub_rn((double)px, map.min[0]);
+  off_d[1] = __dsub_rn((double)py, map.min[1]);
+  off_d[2] = __dsub_rn((double)pz, map.min[2]);
+  float off_f[3];
+  bool f32_exact = true;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    off_f[a] = __double2float_rn(off_d[a]);
+    f32_exact = f32_exact && ((double)off_f[a] == off_d[a]);
+  }
+  // warp-uniform choice of the loop flavour; lanes that are not in the map do not vote it down
+  const bool warp_f32 = __all_sync(0xffffffffu, f32_exact || !inmap);
+
+  const uint32_t ntiles = (npad + kTile - 1) / kTile;
+  if (tid == 0)
+  {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s)
+      mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0)
+  {
+    for (uint32_t t = 0; t < ntiles && t < (uint32_t)kStages; ++t)
+    {
+      const uint32_t count = min((uint32_t)kTile, npad - t * kTile);
+      mbar_expect_tx(&full_bar[t], count * 16u);
+      tma_bulk_g2s(&tile[t][0], cloud + (size_t)t * kTile, count * 16u, &full_bar[t]);
+    }
+  }
+
+  float weight = 0.f;
+  int cnt = 0;
+  for (uint32_t t = 0; t < ntiles; ++t)
+  {
+    const uint32_t s = t % kStages;
+    const uint32_t parity = (t / kStages) & 1u;
+    mbar_wait(&full_bar[s], parity);
+    const uint32_t count = min((uint32_t)kTile, npad - t * kTile);
+    if (inmap)
+    {
+      if (warp_f32)
+        tile_loop<true>(map, &tile[s][0], count, r, off_f, off_d, weight, cnt);
+      else
+        tile_loop<false>(map, &tile[s][0], count, r, off_f, off_d, weight, cnt);
+    }
+    __syncthreads();  // every lane is done with stage s before TMA overwrites it
+    if (tid == 0 && t + kStages < ntiles)
+    {
+      const uint32_t tn = t + kStages;
+      const uint32_t cn = min((uint32_t)kTile, npad - tn * kTile);
+      mbar_expect_tx(&full_bar[s], cn * 16u);
+      tma_bulk_g2s(&tile[s][0], cloud + (size_t)tn * kTile, cn * 16u, &full_bar[s]);
+    }
+  }
+
+  if (live)
+  {
+    // Grid3d.cpp:299: (n < 10) ? 0 : weight / cloud->size()   (f32 / (float)size_t)
+    float w = 0.f;
+    if (inmap && cnt >= 10)
+      w = __fdiv_rn(weight, __uint2float_rn(npts));
+    particles[(size_t)7 * i + 6] = w;
+
+    if (wr_out != nullptr)
+    {
+      // row R: wr = prod_b k1*exp(-k2*(|p - a_b| - r_b)^2); 0 outside the map or without beacons
+      float wr = 0.f;
+      const uint32_t nb = beacons->n;
+      if (inmap && nb > 0)
+      {
+        wr = 1.f;
+        const float k1 = beacons->k1, k2 = beacons->k2;
+        for (uint32_t b = 0; b < nb; ++b)
+        {
+          const float dx = __fsub_rn(px, beacons->ax[b]);
+          const float dy = __fsub_rn(py, beacons->ay[b]);
+          const float dz = __fsub_rn(pz, beacons->az[b]);
+          const float rr = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+          const float e = __fsub_rn(rr, beacons->r[b]);
+          wr = __fmul_rn(wr, __fmul_rn(k1, expf(__fmul_rn(__fmul_rn(-k2, e), e))));
+        }
+      }
+      wr_out[i] = wr;
+    }
+  }
+  if (counter != nullptr)
+  {
+    unsigned int c = (unsigned int)cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((tid & 31u) == 0 && c)
+      atomicAdd(counter, (unsigned long long)c);
+  }
+}
+
+__global__ void pack_cloud_kernel(const float* __restrict__ src, uint32_t stride, uint32_t npts, float4* __restrict__ dst,
+                                  uint32_t npad)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npad)
+    return;
+  float4 o;
+  if (i < npts)
+  {
+    const float* p = src + (size_t)i * stride;
+    o = make_float4(p[0], p[1], p[2], 0.f);
+  }
+  else
+  {
+    const float nanv = CUDART_NAN_F;  // a NaN point fails every bounds test: contributes nothing
+    o = make_float4(nanv, nanv, nanv, 0.f);
+  }
+  dst[i] = o;
+}
+
+// ---- random-sector gather micro-benchmark (states the gather roofline) ---------------
+__device__ __forceinline__ uint64_t splitmix(uint64_t& s)
+{
+  s += 0x9E3779B97F4A7C15ull;
+  uint64_t z = s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+    gather_bench_kernel(const float* __restrict__ cells, uint64_t window, uint32_t iters, int coherent,
+                        float* __restrict__ sink)
+{
+  const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t s = gtid * 0x632BE59BD9B4E019ull + 12345;
+  float acc = 0.f;
+  // coherent: every thread of the grid walks the same slowly moving 4 MB neighbourhood (the access
+  // pattern of clustered particles sweeping the cloud in lock-step); else uniform over the window
+  const uint64_t blob = 1ull << 20;  // cells
+  for (uint32_t it = 0; it < iters; ++it)
+  {
+    uint64_t idx[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+    {
+      const uint64_t h = splitmix(s);
+      if (coherent)
+      {
+        const uint64_t centre = ((uint64_t)it * 8u + u) * 4099ull * 32ull;
+        idx[u] = (centre + (h % blob)) % window;
+      }
+      else
+        idx[u] = h % window;
+    }
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      v[u] = __ldg(cells + idx[u]);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      acc += v[u];
+  }
+  if (acc == 123.456f)
+    sink[0] = acc;
+}
+}  // namespace
+
+cudaError_t launch_update(const MapDev& map, float* particles, uint32_t n, const float4* cloud4, uint32_t npts,
+                          uint32_t npts_padded, const BeaconSet* beacons, float* wr_out, int trig_mode,
+                          unsigned long long* counter, cudaStream_t stream)
+{
+  if (n == 0)
+    return cudaSuccess;
+  const uint32_t blocks = (n + kThreads - 1) / kThreads;
+  update_kernel<<<blocks, kThreads, 0, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons, wr_out,
+                                                 trig_mode, counter);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_cloud(const float* src, uint32_t stride, uint32_t npts, float4* dst, uint32_t npts_padded,
+                              cudaStream_t stream)
+{
+  if (npts_padded == 0)
+    return cudaSuccess;
+  pack_cloud_kernel<<<(npts_padded + 255) / 256, 256, 0, stream>>>(src, stride, npts, dst, npts_padded);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_bench(const float* cells, uint64_t window, uint32_t blocks, uint32_t iters, int coherent,
+                                float* sink, cudaStream_t stream)
+{
+  gather_bench_kernel<<<blocks, 256, 0, stream>>>(cells, window, iters, coherent, sink);
+  return cudaGetLastError();
+}
+
+}  // namespace a3d

@@ -1,0 +1,212 @@
+/*
+ * amcl3d_b200.h -- C-ABI of the B200-native amcl3d particle-weighting path.
+ *
+ * One shared library (libamcl3d_b200.so, hand-written sm_100a CUDA) behind plain C entry points:
+ * opaque handles, plain pointers and sizes, int status codes.  There is no CPU fallback: every
+ * compute entry point launches CUDA kernels and fails with AMCL3D_B200_ERR_CUDA when no device is
+ * usable.  The reference has no FFI of its own (it is a C++ static library); each entry point below
+ * names the reference member function it stands behind (paths relative to the reference tree), and
+ * include/amcl3d/{Grid3d,ParticleFilter,PointCloudTools}.h are the source-compatible C++ classes
+ * that bind them.
+ *
+ * Layouts
+ *   particle : 7 packed floats x,y,z,roll,pitch,yaw,w        (amcl3d/src/ParticleFilter.h:32-48)
+ *   cloud    : floats, `stride` floats from one point to the next, x,y,z first (pcl::PointXYZI: stride 8)
+ *   grid     : float prob per voxel, x fastest, then y, then z  (amcl3d/src/PointCloudTools.h:30-52)
+ *
+ * Threading: a handle is not thread-safe (neither is the reference); different handles are independent.
+ * All functions are synchronous with respect to the host unless stated otherwise.
+ */
+#ifndef AMCL3D_B200_H
+#define AMCL3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define AMCL3D_B200_ABI_VERSION 1
+
+enum
+{
+  AMCL3D_B200_OK = 0,
+  AMCL3D_B200_ERR_ARG = 1,    /* bad argument / handle */
+  AMCL3D_B200_ERR_STATE = 2,  /* map or grid not set (the reference returns 0 / false here) */
+  AMCL3D_B200_ERR_CUDA = 3,   /* CUDA runtime error, see amcl3d_b200_last_error() */
+  AMCL3D_B200_ERR_IO = 4,     /* file open / short read */
+  AMCL3D_B200_ERR_MISMATCH = 5, /* .grid sensor_dev differs (Grid3d.cpp:422-427) */
+  AMCL3D_B200_ERR_EMPTY = 6   /* cloud with <= 1 point (PointCloudTools.cpp:89-91 throws) */
+};
+
+/* how `const auto sr = sin(roll)` binds (Grid3d.cpp:240-245) */
+enum
+{
+  AMCL3D_B200_TRIG_F64 = 0, /* default: ::sin(double), f64 products rounded once to f32 */
+  AMCL3D_B200_TRIG_F32 = 1  /* sinf/cosf and f32 products (device libm; not bit-pinned) */
+};
+
+/* grid builders */
+enum
+{
+  AMCL3D_B200_GRID_QUIRK = 0,    /* computeGrid as written: prob = c1*expf(-(d^2)^2*c2) (PointCloudTools.cpp:160-162) */
+  AMCL3D_B200_GRID_GAUSSIAN = 1, /* c1*expf(-d^2*c2): labelled extension */
+  AMCL3D_B200_GRID_SPLAT = 2     /* computeGrid2: 27-neighbour max splat (PointCloudTools.cpp:176-254) */
+};
+
+typedef struct amcl3d_b200_grid_s* amcl3d_b200_grid_t;
+typedef struct amcl3d_b200_pf_s* amcl3d_b200_pf_t;
+
+/* rosinrange_msg/msg/RangePose.msg:1-6 -- the fields the range weight consumes */
+typedef struct
+{
+  double position[3];
+  double range;
+} amcl3d_b200_beacon_t;
+
+typedef struct
+{
+  double min[3], max[3], resol, sensor_dev; /* PointCloudInfo + Grid3dInfo::sensor_dev */
+  uint32_t size[3];                         /* Grid3dInfo::size_{x,y,z} */
+  uint64_t n_cells;                         /* size_x*size_y*size_z (64-bit; the reference wraps at 2^32) */
+  int has_map;                              /* pc_info_ set */
+  int has_grid;                             /* grid_info_ set */
+  int device;
+} amcl3d_b200_grid_info_t;
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+int amcl3d_b200_abi_version(void);
+/* message of the last failing call on this thread */
+const char* amcl3d_b200_last_error(void);
+/* any argument may be NULL */
+int amcl3d_b200_device_info(int device, int* device_count, int* sm_count, int* cc_major, int* cc_minor,
+                            uint64_t* l2_bytes, uint64_t* mem_bytes);
+
+/* ---- Grid3d (amcl3d/src/Grid3d.{h,cpp}, PointCloudTools.{h,cpp}) ---------------------------- */
+int amcl3d_b200_grid_create(int device, amcl3d_b200_grid_t* out);
+int amcl3d_b200_grid_destroy(amcl3d_b200_grid_t g);
+int amcl3d_b200_grid_get_info(amcl3d_b200_grid_t g, amcl3d_b200_grid_info_t* info);
+
+/* computePointCloud (PointCloudTools.cpp:84-109): min/max of the map cloud by a device reduction,
+ * installs them with `resol` as the handle's PointCloudInfo and sizes the grid (PointCloudTools.cpp:
+ * 120-130).  n <= 1 -> AMCL3D_B200_ERR_EMPTY.  min/max (optional) receive the bounds. */
+int amcl3d_b200_grid_compute_bounds(amcl3d_b200_grid_t g, const float* xyz, uint32_t stride, uint64_t n,
+                                    double resol, double min[3], double max[3]);
+/* installs PointCloudInfo directly */
+int amcl3d_b200_grid_set_map(amcl3d_b200_grid_t g, const double min[3], const double max[3], double resol);
+
+/* computeGrid / computeGrid2 (PointCloudTools.cpp:111-174 / 176-254) on the device.  QUIRK/GAUSSIAN:
+ * exact Euclidean distance transform on the lattice of pitch resol/sub (sub = 1 or 2; map points are
+ * snapped to it, bit-exact with the kd-tree build when they already lie on it) followed by the fused
+ * Gaussian writer.  SPLAT takes arbitrary points.  keep_edt != 0 keeps the int32 squared distances
+ * (units (resol/sub)^2) for amcl3d_b200_grid_download_edt. */
+int amcl3d_b200_grid_build(amcl3d_b200_grid_t g, const float* xyz, uint32_t stride, uint64_t n,
+                           double sensor_dev, int mode, int sub, int keep_edt);
+int amcl3d_b200_grid_download_edt(amcl3d_b200_grid_t g, int32_t* d2, uint64_t cap);
+
+/* loadGrid's payload (Grid3d.cpp:404-442): cells + sizes + sensor_dev from host memory */
+int amcl3d_b200_grid_upload(amcl3d_b200_grid_t g, const float* prob, const uint32_t size[3], double sensor_dev);
+int amcl3d_b200_grid_download(amcl3d_b200_grid_t g, float* prob, uint64_t cap);
+/* saveGrid / loadGrid file format (Grid3d.cpp:388-395): u32 sx, sy, sz, f64 sensor_dev, cells */
+int amcl3d_b200_grid_save_file(amcl3d_b200_grid_t g, const char* path);
+int amcl3d_b200_grid_load_file(amcl3d_b200_grid_t g, const char* path, double sensor_dev);
+
+/* Grid3d::isIntoMap (Grid3d.cpp:365-372); *inside = 0 when no map is set */
+int amcl3d_b200_grid_is_into_map(amcl3d_b200_grid_t g, float x, float y, float z, int* inside);
+/* Grid3d::computeCloudWeight 7-arg (Grid3d.cpp:234-301) for one pose; *weight = 0 when the grid or
+ * the map is missing (Grid3d.cpp:237-238) */
+int amcl3d_b200_grid_cloud_weight(amcl3d_b200_grid_t g, const float* cloud, uint32_t stride, uint32_t npts,
+                                  float tx, float ty, float tz, float roll, float pitch, float yaw,
+                                  int trig_mode, float* weight);
+/* raw device pointer of the cells (for callers that keep data resident, e.g. NCCL broadcast) */
+int amcl3d_b200_grid_device_ptr(amcl3d_b200_grid_t g, void** d_prob);
+
+/* ---- ParticleFilter (amcl3d/src/ParticleFilter.{h,cpp}) -------------------------------------- */
+int amcl3d_b200_pf_create(amcl3d_b200_grid_t g, amcl3d_b200_pf_t* out);
+int amcl3d_b200_pf_destroy(amcl3d_b200_pf_t pf);
+int amcl3d_b200_pf_set_trig_mode(amcl3d_b200_pf_t pf, int trig_mode);
+/* run this handle's kernels on a caller-owned cudaStream_t (NULL = the handle's own stream) */
+int amcl3d_b200_pf_set_stream(amcl3d_b200_pf_t pf, void* cuda_stream);
+
+/* p_ mirror: host <-> device copies of the particle set */
+int amcl3d_b200_pf_set_particles(amcl3d_b200_pf_t pf, const float* aos7, uint64_t n);
+int amcl3d_b200_pf_get_particles(amcl3d_b200_pf_t pf, float* aos7, uint64_t cap, uint64_t* n);
+int amcl3d_b200_pf_size(amcl3d_b200_pf_t pf, uint64_t* n);
+/* adopt a caller-owned DEVICE buffer of `capacity` particles as p_ (e.g. a torch tensor that also
+ * takes part in NCCL collectives); n of them are live.  The handle never frees it. */
+int amcl3d_b200_pf_bind_device(amcl3d_b200_pf_t pf, void* d_aos7, uint64_t n, uint64_t capacity);
+int amcl3d_b200_pf_device_ptr(amcl3d_b200_pf_t pf, void** d_aos7, uint64_t* n);
+
+/* the sensor cloud: copied H2D and packed (x,y,z,0) per point for the kernels */
+int amcl3d_b200_pf_set_cloud(amcl3d_b200_pf_t pf, const float* cloud, uint32_t stride, uint32_t npts);
+/* same from a DEVICE buffer (no host round trip) */
+int amcl3d_b200_pf_set_cloud_device(amcl3d_b200_pf_t pf, const void* d_cloud, uint32_t stride, uint32_t npts);
+
+/* ParticleFilter::update(cloud) (ParticleFilter.cpp:114-139) on the cloud set above: w = 0 outside the
+ * map, else computeCloudWeight.  With nb > 0 the range-only beacon weight (row R of SURVEY 8(a);
+ * not present in the reference tree) is evaluated in the same kernel and fused as
+ * w = alpha*wp/sum(wp) + (1-alpha)*wr/sum(wr).  in_bounds (optional) receives the number of
+ * particle x point evaluations that loaded a voxel. */
+int amcl3d_b200_pf_update(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beacons, uint32_t nb, float alpha,
+                          float sigma, uint64_t* in_bounds);
+/* convenience: set_cloud + update */
+int amcl3d_b200_pf_update_cloud(amcl3d_b200_pf_t pf, const float* cloud, uint32_t stride, uint32_t npts);
+
+/* ParticleFilter::particleNormalize (ParticleFilter.cpp:168-196); wtp (optional) = the f32 sum */
+int amcl3d_b200_pf_normalize(amcl3d_b200_pf_t pf, float* wtp);
+/* MonteCarloLocalization::addParticleWeight (amcl3d.cpp:205-217): w *= 1/max(w) */
+int amcl3d_b200_pf_scale_by_max(amcl3d_b200_pf_t pf);
+
+/* ParticleFilter::resample (ParticleFilter.cpp:230-254) with r = (1/N)*u01.  Bit-exact indices:
+ * the inclusive prefix is the reference's sequential f32 chain.  Outputs [m0, m1) only are produced
+ * (m1 = 0 means N): d_out (optional, DEVICE, (m1-m0) particles) receives them, otherwise p_ is replaced
+ * (requires m0 = 0, m1 = N).  idx (optional, HOST, m1-m0 ints) receives the source indices.  The
+ * reference's read past the end (ParticleFilter.cpp:244-248) is clamped to N-1. */
+int amcl3d_b200_pf_resample(amcl3d_b200_pf_t pf, float u01, uint64_t m0, uint64_t m1, void* d_out, int32_t* idx);
+
+/* ParticleFilter::uniformSample (ParticleFilter.cpp:256-280): normalise, then S outputs at thresholds
+ * 0.5/S + k/S (sequential f32 chain), first index with prefix > threshold.  Outputs [k0, k1) (k1 = 0
+ * means S) go to d_out (DEVICE) or replace p_ (then size becomes S, requires k0 = 0, k1 = S); the tail
+ * that the reference leaves as zero particles is zero here too, idx = -1 there.  emitted (optional). */
+int amcl3d_b200_pf_uniform_sample(amcl3d_b200_pf_t pf, int sample_num, uint64_t k0, uint64_t k1, void* d_out,
+                                  int32_t* idx, int* emitted);
+
+/* ParticleFilter::getMean (ParticleFilter.cpp:198-216): exact != 0 replays the sequential f32 sums,
+ * otherwise a deterministic f64 tree reduction of the f32 products.  out7 = x..yaw, w = max weight */
+int amcl3d_b200_pf_mean(amcl3d_b200_pf_t pf, int exact, float out7[7]);
+/* ParticleFilter::getBestParticle (ParticleFilter.cpp:218-228): first arg-max with w > 0 */
+int amcl3d_b200_pf_best(amcl3d_b200_pf_t pf, float out7[7]);
+
+/* ParticleFilter::predict (ParticleFilter.cpp:91-112) with caller-supplied noise: 6 floats per
+ * particle in draw order x,y,z,roll,pitch,yaw (what ranGaussian returned), HOST memory */
+int amcl3d_b200_pf_predict(amcl3d_b200_pf_t pf, const double delta[6], const float* noise6);
+
+/* sequential f32 inclusive prefix of the current weights (ParticleFilter.cpp:259-264), for tests and
+ * for multi-GPU callers: DEVICE pointer valid until the next call on the handle */
+int amcl3d_b200_pf_prefix(amcl3d_b200_pf_t pf, void** d_prefix, float* host_out, uint64_t cap);
+
+/* device time in ms of the kernels of the last update / normalize / resample / uniform_sample /
+ * mean call on this handle, measured with CUDA events on the handle's stream */
+int amcl3d_b200_pf_last_kernel_ms(amcl3d_b200_pf_t pf, float* ms);
+/* kernels launched by this handle since creation */
+int amcl3d_b200_pf_launch_count(amcl3d_b200_pf_t pf, uint64_t* launches);
+
+/* ---- measurement helpers ------------------------------------------------------------------ */
+/* random-sector gather micro-benchmark used to state the gather roofline: every thread
+ * of `blocks x 256` does `iters` x 8 independent 4-byte loads at hashed indices inside
+ * [0, window_cells) of the grid's cells; returns device ms and the number of loads issued.
+ * via_tex != 0 is reserved. */
+int amcl3d_b200_bench_gather(amcl3d_b200_grid_t g, uint64_t window_cells, uint32_t blocks, uint32_t iters,
+                             int coherent, float* ms, uint64_t* loads);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,113 @@
+"""Grid build parity: exact EDT (bit-exact integer distances), fused Gaussian, splat, .grid files."""
+import numpy as np
+import pytest
+
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_map(O, seed=3, extent=(6.4, 5.0, 3.1), resol=0.1, n=900, lattice="centre"):
+    rng = np.random.RandomState(seed)
+    size = np.round(np.array(extent) / resol).astype(int)
+    vox = np.stack([rng.randint(0, size[a], n) for a in range(3)], 1)
+    if lattice == "centre":
+        pts = (vox + 0.5) * resol
+    elif lattice == "corner":
+        pts = vox * resol
+    else:  # mixed half-lattice
+        pts = (vox + rng.randint(0, 2, (n, 3)) * 0.5) * resol
+    pts = np.concatenate([[[0, 0, 0], list(extent)], pts]).astype(np.float32)
+    mn, mx = O.compute_bounds(pts)
+    return pts, O.Map(mn, mx, resol, 0.05)
+
+
+@pytest.mark.parametrize("lattice,sub", [("centre", 2), ("corner", 1), ("corner", 2), ("mixed", 2)])
+def test_edt_bit_exact_small(O, lattice, sub):
+    from amcl3d_test_b200 import Grid3d
+
+    pts, m = _small_map(O, lattice=lattice)
+    ref = O.edt_exact(m, pts, sub=sub)
+    brute = O.edt_brute(m, pts, sub=sub)
+    assert np.array_equal(ref, brute)
+    g = Grid3d(0)
+    g.computePointCloud(pts, m.resol)
+    assert g.info()["size"] == m.size
+    g.computeGrid(pts, 0.05, mode=O.GRID_QUIRK, sub=sub, keep_edt=True)
+    assert np.array_equal(g.edt(), ref)
+    prob = g.downloadGrid()
+    ref_prob = O.grid_from_edt(m, ref, sub, O.GRID_QUIRK)
+    assert np.allclose(prob, ref_prob, rtol=1e-6, atol=1e-30)
+    assert np.array_equal(prob == 0, ref_prob == 0)
+
+
+def test_edt_c1_map(O, world_c1):
+    from amcl3d_test_b200 import Grid3d
+
+    w = world_c1
+    g = Grid3d(0)
+    mn, mx = g.computePointCloud(w["synth"].points, 0.1)
+    assert np.array_equal(mn, w["map"].mn) and np.array_equal(mx, w["map"].mx)
+    g.computeGrid(w["synth"].points, 0.05, sub=2, keep_edt=True)
+    assert np.array_equal(g.edt(), w["d2"])
+    assert np.allclose(g.downloadGrid(), w["prob"], rtol=1e-6, atol=1e-30)
+    # gaussian (non-quirk) mode
+    g.computeGrid(w["synth"].points, 0.05, mode=O.GRID_GAUSSIAN, sub=2)
+    assert np.allclose(g.downloadGrid(), O.grid_from_edt(w["map"], w["d2"], 2, O.GRID_GAUSSIAN), rtol=1e-6, atol=1e-30)
+
+
+def test_edt_empty_rows_and_single_site(O):
+    from amcl3d_test_b200 import Grid3d
+
+    pts = np.array([[0, 0, 0], [3.2, 2.0, 1.0], [1.05, 0.55, 0.35]], np.float32)  # two corners + one centre site
+    mn, mx = O.compute_bounds(pts)
+    m = O.Map(mn, mx, 0.1, 0.05)
+    ref = O.edt_exact(m, pts, sub=2)
+    g = Grid3d(0)
+    g.computePointCloud(pts, 0.1)
+    g.computeGrid(pts, 0.05, sub=2, keep_edt=True)
+    assert np.array_equal(g.edt(), ref)
+    # dense single class with whole empty rows/planes
+    rng = np.random.RandomState(0)
+    wall = np.stack([np.full(400, 7), rng.randint(0, 20, 400), rng.randint(0, 10, 400)], 1)
+    pts2 = np.concatenate([pts[:2], (wall + 0.5) * 0.1]).astype(np.float32)
+    ref2 = O.edt_exact(m, pts2, sub=2)
+    g.computeGrid(pts2, 0.05, sub=2, keep_edt=True)
+    assert np.array_equal(g.edt(), ref2)
+
+
+def test_splat_matches_compute_grid2(O, world_c1):
+    from amcl3d_test_b200 import Grid3d
+
+    rng = np.random.RandomState(9)
+    pts = (rng.uniform(0, 1, (5000, 3)) * [8.0, 6.0, 3.0]).astype(np.float32)  # arbitrary (off-lattice) points
+    mn, mx = O.compute_bounds(pts)
+    m = O.Map(mn, mx, 0.3, 0.05)  # Grid3d.cpp:156 hard-codes 0.3
+    ref = O.compute_grid2(m, pts)
+    g = Grid3d(0)
+    g.computePointCloud(pts, 0.3)
+    g.computeGrid(pts, 0.05, mode=O.GRID_SPLAT)
+    got = g.downloadGrid()
+    assert np.array_equal(got == 0, ref == 0)
+    assert np.allclose(got, ref, rtol=1e-6, atol=1e-30)
+
+
+def test_grid_file_roundtrip(O, world_c1, gpu_c1, tmp_path):
+    from amcl3d_test_b200 import Grid3d
+
+    w = world_c1
+    path = tmp_path / "cloud.grid"
+    assert gpu_c1.saveGrid(path)
+    # byte-identical to the oracle's writer (Grid3d.cpp:388-395 format)
+    ref_path = tmp_path / "ref.grid"
+    assert O.save_grid(ref_path, w["map"]) == 0
+    assert path.read_bytes() == ref_path.read_bytes()
+    g = Grid3d(0)
+    g.setMap(w["map"].mn, w["map"].mx, 0.1)
+    assert g.loadGrid(path, 0.05)
+    assert np.array_equal(bits(g.downloadGrid()), bits(w["prob"]))
+    assert g.info()["size"] == w["map"].size
+    assert not g.loadGrid(path, 0.06)  # Grid3d.cpp:422-427
+    assert not g.loadGrid(tmp_path / "missing.grid", 0.05)
+    with pytest.raises(RuntimeError):
+        g.computePointCloud(np.zeros((1, 3), np.float32), 0.1)  # PointCloudTools.cpp:89-91

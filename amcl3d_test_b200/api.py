@@ -133,7 +133,7 @@ class Grid3d:
 
     def bench_gather(self, window_cells=0, blocks=148 * 8, iters=64, coherent=False):
         ms, loads = C.c_float(0), C.c_uint64(0)
-        check(self._L.amcl3d_b200_bench_gather(self._h, int(window_cells), blocks, iters, int(coherent), C.byref(ms), C.byref(loads)))
+        check(self._L.amcl3d_b200_bench_gather(self._h, int(window_cells), blocks, iters, int(coherent) if not isinstance(coherent, bool) else int(coherent), C.byref(ms), C.byref(loads)))
         return ms.value, loads.value
 
 

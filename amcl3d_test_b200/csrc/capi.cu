@@ -214,6 +214,28 @@ int amcl3d_b200_device_info(int device, int* device_count, int* sm_count, int* c
   return AMCL3D_B200_OK;
 }
 
+int amcl3d_b200_set_l2_fetch_granularity(int device, int bytes)
+{
+  if (bytes != 32 && bytes != 64 && bytes != 128)
+    return fail(AMCL3D_B200_ERR_ARG, "granularity must be 32, 64 or 128");
+  if (int rc = use_device(device))
+    return rc;
+  CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_get_l2_fetch_granularity(int device, int* bytes)
+{
+  if (!bytes)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  if (int rc = use_device(device))
+    return rc;
+  size_t v = 0;
+  CU(cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity));
+  *bytes = (int)v;
+  return AMCL3D_B200_OK;
+}
+
 /* ============================================ Grid3d ============================================ */
 
 int amcl3d_b200_grid_create(int device, amcl3d_b200_grid_t* out)

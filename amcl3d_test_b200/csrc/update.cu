@@ -355,9 +355,11 @@ __device__ __forceinline__ uint64_t splitmix(uint64_t& s)
 }
 
 __global__ void __launch_bounds__(256)
-    gather_bench_kernel(const float* __restrict__ cells, uint64_t window, uint32_t iters, int coherent,
+    gather_bench_kernel(const float* __restrict__ cells, uint64_t window, uint32_t iters, int mode,
                         float* __restrict__ sink)
 {
+  const int coherent = mode & 1;
+  const int flavor = mode >> 1;  // which load instruction (development probe)
   const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t s = gtid * 0x632BE59BD9B4E019ull + 12345;
   float acc = 0.f;
@@ -382,7 +384,20 @@ __global__ void __launch_bounds__(256)
     float v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u)
-      v[u] = __ldg(cells + idx[u]);
+    {
+      const float* a = cells + idx[u];
+      switch (flavor)
+      {
+        case 1: asm volatile("ld.global.ca.f32 %0, [%1];" : "=f"(v[u]) : "l"(a)); break;
+        case 2: asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v[u]) : "l"(a)); break;
+        case 3: asm volatile("ld.global.cv.f32 %0, [%1];" : "=f"(v[u]) : "l"(a)); break;
+        case 4: asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v[u]) : "l"(a)); break;
+        case 5: asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v[u]) : "l"(a)); break;
+        case 6: asm volatile("ld.global.L1::evict_first.f32 %0, [%1];" : "=f"(v[u]) : "l"(a)); break;
+        case 7: asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v[u]) : "l"(a)); break;
+        default: v[u] = __ldg(a); break;
+      }
+    }
 #pragma unroll
     for (int u = 0; u < 8; ++u)
       acc += v[u];

@@ -1,0 +1,121 @@
+"""Particles sharded across the GPUs of one box; one process per GPU, torch.distributed.
+
+Partitioning: the grid is replicated, rank r owns the contiguous block [r*n_local, (r+1)*n_local) of the
+global particle order (contiguous blocks keep the order the reference's serial prefix needs).  The update
+is embarrassingly parallel (no collective).  Normalise + resample has one real exchange step: an
+all-gather of the freshly weighted particle blocks (28 B x N over NVLink); every rank then replays the
+reference's sequential f32 chains over the full set -- so weights, prefix and resampled indices are
+bit-identical to the 1-GPU / CPU result -- and produces only its own slice [m0, m1) of the output.
+The mean is a sum of per-rank partial means (all-reduce of 7 floats).
+
+The collective plumbing is backend-agnostic so that the same orchestration is exercised on CPU with gloo
+(tests/test_sharded_gloo.py, compute supplied by the test) and on GPUs with NCCL (CudaShard below).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_total: int, world: int, rank: int):
+    """Contiguous block partition; the first (n_total % world) ranks get one extra particle."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ShardedFilter:
+    """Orchestration only.  `shard` supplies the compute on this rank's memory:
+
+    shard.local  : tensor (n_local, 7)   this rank's particle block (weights in column 6)
+    shard.full   : tensor (N, 7)         gather target, same device
+    shard.update()                                   -> weights of shard.local
+    shard.normalize_full()                           -> particleNormalize over shard.full, returns wtp
+    shard.resample_full(u01, m0, m1)                 -> writes outputs [m0, m1) into shard.local
+    shard.uniform_full(S, k0, k1) -> (emitted)       -> writes outputs [k0, k1) into shard.local_out(S)
+    shard.mean_local()                               -> 7 floats (weighted sums over shard.local, max w)
+    """
+
+    def __init__(self, shard, n_total: int, group=None):
+        self.shard = shard
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_total = n_total
+        self.lo, self.hi = shard_bounds(n_total, self.world, self.rank)
+        assert shard.local.shape[0] == self.hi - self.lo
+
+    # -- exchange step -----------------------------------------------------------------------------
+    def gather(self):
+        full, local = self.shard.full, self.shard.local
+        if self.world == 1:
+            full.copy_(local)
+            return
+        if self.n_total % self.world == 0:
+            dist.all_gather_into_tensor(full, local, group=self.group)
+        else:  # ragged blocks: gather a list
+            parts = []
+            for r in range(self.world):
+                lo, hi = shard_bounds(self.n_total, self.world, r)
+                parts.append(full[lo:hi])
+            dist.all_gather(parts, local, group=self.group)
+
+    # -- the path ----------------------------------------------------------------------------------
+    def update(self):
+        self.shard.update()
+
+    def resample(self, u01: float):
+        """update() must have run.  Global ParticleFilter::particleNormalize + resample, bit-exact."""
+        self.gather()
+        wtp = self.shard.normalize_full()
+        self.shard.resample_full(u01, self.lo, self.hi)
+        return wtp
+
+    def mean(self):
+        part = torch.as_tensor(np.asarray(self.shard.mean_local(), np.float64))
+        if self.world > 1:
+            dev = self.shard.local.device
+            sums = part[:6].to(dev)
+            wmax = part[6:].to(dev)
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(wmax, op=dist.ReduceOp.MAX, group=self.group)
+            part = torch.cat([sums, wmax]).cpu()
+        return part.numpy().astype(np.float32)
+
+
+class CudaShard:
+    """This rank's CUDA state: a grid replica, the local block and the gather target as torch tensors
+    bound (zero-copy) to two C-ABI ParticleFilter handles."""
+
+    def __init__(self, grid3d, n_local: int, n_total: int, device: torch.device):
+        from .api import ParticleFilter
+
+        self.device = device
+        self.local = torch.zeros((n_local, 7), dtype=torch.float32, device=device)
+        self.full = torch.zeros((n_total, 7), dtype=torch.float32, device=device)
+        self.pf_local = ParticleFilter(grid3d)
+        self.pf_full = ParticleFilter(grid3d)
+        self.pf_local.bind_device(self.local.data_ptr(), n_local, n_local, keep=self.local)
+        self.pf_full.bind_device(self.full.data_ptr(), n_total, n_total, keep=self.full)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        self.pf_local.set_stream(stream)
+        self.pf_full.set_stream(stream)
+
+    def set_cloud(self, cloud):
+        self.pf_local.set_cloud(cloud)
+
+    def update(self):
+        self.pf_local.update()
+
+    def normalize_full(self):
+        return self.pf_full.particleNormalize()
+
+    def resample_full(self, u01, m0, m1):
+        self.pf_full.resample(u01, m0=m0, m1=m1, d_out=self.local.data_ptr())
+
+    def mean_local(self):
+        return self.pf_local.getMean(exact=False)
+
+    def launch_count(self):
+        return self.pf_local.launch_count() + self.pf_full.launch_count()

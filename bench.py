@@ -1,0 +1,450 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the amcl3d particle-weighting path on B200.
+
+Metric (BASELINE.json): particle x point weight evaluations per second; one step = one pass of the hot
+path over one batch of synthetic input = ParticleFilter::update over the whole cloud, then
+particleNormalize + resample (bit-exact sequential chains) + getMean.
+Workload at N=1: BASELINE config 3 -- 100 k particles x 10 k-point cloud on the config-2 map
+(100 x 100 x 20 m at 0.05 m = 2000 x 2000 x 400 voxels, 6.4 GB float grid built on the GPU by the exact
+EDT + fused Gaussian writer).  At N>1 every rank holds a grid replica and its own 100 k-particle block
+(weak scaling); normalise/resample is global and bit-exact (all-gather + replicated sequential chain).
+
+  python bench.py --gpus 1 --steps 20 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...      (the reference's own CPU implementation, oracle/_ref)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "particle_x_point_weight_evals_per_sec"
+UNIT = "evals/s"
+
+WORKLOADS = {
+    # name: (map extent m, resol, particles per GPU, cloud points, cloud radius)
+    "C3": ((100.0, 100.0, 20.0), 0.05, 100_000, 10_000, 30.0),
+    "C3-small": ((50.0, 50.0, 10.0), 0.05, 100_000, 10_000, 22.0),
+    "C4": ((100.0, 100.0, 20.0), 0.05, 1_000_000, 20_000, 30.0),  # particles are the TOTAL here (strong)
+    "C1": ((20.0, 20.0, 5.0), 0.1, 600, 2_000, 12.0),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--particles", default="T", choices=["T", "G"], help="tracking cluster / global uniform")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        mhz = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": mhz, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_inputs(workload: str, kind: str, n_particles: int, seed_shift: int = 0):
+    from amcl3d_test_b200 import synth
+
+    extent, resol, _, n_pts, radius = WORKLOADS[workload]
+    sm = synth.make_map(extent, resol)
+    cloud = synth.make_cloud(sm, n_pts, radius)
+    P = synth.make_particles(sm, n_particles, kind, seed=synth.SEED_PARTICLES + seed_shift)
+    return sm, cloud, P
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms (checker code paths: only here, in tests/ and in smoke())
+# ------------------------------------------------------------------------------------------------
+def cpu_grid(sm, resol):
+    """Likelihood field for the CPU arms, built by the oracle's exact EDT on a crop around the ground
+    truth (the CPU arms only ever look up voxels there; building 1.6e9 voxels on the host is pointless)."""
+    from oracle import loader as O
+
+    mn, mx = O.compute_bounds(sm.points)
+    return O, O.Map(mn, mx, resol, 0.05)
+
+
+def cpu_update_resample(O, m, ref_pf_factory, P, cloud, u01, threads):
+    """One CPU step on particle block P: update (threads shards) + normalise + resample + mean."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    t0 = time.perf_counter()
+    if ref_pf_factory is not None:
+        shards = np.array_split(np.arange(P.shape[0]), threads)
+
+        def work(ix):
+            pf = ref_pf_factory()
+            pf.set(P[ix])
+            pf.update(cloud)
+            return pf.get()
+
+        with ThreadPoolExecutor(threads) as ex:
+            parts = list(ex.map(work, shards))
+        W = np.concatenate(parts, 0)
+        t1 = time.perf_counter()
+        pf = ref_pf_factory()
+        pf.set(W)
+        pf.normalize()
+        pf.seed(4004)
+        pf.resample()
+        pf.mean()
+    else:
+        W = O.update(m, O.particles(P), cloud, threads=threads)
+        t1 = time.perf_counter()
+        O.normalize(m, W)
+        out, _ = O.resample(W, u01)
+        O.mean(out)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def cpu_arm_setup(workload, kind):
+    """Shared set-up of cpu_baseline and --impl reference: full-size map grid is too large for the host
+    oracle to build, so the CPU arms run on the same synthetic office built at the same resolution but
+    cropped to the cloud radius around the ground-truth pose (identical voxels where the cloud lands)."""
+    from amcl3d_test_b200 import synth
+    from oracle import loader as O
+
+    extent, resol, _, n_pts, radius = WORKLOADS[workload]
+    crop = tuple(min(e, 2 * radius + 10.0) for e in extent)
+    sm = synth.make_map(crop, resol)
+    cloud = synth.make_cloud(sm, n_pts, min(radius, min(crop[:2]) / 2 - 1.0))
+    mn, mx = O.compute_bounds(sm.points)
+    m = O.Map(mn, mx, resol, 0.05)
+    d2 = O.edt_exact(m, sm.points, sub=2)
+    m.set_prob(O.grid_from_edt(m, d2, 2, O.GRID_QUIRK))
+    factory, kind_name = None, "port"
+    if O.ref_available():
+        try:
+            rg = O.RefGrid(m)
+            factory = lambda: O.RefPF(rg)  # noqa: E731
+            factory()
+            kind_name = "reference"
+        except Exception:
+            factory = None
+    return O, sm, m, cloud, factory, kind_name
+
+
+def run_cpu_sample(workload, kind, n_sample, threads, reps=1, setup=None):
+    from amcl3d_test_b200 import synth
+
+    O, sm, m, cloud, factory, kind_name = setup or cpu_arm_setup(workload, kind)
+    P = synth.make_particles(sm, n_sample, kind)
+    u01 = float(synth.resample_offset())
+    best = None
+    for _ in range(reps):
+        tu, tr = cpu_update_resample(O, m, factory, P, cloud, u01, threads)
+        if best is None or tu + tr < best[0] + best[1]:
+            best = (tu, tr)
+    evals = n_sample * cloud.shape[0]
+    return dict(evals=evals, t_update=best[0], t_resample=best[1], kind=kind_name, n_sample=n_sample,
+                n_pts=int(cloud.shape[0]))
+
+
+def cpu_baseline(workload, kind, target_seconds):
+    threads = os.cpu_count() or 1
+    setup = cpu_arm_setup(workload, kind)
+    cal = run_cpu_sample(workload, kind, 64 * threads, threads, setup=setup)
+    rate = cal["evals"] / (cal["t_update"] + cal["t_resample"])
+    n_pts = cal["n_pts"]
+    n_sample = int(max(64 * threads, min(200_000, target_seconds * rate / n_pts)))
+    r = run_cpu_sample(workload, kind, n_sample, threads, setup=setup)
+    t = r["t_update"] + r["t_resample"]
+    return {
+        "value": r["evals"] / t, "unit": UNIT, "cores": threads, "kind": r["kind"],
+        "sample": f"{n_sample} particles x {n_pts} points of the {workload} workload ({kind} particles), "
+                  f"update {r['t_update']*1e3:.0f} ms + normalise/resample/mean {r['t_resample']*1e3:.0f} ms, "
+                  f"{threads} host threads over particle shards; scales linearly in particles",
+        "update_ms": r["t_update"] * 1e3, "resample_ms": r["t_resample"] * 1e3,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    setup = cpu_arm_setup(args.workload, args.particles)
+    cal = run_cpu_sample(args.workload, args.particles, 32 * threads, threads, setup=setup)
+    rate = cal["evals"] / (cal["t_update"] + cal["t_resample"])
+    n_pts = cal["n_pts"]
+    per_step_s = 2.0  # bounded sample per step so steps+warmup ends within minutes
+    n_sample = int(max(32 * threads, min(100_000, per_step_s * rate / n_pts)))
+    times = []
+    for s in range(args.warmup + args.steps):
+        r = run_cpu_sample(args.workload, args.particles, n_sample, threads, setup=setup)
+        if s >= args.warmup:
+            times.append(r["t_update"] + r["t_resample"])
+    total = float(np.sum(times))
+    value = n_sample * n_pts * len(times) / total
+    extent, resol, _, _, _ = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {n_sample}-particle bounded sample of the per-GPU block x {n_pts} points, "
+                               f"{args.particles} particles, map cropped to the cloud radius at {resol} m",
+                   "particles_kind": args.particles},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": r["kind"],
+                         "sample": f"{n_sample} particles x {n_pts} points per step, {threads} host threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from amcl3d_test_b200 import Grid3d, ParticleFilter, synth
+    from amcl3d_test_b200.sharded import CudaShard, ShardedFilter
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    extent, resol, n_per_gpu, n_pts, radius = WORKLOADS[args.workload]
+    strong = args.workload == "C4"
+    n_total = n_per_gpu if strong else n_per_gpu * world
+    lo = (n_total // world) * rank
+    n_local = n_total // world
+    assert n_total % world == 0
+
+    t_setup = time.time()
+    sm = synth.make_map(extent, resol)
+    cloud = synth.make_cloud(sm, n_pts, radius)
+    P_all = synth.make_particles(sm, n_total, args.particles)
+    P = np.ascontiguousarray(P_all[lo:lo + n_local])
+    u01 = float(synth.resample_offset())
+
+    grid = Grid3d(local_rank)
+    grid.computePointCloud(sm.points, resol)
+    tb = time.time()
+    grid.computeGrid(sm.points, 0.05, sub=2)
+    grid_build_s = time.time() - tb
+    info = grid.info()
+    del sm.points  # free host memory
+
+    shard = CudaShard(grid, n_local, n_total, device)
+    filt = ShardedFilter(shard, n_total)
+    backup = torch.from_numpy(P).to(device)
+    shard.set_cloud(cloud)
+    stream = torch.cuda.current_stream(device)
+
+    def step():
+        shard.local.copy_(backup)       # same workload every step (resampling collapses the set)
+        filt.update()
+        filt.resample(u01)
+        return filt.mean()
+
+    # in-bounds count of this workload (for the roofline's algorithmic bytes)
+    shard.local.copy_(backup)
+    n_in = shard.pf_local.update(count=True)
+    upd_ms = []
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = shard.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        shard.local.copy_(backup)
+        filt.update()
+        upd_ms.append(shard.pf_local.last_kernel_ms())
+        filt.resample(u01)
+        filt.mean()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    launches = shard.launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    evals_step = n_total * n_pts
+    value = evals_step / (ms_step * 1e-3)
+
+    # ---- end to end through the public API with host buffers (pinned), every step ---------------------
+    pin_p = torch.from_numpy(P).pin_memory()
+    pin_c = torch.from_numpy(cloud).pin_memory()
+    pin_out = torch.empty((n_local, 7), dtype=torch.float32).pin_memory()
+    pf = ParticleFilter(grid)
+    pf.set_stream(stream.cuda_stream)
+
+    def e2e_step():
+        pf.p_ = pin_p.numpy()               # H2D particles
+        pf.update(pin_c.numpy())            # H2D cloud + K3
+        pf.particleNormalize()
+        pf.resample(u01)
+        got = pf.p_                         # D2H resampled set
+        pin_out.numpy()[...] = got
+        return pf.getMean()                 # D2H 7 floats
+
+    for _ in range(max(1, args.warmup)):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([wall], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+    e2e_value = evals_step * args.steps / wall   # per-rank API calls are independent: whole job = all ranks
+    h2d = int(pin_p.numel() * 4 + pin_c.numel() * 4)
+    d2h = int(pin_out.numel() * 4 + 28)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    upd = float(np.mean(upd_ms))
+    achieved = n_in * 32.0 / (upd * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload}: {n_local} particles/GPU x {n_pts}-point cloud, map {extent[0]:g}x{extent[1]:g}x{extent[2]:g} m "
+                        f"at {resol} m = {info['size'][0]}x{info['size'][1]}x{info['size'][2]} voxels "
+                        f"({info['n_cells']*4/1e9:.2f} GB grid replica per GPU), step = update + normalise + resample + mean",
+            "particles_kind": args.particles, "particles_total": n_total, "points": n_pts,
+            "l2": "inputs larger than L2 (grid replica >> 126 MB), no flush",
+            "in_bounds_fraction": n_in / (n_local * n_pts),
+            "grid_build_s_incl_h2d": grid_build_s,
+        },
+        "update_ms": upd, "resample_mean_ms": ms_step - upd,
+        "update_evals_per_sec": n_local * n_pts / (upd * 1e-3) * world,
+        "roofline": {
+            "bound": "hbm", "kernel": "update_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": n_in * 32,
+            "note": "32 B sector per in-bounds particle x point evaluation (SURVEY 8(d)); duration = CUDA events around the kernel on its launch stream",
+        },
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": wall / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "setup_s": time.time() - t_setup,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline(args.workload, args.particles, args.cpu_seconds)
+        except Exception as e:  # the checker must never take the product's number down with it
+            line["cpu_baseline"] = {"error": repr(e)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

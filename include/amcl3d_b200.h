@@ -86,6 +86,12 @@ const char* amcl3d_b200_last_error(void);
 int amcl3d_b200_device_info(int device, int* device_count, int* sm_count, int* cc_major, int* cc_minor,
                             uint64_t* l2_bytes, uint64_t* mem_bytes);
 
+/* cudaLimitMaxL2FetchGranularity of the current context (32, 64 or 128 bytes).  The weighting kernel
+ * consumes 4 bytes per 32-byte sector at scattered addresses, so anything above 32 only multiplies
+ * DRAM traffic; grid_create sets 32 unless AMCL3D_B200_L2_FETCH is set in the environment. */
+int amcl3d_b200_set_l2_fetch_granularity(int device, int bytes);
+int amcl3d_b200_get_l2_fetch_granularity(int device, int* bytes);
+
 /* ---- Grid3d (amcl3d/src/Grid3d.{h,cpp}, PointCloudTools.{h,cpp}) ---------------------------- */
 int amcl3d_b200_grid_create(int device, amcl3d_b200_grid_t* out);
 int amcl3d_b200_grid_destroy(amcl3d_b200_grid_t g);

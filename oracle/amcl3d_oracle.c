@@ -787,8 +787,8 @@ int orc_edt_exact(const orc_map* m, const float* xyz, uint32_t stride, uint64_t 
     d2out[i] = EDT_INF;
 
   uint8_t* occ = (uint8_t*)malloc(wcells);
-  int64_t* a = (int64_t*)malloc(sizeof(int64_t) * (size_t)sx * wy * wz); /* after x pass: [wz][wy][sx] */
-  int64_t* b = (int64_t*)malloc(sizeof(int64_t) * (size_t)sx * sy * wz); /* after y pass: [wz][sy][sx] */
+  int32_t* a = (int32_t*)malloc(sizeof(int32_t) * (size_t)sx * wy * wz); /* after x pass: [wz][wy][sx] */
+  int32_t* b = (int32_t*)malloc(sizeof(int32_t) * (size_t)sx * sy * wz); /* after y pass: [wz][sy][sx] */
   if (!occ || !a || !b)
     return -2;
 
@@ -841,7 +841,8 @@ int orc_edt_exact(const orc_map* m, const float* xyz, uint32_t stride, uint64_t 
         for (int j = 0; j < wx; ++j)
           g[j] = r[j] ? 0 : (int64_t)EDT_INF;
         envelope_1d(g, wx, step, px, o, sx, v, z);
-        memcpy(a + (size_t)row * sx, o, sizeof(int64_t) * (size_t)sx);
+        for (int i = 0; i < sx; ++i)
+          a[(size_t)row * sx + i] = (int32_t)o[i];
       }
       /* y pass: columns (ix, jz) over jy -> queries iy */
 #pragma omp for schedule(static)
@@ -853,7 +854,7 @@ int orc_edt_exact(const orc_map* m, const float* xyz, uint32_t stride, uint64_t 
           g[j] = a[((size_t)jz * wy + j) * sx + ixx];
         envelope_1d(g, wy, step, py, o, sy, v, z);
         for (int i = 0; i < sy; ++i)
-          b[((size_t)jz * sy + i) * sx + ixx] = o[i];
+          b[((size_t)jz * sy + i) * sx + ixx] = (int32_t)o[i];
       }
       /* z pass: columns (ix, iy) over jz -> queries iz, min-combined across parity classes */
 #pragma omp for schedule(static)

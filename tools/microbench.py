@@ -27,7 +27,21 @@ def main():
     g.computeGrid(sm.points, 0.05, sub=2)
     print(f"grid build (incl. H2D of points) {time.time()-t:.3f}s")
     out = {}
-    for win_mb in (8, 64, 512, 0):
+    import ctypes as C
+    from amcl3d_test_b200 import capi
+    L = capi.load()
+    cur = C.c_int(0); L.amcl3d_b200_get_l2_fetch_granularity(0, C.byref(cur)); print("default L2 fetch granularity", cur.value)
+    for gran in (128, 64, 32):
+        print("set granularity", gran, "rc", L.amcl3d_b200_set_l2_fetch_granularity(0, gran))
+        ms, loads = g.bench_gather(window_cells=0, blocks=148 * 8, iters=256, coherent=False)
+        print(f"  random gather over whole grid: {loads/ms/1e6:.1f} G loads/s")
+        ms, loads = g.bench_gather(window_cells=0, blocks=148 * 8, iters=256, coherent=True)
+        print(f"  coherent gather over whole grid: {loads/ms/1e6:.1f} G loads/s")
+    for flavor, name in enumerate(["ldg.nc", "ld.ca", "ld.cg", "ld.cv", "nc.noalloc", "ld.noalloc", "evict_first", "ld.cs"]):
+        ms, loads = g.bench_gather(window_cells=0, blocks=148 * 8, iters=256, coherent=flavor << 1)
+        ms2, loads2 = g.bench_gather(window_cells=0, blocks=148 * 8, iters=256, coherent=(flavor << 1) | 1)
+        print(f"flavor {name}: random {loads/ms/1e6:.1f} G/s, coherent {loads2/ms2/1e6:.1f} G/s")
+    for win_mb in (8, 0):
         cells = win_mb * (1 << 20) // 4
         for coh in (0, 1):
             ms, loads = g.bench_gather(window_cells=cells, blocks=148 * 8, iters=256, coherent=bool(coh))

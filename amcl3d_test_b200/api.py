@@ -53,7 +53,12 @@ class Grid3d:
         check(self._L.amcl3d_b200_grid_get_info(self._h, C.byref(gi)))
         return dict(min=np.array(list(gi.min)), max=np.array(list(gi.max)), resol=gi.resol, sensor_dev=gi.sensor_dev,
                     size=tuple(int(v) for v in gi.size), n_cells=int(gi.n_cells), has_map=bool(gi.has_map),
-                    has_grid=bool(gi.has_grid), device=gi.device)
+                    has_grid=bool(gi.has_grid), device=gi.device, rep=gi.rep, lut_n=int(gi.lut_n),
+                    coded_bytes=int(gi.coded_bytes))
+
+    def useCodes(self, enable: bool):
+        """A/B switch for the lossless dictionary-coded copy (bit-identical results either way)."""
+        check(self._L.amcl3d_b200_grid_use_codes(self._h, int(bool(enable))))
 
     def computePointCloud(self, xyz, resolution):
         """computePointCloud (PointCloudTools.cpp:84-109): bounds of the map cloud; raises on <= 1 point."""

@@ -50,7 +50,8 @@ def build_native(verbose: bool = False, force: bool = False) -> Path:
         obj = objdir / (src + ".o")
         objs.append(obj)
         if force or _stale(obj, [CSRC / src, *headers]):
-            cmd = [nvcc(), *ccbin, *NVCC_FLAGS, "-Xptxas", "-v", "-c", str(CSRC / src), "-o", str(obj)]
+            extra = os.environ.get("AMCL3D_NVCC_DEFS", "").split()  # e.g. "-DAMCL3D_UNROLL=16" for tuning sweeps
+            cmd = [nvcc(), *ccbin, *NVCC_FLAGS, *extra, "-Xptxas", "-v", "-c", str(CSRC / src), "-o", str(obj)]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if verbose or r.returncode != 0:
                 sys.stderr.write(r.stdout + r.stderr)

@@ -19,7 +19,7 @@ SYMBOLS = [
     "amcl3d_b200_grid_compute_bounds", "amcl3d_b200_grid_set_map", "amcl3d_b200_grid_build",
     "amcl3d_b200_grid_download_edt", "amcl3d_b200_grid_upload", "amcl3d_b200_grid_download",
     "amcl3d_b200_grid_save_file", "amcl3d_b200_grid_load_file", "amcl3d_b200_grid_is_into_map",
-    "amcl3d_b200_grid_cloud_weight", "amcl3d_b200_grid_device_ptr",
+    "amcl3d_b200_grid_cloud_weight", "amcl3d_b200_grid_device_ptr", "amcl3d_b200_grid_use_codes",
     "amcl3d_b200_pf_create", "amcl3d_b200_pf_destroy", "amcl3d_b200_pf_set_trig_mode", "amcl3d_b200_pf_set_stream",
     "amcl3d_b200_pf_set_particles", "amcl3d_b200_pf_get_particles", "amcl3d_b200_pf_size",
     "amcl3d_b200_pf_bind_device", "amcl3d_b200_pf_device_ptr", "amcl3d_b200_pf_set_cloud",
@@ -39,7 +39,7 @@ class GridInfo(C.Structure):
     _fields_ = [
         ("min", C.c_double * 3), ("max", C.c_double * 3), ("resol", C.c_double), ("sensor_dev", C.c_double),
         ("size", C.c_uint32 * 3), ("n_cells", C.c_uint64), ("has_map", C.c_int), ("has_grid", C.c_int),
-        ("device", C.c_int),
+        ("device", C.c_int), ("rep", C.c_int), ("lut_n", C.c_uint32), ("coded_bytes", C.c_uint64),
     ]
 
 
@@ -88,6 +88,7 @@ def load():
         "amcl3d_b200_grid_is_into_map": (i, [vp, f32, f32, f32, P(i)]),
         "amcl3d_b200_grid_cloud_weight": (i, [vp, vp, u32, u32, f32, f32, f32, f32, f32, f32, i, P(f32)]),
         "amcl3d_b200_grid_device_ptr": (i, [vp, P(vp)]),
+        "amcl3d_b200_grid_use_codes": (i, [vp, i]),
         "amcl3d_b200_pf_create": (i, [vp, P(vp)]),
         "amcl3d_b200_pf_destroy": (i, [vp]),
         "amcl3d_b200_pf_set_trig_mode": (i, [vp, i]),

@@ -79,6 +79,8 @@ struct amcl3d_b200_grid_s
   uint64_t prob_cap = 0;
   int32_t* d_edt = nullptr;
   uint64_t edt_cells = 0;
+  CodedGrid coded{};       // lossless dictionary-coded copy (rep == kRepFloat: absent)
+  int use_codes = 1;       // AMCL3D_B200_CODES=0 or grid_set_option disables it
   cudaStream_t stream = nullptr;
   amcl3d_b200_pf_t scratch_pf = nullptr;  // for the single-pose computeCloudWeight
 };
@@ -145,6 +147,20 @@ void refresh_map(amcl3d_b200_grid_t g)
   m.step_z = (uint64_t)m.size[0] * (uint64_t)m.size[1];
   m.n_cells = (uint64_t)m.size[0] * (uint64_t)m.size[1] * (uint64_t)m.size[2];
   m.prob = g->d_prob;
+  const bool coded = g->use_codes && g->coded.rep != kRepFloat && g->coded.codes != nullptr;
+  m.rep = coded ? g->coded.rep : kRepFloat;
+  m.codes = coded ? g->coded.codes : nullptr;
+  m.lut = coded ? g->coded.lut : nullptr;
+  m.lut_n = coded ? g->coded.lut_n : 0;
+  m.nbx = coded ? g->coded.nbx : 0;
+  m.nby = coded ? g->coded.nby : 0;
+}
+
+void drop_codes(amcl3d_b200_grid_t g)
+{
+  cudaFree(g->coded.codes_alloc);
+  cudaFree(g->coded.lut);
+  g->coded = CodedGrid{};
 }
 
 // PointCloudTools.cpp:120-125
@@ -253,6 +269,17 @@ int amcl3d_b200_grid_create(int device, amcl3d_b200_grid_t* out)
   if (!g)
     return fail(AMCL3D_B200_ERR_ARG, "out of host memory");
   g->device = device;
+  if (const char* env = getenv("AMCL3D_B200_CODES"))
+    g->use_codes = atoi(env) != 0;
+  {
+    // the weighting kernel uses 1-4 bytes of every line it touches: ask L2 for the smallest DRAM fetch
+    int gran = 32;
+    if (const char* env = getenv("AMCL3D_B200_L2_FETCH"))
+      gran = atoi(env);
+    if (gran == 32 || gran == 64 || gran == 128)
+      (void)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
+    (void)cudaGetLastError();
+  }
   cudaError_t e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess)
   {
@@ -272,6 +299,7 @@ int amcl3d_b200_grid_destroy(amcl3d_b200_grid_t g)
     amcl3d_b200_pf_destroy(g->scratch_pf);
   cudaFree(g->d_prob);
   cudaFree(g->d_edt);
+  drop_codes(g);
   if (g->stream)
     cudaStreamDestroy(g->stream);
   delete g;
@@ -294,6 +322,18 @@ int amcl3d_b200_grid_get_info(amcl3d_b200_grid_t g, amcl3d_b200_grid_info_t* inf
   info->has_map = g->map.has_map;
   info->has_grid = g->map.has_grid;
   info->device = g->device;
+  info->rep = g->map.rep;
+  info->lut_n = g->map.lut_n;
+  info->coded_bytes = g->map.rep != kRepFloat ? g->coded.bytes : 0;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_grid_use_codes(amcl3d_b200_grid_t g, int enable)
+{
+  if (!g)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+  g->use_codes = enable != 0;
+  refresh_map(g);
   return AMCL3D_B200_OK;
 }
 
@@ -380,6 +420,7 @@ int amcl3d_b200_grid_upload(amcl3d_b200_grid_t g, const float* prob, const uint3
     g->map.size[a] = size[a];
   g->sensor_dev = sensor_dev;
   g->map.has_grid = 1;
+  drop_codes(g);  // an uploaded float grid is used as is (linear f32)
   refresh_map(g);
   return AMCL3D_B200_OK;
 }
@@ -430,6 +471,8 @@ int amcl3d_b200_grid_build(amcl3d_b200_grid_t g, const float* xyz, uint32_t stri
   cudaFree(g->d_edt);
   g->d_edt = nullptr;
   g->edt_cells = 0;
+  drop_codes(g);
+  refresh_map(g);
 
   float* d_xyz = nullptr;
   CU(cudaMalloc(&d_xyz, sizeof(float) * std::max<uint64_t>(n, 1) * stride));
@@ -441,7 +484,7 @@ int amcl3d_b200_grid_build(amcl3d_b200_grid_t g, const float* xyz, uint32_t stri
       e = build_grid_splat(g->map, d_xyz, stride, n, sensor_dev, g->d_prob, g->stream);
     else
       e = build_grid_edt(g->map, d_xyz, stride, n, sensor_dev, mode, sub, g->d_prob, keep_edt ? &g->d_edt : nullptr,
-                         g->stream, msg, sizeof(msg));
+                         g->use_codes ? &g->coded : nullptr, g->stream, msg, sizeof(msg));
   }
   if (e == cudaSuccess)
     e = cudaStreamSynchronize(g->stream);

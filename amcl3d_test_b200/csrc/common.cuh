@@ -26,7 +26,69 @@ struct MapDev
   const float* prob;
   int has_map;
   int has_grid;
+  // Lossless dictionary-coded copy of the grid for the weighting kernel (device-private; the public
+  // format stays the linear float grid).  An EDT-built field takes only a few hundred distinct float
+  // values (one per attainable integer squared distance below the expf underflow), so every voxel is
+  // stored as a 1- or 2-byte code into `lut` and the kernel adds lut[code] -- the very same f32 the
+  // float grid holds, hence bit-identical weights -- while a 128-byte line now covers an 8x4x4 (u8) or
+  // 4x4x4 (u16) voxel brick instead of 32 voxels of one x-row.
+  int rep;                 // kRepFloat / kRepCode8 / kRepCode16
+  const void* codes;       // bricked codes, 2 MB aligned
+  const float* lut;        // lut_n floats
+  uint32_t lut_n;
+  uint32_t nbx, nby;       // 128^3-voxel blocks along x and y
 };
+
+enum
+{
+  kRepFloat = 0,
+  kRepCode8 = 1,   // brick 8 x 4 x 4 voxels = 128 B
+  kRepCode16 = 2   // brick 4 x 4 x 4 voxels = 128 B
+};
+
+// Two-level layout of the coded copy.  Level 1: 128-byte bricks (8x4x4 one-byte or 4x4x4 two-byte codes)
+// so that one cache line is a compact 3-D neighbourhood.  Level 2: 128^3-voxel blocks stored contiguously
+// (2 MB of u8 codes = exactly one large page, 4 MB of u16 codes): a scattered gather over a compact 3-D
+// region then touches a handful of pages instead of one page per (y,z) row group -- measured on B200,
+// random 4-byte gathers collapse from ~2.6e11/s to ~4e10/s once the touched address range outgrows the
+// TLB reach, even when the touched lines themselves fit in L2.
+template <int kRep>
+__host__ __device__ __forceinline__ uint64_t coded_index(uint32_t ix, uint32_t iy, uint32_t iz, uint32_t nbx, uint32_t nby)
+{
+  const uint64_t block = ((uint64_t)(iz >> 7) * nby + (iy >> 7)) * nbx + (ix >> 7);
+  if (kRep == kRepCode8)
+  {
+    const uint32_t brick = (((iz >> 2) & 31u) << 9) | (((iy >> 2) & 31u) << 4) | ((ix >> 3) & 15u);
+    const uint32_t vox = ((iz & 3u) << 5) | ((iy & 3u) << 3) | (ix & 7u);
+    return (block << 21) | (brick << 7) | vox;
+  }
+  const uint32_t brick = (((iz >> 2) & 31u) << 10) | (((iy >> 2) & 31u) << 5) | ((ix >> 2) & 31u);
+  const uint32_t vox = ((iz & 3u) << 4) | ((iy & 3u) << 2) | (ix & 3u);
+  return (block << 21) | (brick << 6) | vox;
+}
+// inverse of coded_index
+template <int kRep>
+__host__ __device__ __forceinline__ void coded_voxel(uint64_t t, uint32_t nbx, uint32_t nby, uint32_t& ix, uint32_t& iy, uint32_t& iz)
+{
+  const uint64_t block = t >> 21;
+  const uint32_t within = (uint32_t)(t & ((1u << 21) - 1));
+  const uint32_t Bx = (uint32_t)(block % nbx), By = (uint32_t)((block / nbx) % nby), Bz = (uint32_t)(block / ((uint64_t)nbx * nby));
+  if (kRep == kRepCode8)
+  {
+    const uint32_t brick = within >> 7, vox = within & 127u;
+    ix = (Bx << 7) | ((brick & 15u) << 3) | (vox & 7u);
+    iy = (By << 7) | (((brick >> 4) & 31u) << 2) | ((vox >> 3) & 3u);
+    iz = (Bz << 7) | ((brick >> 9) << 2) | (vox >> 5);
+  }
+  else
+  {
+    const uint32_t brick = within >> 6, vox = within & 63u;
+    ix = (Bx << 7) | ((brick & 31u) << 2) | (vox & 3u);
+    iy = (By << 7) | (((brick >> 5) & 31u) << 2) | ((vox >> 2) & 3u);
+    iz = (Bz << 7) | ((brick >> 10) << 2) | (vox >> 4);
+  }
+}
+constexpr uint32_t kMaxLutSmem = 8192;  // LUT entries staged in shared memory (32 KB)
 
 constexpr int kMaxBeacons = 16;
 
@@ -84,13 +146,19 @@ cudaError_t launch_predict(float* particles, uint64_t n, const double* delta6_de
 // ---- grid build (gridbuild.cu) ------------------------------------------------------------------
 cudaError_t launch_bounds(const float* xyz, uint32_t stride, uint64_t n, float* out6 /*min3,max3*/,
                           cudaStream_t stream);
-struct EdtResult
+struct CodedGrid
 {
-  int32_t* d2;  // device, size_x*size_y*size_z, caller frees with cudaFree (nullptr if !keep)
+  int rep;  // kRepFloat: nothing allocated
+  void* codes;        // 2 MB aligned view into codes_alloc
+  void* codes_alloc;  // what cudaFree takes
+  float* lut;
+  uint32_t lut_n, nbx, nby;
+  uint64_t bytes;
 };
-// full build: EDT (+ optional kept distances) and fused Gaussian into prob (device, n_cells floats)
+// full build: EDT (+ optional kept distances) and fused Gaussian into prob (device, n_cells floats);
+// coded (nullable) additionally receives the dictionary-coded bricked copy (caller frees codes / lut)
 cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t stride, uint64_t n, double sensor_dev,
-                           int mode, int sub, float* prob, int32_t** keep_d2, cudaStream_t stream,
+                           int mode, int sub, float* prob, int32_t** keep_d2, CodedGrid* coded, cudaStream_t stream,
                            char* err, size_t errlen);
 cudaError_t build_grid_splat(const MapDev& map, const float* d_xyz, uint32_t stride, uint64_t n, double sensor_dev,
                              float* prob, cudaStream_t stream);

@@ -22,6 +22,8 @@
 #include <float.h>
 #include <stdio.h>
 
+#include <vector>
+
 namespace a3d
 {
 namespace
@@ -464,6 +466,51 @@ __global__ void splat_kernel(const __grid_constant__ SplatArgs S, const float* _
   atomicMax(&prob_bits[index], __float_as_int(v));
 }
 
+// ---- lossless dictionary coding of the field ----------------------------------------------------------
+// smallest d2 in [0, limit) whose probability is exactly 0.0f (prob is non-increasing in d2)
+__global__ void find_cap_kernel(const __grid_constant__ Gauss g, uint32_t limit, unsigned int* __restrict__ cap)
+{
+  const uint32_t d2 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d2 < limit && prob_of(g, (int32_t)d2) == 0.f)
+    atomicMin(cap, d2);
+}
+// present[min(d2, cap)] = 1
+__global__ void present_kernel(const int32_t* __restrict__ d2, uint64_t cells, uint32_t cap, uint8_t* __restrict__ present)
+{
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (uint64_t)gridDim.x * blockDim.x)
+  {
+    const int32_t v = d2[i];
+    const uint32_t k = (v < 0 || (uint32_t)v > cap) ? cap : (uint32_t)v;
+    if (!present[k])
+      present[k] = 1;
+  }
+}
+// lut[c] = prob_of(values[c]) with the same device function that wrote the float grid
+__global__ void lut_kernel(const __grid_constant__ Gauss g, const int32_t* __restrict__ values, uint32_t n, float* __restrict__ lut)
+{
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n)
+    lut[c] = prob_of(g, values[c]);
+}
+// one thread per code slot, in coded (output) order
+template <typename TCode, int kRep>
+__global__ void encode_kernel(const int32_t* __restrict__ d2, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t nbx, uint32_t nby,
+                              uint64_t slots, uint32_t cap, const uint16_t* __restrict__ rank, TCode* __restrict__ codes)
+{
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= slots)
+    return;
+  uint32_t ix, iy, iz;
+  coded_voxel<kRep>(t, nbx, nby, ix, iy, iz);
+  uint32_t k = cap;  // padding voxels: the zero class (never addressed by the kernel)
+  if (ix < sx && iy < sy && iz < sz)
+  {
+    const int32_t v = d2[(uint64_t)ix + (uint64_t)iy * sx + (uint64_t)iz * sx * sy];
+    k = (v < 0 || (uint32_t)v > cap) ? cap : (uint32_t)v;
+  }
+  codes[t] = (TCode)rank[k];
+}
+
 void gauss_consts(double sensor_dev, float* c1, float* c2)
 {
   *c1 = static_cast<float>(1. / (sensor_dev * sqrt(2 * M_PI)));   // PointCloudTools.cpp:139
@@ -523,9 +570,106 @@ cudaError_t build_grid_splat(const MapDev& map, const float* d_xyz, uint32_t str
   return cudaGetLastError();
 }
 
+// Builds the dictionary-coded, bricked copy of the field from the linear int32 distance transform.
+// On success out->rep is kRepCode8 / kRepCode16; kRepFloat (no allocation) if the field has too many
+// distinct values for 16-bit codes or never underflows to zero inside the probed range.
+static cudaError_t build_codes(const MapDev& map, const int32_t* d_d2, const Gauss& G, CodedGrid* out, cudaStream_t stream)
+{
+  cudaError_t rc = cudaSuccess;
+  out->rep = kRepFloat;
+  out->codes = nullptr;
+  out->codes_alloc = nullptr;
+  out->lut = nullptr;
+  out->lut_n = 0;
+  const uint32_t sx = map.size[0], sy = map.size[1], sz = map.size[2];
+  const uint64_t cells = (uint64_t)sx * sy * sz;
+  const uint32_t kLimit = 1u << 22;
+  unsigned int* d_cap = nullptr;
+  uint8_t* d_present = nullptr;
+  uint16_t* d_rank = nullptr;
+  int32_t* d_values = nullptr;
+  void* d_codes = nullptr;
+  float* d_lut = nullptr;
+  unsigned int h_cap = 0xFFFFFFFFu;
+  std::vector<uint8_t> present;
+  std::vector<uint16_t> rank;
+  std::vector<int32_t> values;
+
+  CK(cudaMalloc(&d_cap, sizeof(unsigned int)));
+  CK(cudaMemcpyAsync(d_cap, &h_cap, sizeof(h_cap), cudaMemcpyHostToDevice, stream));
+  find_cap_kernel<<<kLimit / 256, 256, 0, stream>>>(G, kLimit, d_cap);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(&h_cap, d_cap, sizeof(h_cap), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  if (h_cap == 0xFFFFFFFFu)
+    goto done;  // the Gaussian never reaches 0.0f: keep the float grid
+  {
+    const uint32_t cap = h_cap;
+    CK(cudaMalloc(&d_present, cap + 1));
+    CK(cudaMemsetAsync(d_present, 0, cap + 1, stream));
+    present_kernel<<<148 * 16, 256, 0, stream>>>(d_d2, cells, cap, d_present);
+    CK(cudaGetLastError());
+    present.resize(cap + 1);
+    CK(cudaMemcpyAsync(present.data(), d_present, cap + 1, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    present[cap] = 1;  // the zero class always exists (padding)
+    rank.assign(cap + 1, 0);
+    for (uint32_t k = 0; k <= cap; ++k)
+      if (present[k])
+      {
+        rank[k] = (uint16_t)values.size();
+        values.push_back((int32_t)k);
+        if (values.size() > 65536)
+          break;
+      }
+    if (values.size() > 65536)
+      goto done;
+    const uint32_t nvals = (uint32_t)values.size();
+    const bool small = nvals <= 256;
+    const uint32_t nbx = (sx + 127) / 128, nby = (sy + 127) / 128, nbz = (sz + 127) / 128;
+    const uint64_t slots = ((uint64_t)nbx * nby * nbz) << 21;
+    const uint64_t code_bytes = slots * (small ? 1 : 2);
+    CK(cudaMalloc(&d_rank, sizeof(uint16_t) * (cap + 1)));
+    CK(cudaMalloc(&d_values, sizeof(int32_t) * nvals));
+    CK(cudaMalloc(&d_lut, sizeof(float) * nvals));
+    CK(cudaMalloc(&d_codes, code_bytes + (2u << 20)));
+    void* const codes_aligned = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(d_codes) + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1));
+    CK(cudaMemcpyAsync(d_rank, rank.data(), sizeof(uint16_t) * (cap + 1), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_values, values.data(), sizeof(int32_t) * nvals, cudaMemcpyHostToDevice, stream));
+    lut_kernel<<<(nvals + 255) / 256, 256, 0, stream>>>(G, d_values, nvals, d_lut);
+    CK(cudaGetLastError());
+    if (small)
+      encode_kernel<uint8_t, kRepCode8><<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(d_d2, sx, sy, sz, nbx, nby, slots, cap,
+                                                                                           d_rank, (uint8_t*)codes_aligned);
+    else
+      encode_kernel<uint16_t, kRepCode16><<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(d_d2, sx, sy, sz, nbx, nby, slots,
+                                                                                             cap, d_rank, (uint16_t*)codes_aligned);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(stream));
+    out->rep = small ? kRepCode8 : kRepCode16;
+    out->codes = codes_aligned;
+    out->codes_alloc = d_codes;
+    out->lut = d_lut;
+    out->lut_n = nvals;
+    out->nbx = nbx;
+    out->nby = nby;
+    out->bytes = code_bytes;
+    d_codes = nullptr;
+    d_lut = nullptr;
+  }
+done:
+  cudaFree(d_cap);
+  cudaFree(d_present);
+  cudaFree(d_rank);
+  cudaFree(d_values);
+  cudaFree(d_codes);
+  cudaFree(d_lut);
+  return rc;
+}
+
 cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t stride, uint64_t n, double sensor_dev,
-                           int mode, int sub, float* prob, int32_t** keep_d2, cudaStream_t stream, char* err,
-                           size_t errlen)
+                           int mode, int sub, float* prob, int32_t** keep_d2, CodedGrid* coded, cudaStream_t stream,
+                           char* err, size_t errlen)
 {
   cudaError_t rc = cudaSuccess;
   const int sx = (int)map.size[0], sy = (int)map.size[1], sz = (int)map.size[2];
@@ -601,7 +745,7 @@ cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t strid
   }
 
   {
-    const bool need_d2 = (keep_d2 != nullptr) || ndense > 1;
+    const bool need_d2 = (keep_d2 != nullptr) || ndense > 1 || coded != nullptr;
     if (need_d2)
       CK(cudaMalloc(&d_d2, sizeof(int32_t) * cells));
 
@@ -673,6 +817,17 @@ cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t strid
       }
     }
     CK(cudaStreamSynchronize(stream));
+    // free the pass temporaries before the coder allocates
+    cudaFree(d_bits);
+    d_bits = nullptr;
+    cudaFree(d_d1);
+    d_d1 = nullptr;
+    cudaFree(d_dxy);
+    d_dxy = nullptr;
+    cudaFree(d_stack);
+    d_stack = nullptr;
+    if (coded != nullptr)
+      CK(build_codes(map, d_d2, G, coded, stream));
     if (keep_d2 != nullptr)
     {
       *keep_d2 = d_d2;

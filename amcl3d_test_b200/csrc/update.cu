@@ -29,10 +29,20 @@ namespace a3d
 {
 namespace
 {
-constexpr int kThreads = 128;
-constexpr int kTile = 1024;  // points per stage: 16 KB
+#ifndef AMCL3D_THREADS
+#define AMCL3D_THREADS 128
+#endif
+#ifndef AMCL3D_TILE
+#define AMCL3D_TILE 512
+#endif
+#ifndef AMCL3D_UNROLL
+#define AMCL3D_UNROLL 4
+#endif
+constexpr int kThreads = AMCL3D_THREADS;  // particles per CTA
+constexpr int kTile = AMCL3D_TILE;        // points per shared-memory stage (16 B each)
 constexpr int kStages = 2;
-constexpr int kUnroll = 8;
+constexpr int kUnroll = AMCL3D_UNROLL;    // independent gathers per batch (two batches in flight)
+static_assert(kTile % (2 * kUnroll) == 0 && 32 % kUnroll == 0, "tiles and the 32-point padding must hold whole batch pairs");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
 {
@@ -133,71 +143,182 @@ __device__ __forceinline__ float add_offset(float s, float off_f, double off_d)
   return __double2float_rn(__dadd_rn((double)s, off_d));
 }
 
-// one tile of `count` points (multiple of kUnroll) for one particle
-template <bool kF32Offset>
-__device__ __forceinline__ void tile_loop(const MapDev& map, const float4* __restrict__ tile, uint32_t count,
-                                          const float r[9], const float off_f[3], const double off_d[3], float& weight,
-                                          int& cnt)
+// element index of voxel (ix,iy,iz) in the representation's layout
+template <int kRep>
+__device__ __forceinline__ uint64_t voxel_address(const MapDev& map, uint32_t ix, uint32_t iy, uint32_t iz)
 {
-  const float* __restrict__ prob = map.prob;
-  const uint64_t step_y = map.size[0];
-  const uint64_t step_z = map.step_z;
-#pragma unroll 1
-  for (uint32_t base = 0; base < count; base += kUnroll)
+  if (kRep != kRepFloat)
+    return coded_index<kRep>(ix, iy, iz, map.nbx, map.nby);
+  return (uint64_t)ix + (uint64_t)iy * map.size[0] + (uint64_t)iz * map.step_z;  // Grid3d.cpp:288
+}
+
+// The gathers use one useful element of every line they touch.  AMCL3D_LOAD_MODE selects the cache
+// operator: 0 ld.global.nc (L1-allocating), 1 ld.global.cg (L2 only), 2 ld.global.nc.L1::no_allocate,
+// 3 ld.global.L1::no_allocate.L2::evict_first.
+#ifndef AMCL3D_LOAD_MODE
+#define AMCL3D_LOAD_MODE 0
+#endif
+#if AMCL3D_LOAD_MODE == 1
+#define A3D_LD(suffix) "ld.global.cg." suffix
+#elif AMCL3D_LOAD_MODE == 2
+#define A3D_LD(suffix) "ld.global.nc.L1::no_allocate." suffix
+#elif AMCL3D_LOAD_MODE == 3
+#define A3D_LD(suffix) "ld.global.L1::no_allocate." suffix
+#else
+#define A3D_LD(suffix) "ld.global.nc." suffix
+#endif
+__device__ __forceinline__ float gather_f32(const float* p)
+{
+  float v;
+  asm volatile(A3D_LD("f32") " %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t gather_u8(const uint8_t* p)
+{
+  uint32_t v;
+  asm volatile(A3D_LD("u8") " %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t gather_u16(const uint16_t* p)
+{
+  uint32_t v;
+  asm volatile(A3D_LD("u16") " %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// ---- one particle x kUnroll consecutive points ------------------------------------------------------
+// The hot loop is software-pipelined by hand: addresses of batch k+1 are computed and their gathers
+// issued before the values of batch k are consumed, so two batches of independent loads are in flight
+// per thread and the gather latency overlaps the (branchy, exact) index arithmetic.
+template <int kRep>
+struct Raw
+{
+  typedef uint32_t type;  // dictionary code
+};
+template <>
+struct Raw<kRepFloat>
+{
+  typedef float type;  // the cell itself
+};
+
+// returns the bit mask of evaluations that pass every bounds test; addr[u] = element index of their voxel
+template <bool kF32Offset, int kRep>
+__device__ __forceinline__ uint32_t batch_addresses(const MapDev& map, const float4* __restrict__ pts, const float r[9],
+                                                    const float off_f[3], const double off_d[3], uint64_t addr[kUnroll])
+{
+  float4 pt[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u)
+    pt[u] = pts[u];  // broadcast LDS.128, issued back to back
+  uint32_t mask = 0;
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u)
   {
-    uint64_t addr[kUnroll];
-    bool ok[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
+    // Grid3d.cpp:275-277
+    const float sx = __fadd_rn(__fadd_rn(__fmul_rn(pt[u].x, r[0]), __fmul_rn(pt[u].y, r[1])), __fmul_rn(pt[u].z, r[2]));
+    const float sy = __fadd_rn(__fadd_rn(__fmul_rn(pt[u].x, r[3]), __fmul_rn(pt[u].y, r[4])), __fmul_rn(pt[u].z, r[5]));
+    const float sz = __fadd_rn(__fadd_rn(__fmul_rn(pt[u].x, r[6]), __fmul_rn(pt[u].y, r[7])), __fmul_rn(pt[u].z, r[8]));
+    const float nx = add_offset<kF32Offset>(sx, off_f[0], off_d[0]);
+    const float ny = add_offset<kF32Offset>(sy, off_f[1], off_d[1]);
+    const float nz = add_offset<kF32Offset>(sz, off_f[2], off_d[2]);
+    // Grid3d.cpp:279-280 (NaN fails every comparison, like the reference)
+    bool in = (nx >= 0.f) & (nx < map.size_up[0]) & (ny >= 0.f) & (ny < map.size_up[1]) & (nz >= 0.f) &
+              (nz < map.size_up[2]);
+    uint64_t a = 0;
+    if (in)
     {
-      const float4 pt = tile[base + u];
-      // Grid3d.cpp:275-277
-      const float sx = __fadd_rn(__fadd_rn(__fmul_rn(pt.x, r[0]), __fmul_rn(pt.y, r[1])), __fmul_rn(pt.z, r[2]));
-      const float sy = __fadd_rn(__fadd_rn(__fmul_rn(pt.x, r[3]), __fmul_rn(pt.y, r[4])), __fmul_rn(pt.z, r[5]));
-      const float sz = __fadd_rn(__fadd_rn(__fmul_rn(pt.x, r[6]), __fmul_rn(pt.y, r[7])), __fmul_rn(pt.z, r[8]));
-      const float nx = add_offset<kF32Offset>(sx, off_f[0], off_d[0]);
-      const float ny = add_offset<kF32Offset>(sy, off_f[1], off_d[1]);
-      const float nz = add_offset<kF32Offset>(sz, off_f[2], off_d[2]);
-      // Grid3d.cpp:279-280 (NaN fails every comparison, like the reference)
-      bool in = (nx >= 0.f) & (nx < map.size_up[0]) & (ny >= 0.f) & (ny < map.size_up[1]) & (nz >= 0.f) &
-                (nz < map.size_up[2]);
-      uint64_t a = 0;
-      if (in)
-      {
-        // Grid3d.cpp:282-288
-        const uint32_t ix = voxel_of(nx, map.rinv_f, map.eps[0], map.rinv, map.resol);
-        const uint32_t iy = voxel_of(ny, map.rinv_f, map.eps[1], map.rinv, map.resol);
-        const uint32_t iz = voxel_of(nz, map.rinv_f, map.eps[2], map.rinv, map.resol);
-        in = (ix < map.size[0]) & (iy < map.size[1]) & (iz < map.size[2]);
-        a = (uint64_t)ix + (uint64_t)iy * step_y + (uint64_t)iz * step_z;
-        in = in & (a < map.n_cells);  // Grid3d.cpp:290
-      }
-      ok[u] = in;
-      addr[u] = a;
+      // Grid3d.cpp:282-288
+      const uint32_t ix = voxel_of(nx, map.rinv_f, map.eps[0], map.rinv, map.resol);
+      const uint32_t iy = voxel_of(ny, map.rinv_f, map.eps[1], map.rinv, map.resol);
+      const uint32_t iz = voxel_of(nz, map.rinv_f, map.eps[2], map.rinv, map.resol);
+      in = (ix < map.size[0]) & (iy < map.size[1]) & (iz < map.size[2]);  // Grid3d.cpp:286 (and :290)
+      a = voxel_address<kRep>(map, ix, iy, iz);
     }
-    float v[kUnroll];
+    mask |= in ? (1u << u) : 0u;
+    addr[u] = a;
+  }
+  return mask;
+}
+
+template <int kRep>
+__device__ __forceinline__ void batch_issue(const MapDev& map, const uint64_t addr[kUnroll], uint32_t mask,
+                                            typename Raw<kRep>::type raw[kUnroll])
+{
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
-      v[u] = ok[u] ? __ldg(prob + addr[u]) : 0.f;
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
+  for (int u = 0; u < kUnroll; ++u)
+  {
+    raw[u] = 0;
+    if ((mask >> u) & 1u)
     {
-      if (ok[u])
-      {
-        weight = __fadd_rn(weight, v[u]);  // Grid3d.cpp:292, cloud order
-        ++cnt;
-      }
+      if (kRep == kRepFloat)
+        raw[u] = gather_f32(map.prob + addr[u]);
+      else if (kRep == kRepCode8)
+        raw[u] = gather_u8(reinterpret_cast<const uint8_t*>(map.codes) + addr[u]);
+      else
+        raw[u] = gather_u16(reinterpret_cast<const uint16_t*>(map.codes) + addr[u]);
     }
   }
 }
 
-__global__ void __launch_bounds__(kThreads)
+template <int kRep>
+__device__ __forceinline__ void batch_consume(const typename Raw<kRep>::type raw[kUnroll], uint32_t mask,
+                                              const float* __restrict__ lut_s, float& weight, int& cnt)
+{
+  float v[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u)
+  {
+    if (kRep == kRepFloat)
+      v[u] = raw[u];
+    else
+      v[u] = lut_s[(uint32_t)raw[u]];  // the same f32 the float grid holds for this voxel
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u)
+    if ((mask >> u) & 1u)
+      weight = __fadd_rn(weight, v[u]);  // Grid3d.cpp:292, cloud order
+  cnt += __popc(mask);
+}
+
+// one tile of `count` points (a multiple of 2*kUnroll) for one particle
+template <bool kF32Offset, int kRep>
+__device__ __forceinline__ void tile_loop(const MapDev& map, const float4* __restrict__ tile, uint32_t count,
+                                          const float r[9], const float off_f[3], const double off_d[3],
+                                          const float* __restrict__ lut_s, float& weight, int& cnt)
+{
+  typedef typename Raw<kRep>::type raw_t;
+  uint64_t addr[kUnroll];
+  raw_t raw_a[kUnroll], raw_b[kUnroll];
+  uint32_t mask_a, mask_b;
+  mask_a = batch_addresses<kF32Offset, kRep>(map, tile, r, off_f, off_d, addr);
+  batch_issue<kRep>(map, addr, mask_a, raw_a);
+#pragma unroll 1
+  for (uint32_t base = kUnroll; base < count; base += 2 * kUnroll)
+  {
+    mask_b = batch_addresses<kF32Offset, kRep>(map, tile + base, r, off_f, off_d, addr);
+    batch_issue<kRep>(map, addr, mask_b, raw_b);
+    batch_consume<kRep>(raw_a, mask_a, lut_s, weight, cnt);
+    if (base + kUnroll < count)
+    {
+      mask_a = batch_addresses<kF32Offset, kRep>(map, tile + base + kUnroll, r, off_f, off_d, addr);
+      batch_issue<kRep>(map, addr, mask_a, raw_a);
+    }
+    batch_consume<kRep>(raw_b, mask_b, lut_s, weight, cnt);
+  }
+}
+
+#ifndef AMCL3D_MINBLOCKS
+#define AMCL3D_MINBLOCKS 6
+#endif
+template <int kRep>
+__global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
     update_kernel(const __grid_constant__ MapDev map, float* __restrict__ particles, uint32_t n,
                   const float4* __restrict__ cloud, uint32_t npts, uint32_t npad, const BeaconSet* __restrict__ beacons,
                   float* __restrict__ wr_out, int trig_mode, unsigned long long* __restrict__ counter)
 {
   __shared__ __align__(128) float4 tile[kStages][kTile];
   __shared__ __align__(8) uint64_t full_bar[kStages];
+  extern __shared__ float lut_s[];  // kRep != kRepFloat: the code -> f32 dictionary
 
   const uint32_t tid = threadIdx.x;
   const uint32_t i = blockIdx.x * kThreads + tid;
@@ -247,6 +368,9 @@ __global__ void __launch_bounds__(kThreads)
       mbar_init(&full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (kRep != kRepFloat)
+    for (uint32_t k = tid; k < map.lut_n; k += kThreads)
+      lut_s[k] = map.lut[k];
   __syncthreads();
   if (tid == 0)
   {
@@ -269,9 +393,9 @@ __global__ void __launch_bounds__(kThreads)
     if (inmap)
     {
       if (warp_f32)
-        tile_loop<true>(map, &tile[s][0], count, r, off_f, off_d, weight, cnt);
+        tile_loop<true, kRep>(map, &tile[s][0], count, r, off_f, off_d, lut_s, weight, cnt);
       else
-        tile_loop<false>(map, &tile[s][0], count, r, off_f, off_d, weight, cnt);
+        tile_loop<false, kRep>(map, &tile[s][0], count, r, off_f, off_d, lut_s, weight, cnt);
     }
     __syncthreads();  // every lane is done with stage s before TMA overwrites it
     if (tid == 0 && t + kStages < ntiles)
@@ -380,6 +504,10 @@ __global__ void __launch_bounds__(256)
       }
       else
         idx[u] = h % window;
+      // flavor >= 16: sparse probe -- only every (flavor-th) 128-byte line of the window is touched, so the
+      // touched bytes fit L2 while the address range (pages) stays large: separates TLB reach from DRAM
+      if (flavor >= 16)
+        idx[u] = ((idx[u] >> 5) / (uint64_t)flavor) * (uint64_t)flavor * 32ull + (idx[u] & 31ull);
     }
     float v[8];
 #pragma unroll
@@ -414,8 +542,28 @@ cudaError_t launch_update(const MapDev& map, float* particles, uint32_t n, const
   if (n == 0)
     return cudaSuccess;
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
-  update_kernel<<<blocks, kThreads, 0, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons, wr_out,
-                                                 trig_mode, counter);
+  if (map.rep == kRepFloat || map.codes == nullptr || map.lut_n > kMaxLutSmem)
+  {
+    update_kernel<kRepFloat><<<blocks, kThreads, 0, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
+                                                              wr_out, trig_mode, counter);
+    return cudaGetLastError();
+  }
+  const size_t dyn = sizeof(float) * map.lut_n;
+  static bool attr_set = false;
+  if (!attr_set)
+  {
+    cudaError_t e = cudaFuncSetAttribute(update_kernel<kRepCode16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(float) * kMaxLutSmem));
+    if (e != cudaSuccess)
+      return e;
+    attr_set = true;
+  }
+  if (map.rep == kRepCode8)
+    update_kernel<kRepCode8><<<blocks, kThreads, dyn, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
+                                                                wr_out, trig_mode, counter);
+  else
+    update_kernel<kRepCode16><<<blocks, kThreads, dyn, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
+                                                                 wr_out, trig_mode, counter);
   return cudaGetLastError();
 }
 

@@ -76,6 +76,10 @@ typedef struct
   int has_map;                              /* pc_info_ set */
   int has_grid;                             /* grid_info_ set */
   int device;
+  int rep;                                  /* what the weighting kernel reads: 0 linear f32, 1 / 2 = lossless
+                                               8- / 16-bit dictionary codes in 128-byte voxel bricks */
+  uint32_t lut_n;                           /* distinct field values (dictionary size), 0 for rep 0 */
+  uint64_t coded_bytes;                     /* size of the coded copy */
 } amcl3d_b200_grid_info_t;
 
 /* ---- runtime ------------------------------------------------------------------------------ */
@@ -128,6 +132,10 @@ int amcl3d_b200_grid_is_into_map(amcl3d_b200_grid_t g, float x, float y, float z
 int amcl3d_b200_grid_cloud_weight(amcl3d_b200_grid_t g, const float* cloud, uint32_t stride, uint32_t npts,
                                   float tx, float ty, float tz, float roll, float pitch, float yaw,
                                   int trig_mode, float* weight);
+/* enable (default) / disable the lossless dictionary-coded copy that grid_build makes for the weighting
+ * kernel (an A/B switch: results are bit-identical either way).  Environment AMCL3D_B200_CODES=0 sets
+ * the default for new handles. */
+int amcl3d_b200_grid_use_codes(amcl3d_b200_grid_t g, int enable);
 /* raw device pointer of the cells (for callers that keep data resident, e.g. NCCL broadcast) */
 int amcl3d_b200_grid_device_ptr(amcl3d_b200_grid_t g, void** d_prob);
 

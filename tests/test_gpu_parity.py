@@ -310,3 +310,55 @@ def test_range_beacon_fusion(O, world_c1, pf):
     pf.update(w["cloud"], beacons=(pos, rng), alpha=0.5, sigma=0.53)
     got = pf.p_
     assert rel_err(got[:, 6], ref[:, 6]).max() < 1e-4  # device expf vs glibc expf, 8 factors
+
+
+@pytest.mark.parametrize("lattice,sensor_dev,expect_rep", [("centre", 0.05, 1), ("mixed", 0.05, 1), ("mixed", 0.3, 2)])
+def test_update_on_coded_grid_is_bit_identical(O, world_c1, lattice, sensor_dev, expect_rep):
+    """A grid built on the device is also kept as lossless dictionary codes in voxel bricks; weights from
+    the coded copy, from the linear f32 grid and from the oracle on the downloaded grid are identical."""
+    from amcl3d_test_b200 import Grid3d, ParticleFilter, synth
+
+    w = world_c1
+    pts = w["synth"].points
+    if lattice == "mixed":  # half of the sites moved onto other parity classes -> many more distinct distances
+        rng = np.random.RandomState(4)
+        pts = pts.copy()
+        sel = rng.rand(pts.shape[0]) < 0.5
+        sel[:2] = False
+        pts[sel] += (rng.randint(0, 2, (int(sel.sum()), 3)) * 0.05).astype(np.float32)
+    g = Grid3d(0)
+    mn, mx = g.computePointCloud(pts, 0.1)
+    g.computeGrid(pts, sensor_dev, sub=2)
+    info = g.info()
+    assert info["rep"] == expect_rep, info
+    prob = g.downloadGrid()
+    assert len(np.unique(prob)) == info["lut_n"] or len(np.unique(prob)) + 1 == info["lut_n"]
+    m = O.Map(mn, mx, 0.1, sensor_dev, prob=prob)
+    pf = ParticleFilter(g)
+    for kind in ("T", "G"):
+        ref = O.update(m, O.particles(w[kind]), w["cloud"])
+        pf.p_ = w[kind]
+        pf.update(w["cloud"])
+        coded = pf.p_
+        g.useCodes(False)
+        assert g.info()["rep"] == 0
+        pf.p_ = w[kind]
+        pf.update(w["cloud"])
+        linear = pf.p_
+        g.useCodes(True)
+        assert np.array_equal(bits(coded[:, 6]), bits(ref[:, 6]))
+        assert np.array_equal(bits(linear[:, 6]), bits(ref[:, 6]))
+    # odd sizes: bricks padded at the high faces
+    sm = synth.make_map((6.3, 5.1, 2.7), 0.1)
+    g2 = Grid3d(0)
+    mn, mx = g2.computePointCloud(sm.points, 0.1)
+    g2.computeGrid(sm.points, 0.05, sub=2)
+    assert g2.info()["rep"] in (1, 2)
+    m2 = O.Map(mn, mx, 0.1, 0.05, prob=g2.downloadGrid())
+    P = synth.make_particles(sm, 300, "G")
+    cloud = synth.make_cloud(sm, 700, 2.4)
+    ref = O.update(m2, O.particles(P), cloud)
+    pf2 = ParticleFilter(g2)
+    pf2.p_ = P
+    pf2.update(cloud)
+    assert np.array_equal(bits(pf2.p_[:, 6]), bits(ref[:, 6]))

@@ -37,6 +37,10 @@ def main():
         print(f"  random gather over whole grid: {loads/ms/1e6:.1f} G loads/s")
         ms, loads = g.bench_gather(window_cells=0, blocks=148 * 8, iters=256, coherent=True)
         print(f"  coherent gather over whole grid: {loads/ms/1e6:.1f} G loads/s")
+    for win_mb, k in ((64, 1), (512, 16), (1024, 32), (2048, 64), (4096, 128), (0, 16), (0, 32), (0, 64)):
+        cells = win_mb * (1 << 20) // 4
+        ms, loads = g.bench_gather(window_cells=cells, blocks=148 * 8, iters=256, coherent=(max(k, 0 if k == 1 else 16) << 1) if k > 1 else 0)
+        print(f"sparse probe window {win_mb or 'all'} MB, 1 line in {k}: {loads/ms/1e6:.1f} G loads/s")
     for flavor, name in enumerate(["ldg.nc", "ld.ca", "ld.cg", "ld.cv", "nc.noalloc", "ld.noalloc", "evict_first", "ld.cs"]):
         ms, loads = g.bench_gather(window_cells=0, blocks=148 * 8, iters=256, coherent=flavor << 1)
         ms2, loads2 = g.bench_gather(window_cells=0, blocks=148 * 8, iters=256, coherent=(flavor << 1) | 1)

@@ -54,12 +54,15 @@ class ShardedFilter:
             return
         if self.n_total % self.world == 0:
             dist.all_gather_into_tensor(full, local, group=self.group)
-        else:  # ragged blocks: gather a list
-            parts = []
+        else:  # ragged blocks: gather equal-sized padded blocks, then compact into the global order
+            pad = -(-self.n_total // self.world)
+            send = torch.zeros((pad, 7), dtype=local.dtype, device=local.device)
+            send[: local.shape[0]] = local
+            recv = torch.empty((self.world * pad, 7), dtype=local.dtype, device=local.device)
+            dist.all_gather_into_tensor(recv, send, group=self.group)
             for r in range(self.world):
                 lo, hi = shard_bounds(self.n_total, self.world, r)
-                parts.append(full[lo:hi])
-            dist.all_gather(parts, local, group=self.group)
+                full[lo:hi] = recv[r * pad : r * pad + (hi - lo)]
 
     # -- the path ----------------------------------------------------------------------------------
     def update(self):

@@ -67,5 +67,36 @@ def build_native(verbose: bool = False, force: bool = False) -> Path:
     return LIB
 
 
+HOST_LIB = LIBDIR / "libamcl3d_host.so"
+HOST_TEST = LIBDIR / "host_api_test"
+
+
+def build_host(verbose: bool = False, force: bool = False) -> Path:
+    """The reference-compatible C++ classes (include/amcl3d/*.h, host/*.cpp) over the C-ABI, plus the C++ test driver."""
+    build_native()
+    root = PKG.parent
+    cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
+    srcs = [PKG / "host" / n for n in ("Grid3d.cpp", "ParticleFilter.cpp", "map_io.cpp")]
+    hdrs = list((root / "include").rglob("*.h")) + [PKG / "host" / "map_io.h"]
+    common = [cxx, "-std=c++14", "-O2", "-fPIC", "-Wall", f"-I{root / 'include'}", f"-I{PKG / 'host'}"]
+    if force or _stale(HOST_LIB, [*srcs, *hdrs, LIB]):
+        cmd = [*common, "-shared", "-o", str(HOST_LIB), *map(str, srcs), f"-L{LIBDIR}", "-lamcl3d_b200", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("host library build failed")
+    drv = root / "tests" / "cpp" / "host_api_test.cpp"
+    if drv.exists() and (force or _stale(HOST_TEST, [drv, HOST_LIB, *hdrs])):
+        cmd = [*common, "-o", str(HOST_TEST), str(drv), f"-L{LIBDIR}", "-lamcl3d_host", "-lamcl3d_b200", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("host test driver build failed")
+    return HOST_LIB
+
+
 if __name__ == "__main__":
+    build_host(verbose="-v" in sys.argv)
     print(build_native(verbose="-v" in sys.argv, force="-f" in sys.argv))

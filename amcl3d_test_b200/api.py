@@ -24,6 +24,11 @@ def device_info(device: int = 0) -> dict:
     return dict(device_count=cnt.value, sm_count=sm.value, cc=(maj.value, mnr.value), l2_bytes=l2.value, mem_bytes=mem.value)
 
 
+def set_chain_mode(mode: int) -> None:
+    """0: exact parallel binade scan (default), 1: serial chain kernel.  Same bits either way."""
+    check(capi.load().amcl3d_b200_set_chain_mode(int(mode)))
+
+
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 

@@ -109,6 +109,8 @@ struct amcl3d_b200_pf_s
   uint64_t thr_cap = 0;
   float* d_wr = nullptr;
   uint64_t wr_cap = 0;
+  float* d_dense = nullptr;  // dense copy of the weights for the scan
+  uint64_t dense_cap = 0;
   int32_t* d_idx = nullptr;
   uint64_t idx_cap = 0;
   float* d_noise = nullptr;
@@ -227,6 +229,14 @@ int amcl3d_b200_device_info(int device, int* device_count, int* sm_count, int* c
     *l2_bytes = (uint64_t)p.l2CacheSize;
   if (mem_bytes)
     *mem_bytes = (uint64_t)p.totalGlobalMem;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_set_chain_mode(int mode)
+{
+  if (mode != 0 && mode != 1)
+    return fail(AMCL3D_B200_ERR_ARG, "chain mode must be 0 or 1");
+  set_chain_mode(mode);
   return AMCL3D_B200_OK;
 }
 
@@ -692,6 +702,7 @@ int amcl3d_b200_pf_destroy(amcl3d_b200_pf_t pf)
   cudaFree(pf->d_prefix);
   cudaFree(pf->d_thr);
   cudaFree(pf->d_wr);
+  cudaFree(pf->d_dense);
   cudaFree(pf->d_idx);
   cudaFree(pf->d_noise);
   cudaFree(pf->d_scalars);
@@ -873,7 +884,8 @@ int amcl3d_b200_pf_update(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beaco
     if (nb && pf->n)
     {
       // w = alpha*wp/sum(wp) + (1-alpha)*wr/sum(wr): both sums as sequential f32 chains
-      CU(launch_chain_prefix(pf->d_p, pf->n, 0, nullptr, pf->d_scalars + 0, pf->stream));
+      CU(ensure(pf->d_dense, pf->dense_cap, pf->n));
+      CU(launch_chain_prefix(pf->d_p, pf->n, 0, nullptr, pf->d_scalars + 0, pf->d_dense, pf->stream));
       CU(launch_chain_sum_array(pf->d_wr, pf->n, pf->d_scalars + 1, pf->stream));
       CU(launch_fuse_range(pf->d_p, pf->d_wr, pf->n, pf->d_scalars + 0, pf->d_scalars + 1, alpha, pf->stream));
       pf->launches += 3;
@@ -901,7 +913,8 @@ int amcl3d_b200_pf_update_cloud(amcl3d_b200_pf_t pf, const float* cloud, uint32_
 
 static int normalize_async(amcl3d_b200_pf_t pf)
 {
-  CU(launch_chain_prefix(pf->d_p, pf->n, 1, nullptr, pf->d_scalars + 0, pf->stream));
+  CU(ensure(pf->d_dense, pf->dense_cap, pf->n));
+  CU(launch_chain_prefix(pf->d_p, pf->n, 1, nullptr, pf->d_scalars + 0, pf->d_dense, pf->stream));
   CU(launch_normalize(pf->grid->map, pf->d_p, pf->n, pf->d_scalars + 0, pf->stream));
   pf->launches += pf->n ? 2 : 1;
   return AMCL3D_B200_OK;
@@ -978,6 +991,7 @@ int amcl3d_b200_pf_resample(amcl3d_b200_pf_t pf, float u01, uint64_t m0, uint64_
     return rc;
   const uint64_t cnt = m1 - m0;
   CU(ensure(pf->d_prefix, pf->prefix_cap, n));
+  CU(ensure(pf->d_dense, pf->dense_cap, n));
   float* out = reinterpret_cast<float*>(d_out);
   if (!out)
   {
@@ -992,7 +1006,7 @@ int amcl3d_b200_pf_resample(amcl3d_b200_pf_t pf, float u01, uint64_t m0, uint64_
   }
   {
     Timed t(pf);
-    CU(launch_chain_prefix(pf->d_p, n, 0, pf->d_prefix, nullptr, pf->stream));
+    CU(launch_chain_prefix(pf->d_p, n, 0, pf->d_prefix, nullptr, pf->d_dense, pf->stream));
     CU(launch_resample_search(pf->d_p, pf->d_prefix, n, u01, m0, m1, out, d_idx, pf->stream));
     pf->launches += 2;
   }
@@ -1022,6 +1036,7 @@ int amcl3d_b200_pf_uniform_sample(amcl3d_b200_pf_t pf, int sample_num, uint64_t 
     return rc;
   const uint64_t cnt = k1 - k0;
   CU(ensure(pf->d_prefix, pf->prefix_cap, n));
+  CU(ensure(pf->d_dense, pf->dense_cap, n));
   CU(ensure(pf->d_thr, pf->thr_cap, S));
   float* out = reinterpret_cast<float*>(d_out);
   if (!out)
@@ -1039,7 +1054,7 @@ int amcl3d_b200_pf_uniform_sample(amcl3d_b200_pf_t pf, int sample_num, uint64_t 
     Timed t(pf);
     if (int rc = normalize_async(pf))  // ParticleFilter.cpp:258
       return rc;
-    CU(launch_chain_prefix(pf->d_p, n, 0, pf->d_prefix, nullptr, pf->stream));
+    CU(launch_chain_prefix(pf->d_p, n, 0, pf->d_prefix, nullptr, pf->d_dense, pf->stream));
     CU(launch_chain_thresholds(sample_num, pf->d_thr, pf->stream));
     CU(launch_uniform_search(pf->d_p, pf->d_prefix, n, pf->d_thr, sample_num, k0, k1, out, d_idx, pf->stream));
     CU(launch_count_emitted(pf->d_thr, sample_num, pf->d_prefix, n, pf->d_int, pf->stream));
@@ -1123,9 +1138,10 @@ int amcl3d_b200_pf_prefix(amcl3d_b200_pf_t pf, void** d_prefix, float* host_out,
   if (int rc = use_device(pf->grid->device))
     return rc;
   CU(ensure(pf->d_prefix, pf->prefix_cap, pf->n));
+  CU(ensure(pf->d_dense, pf->dense_cap, pf->n));
   {
     Timed t(pf);
-    CU(launch_chain_prefix(pf->d_p, pf->n, 0, pf->d_prefix, nullptr, pf->stream));
+    CU(launch_chain_prefix(pf->d_p, pf->n, 0, pf->d_prefix, nullptr, pf->d_dense, pf->stream));
     pf->launches += 1;
   }
   if (host_out && pf->n)

@@ -130,6 +130,278 @@ __global__ void __launch_bounds__(kChainThreads)
     total[0] = acc;
 }
 
+// ---- exact parallel evaluation of the sequential f32 recurrence ---------------------------------------
+// c_i = fl(c_{i-1} + w_i), w_i >= 0.  While the running sum stays inside one binade [2^e, 2^(e+1)) every
+// add rounds onto the fixed grid u = 2^(e-23): with c = s*u and w = (k + f)*u the result is
+//   s' = s + k            (f < 1/2)        s' = s + k + 1     (f > 1/2)
+//   s' = s + k + ((s+k)&1)                 (f == 1/2, ties to even)
+// i.e. an integer step that depends on the input only through its parity.  Such steps compose
+// associatively as pairs (increment for even input, increment for odd input), so a whole binade is an
+// integer prefix scan -- bit-identical to the serial chain.  The first element whose result reaches
+// 2^(e+1) (a binade crossing: at most a few dozen per array) is redone with a real f32 add and the scan
+// restarts on the coarser grid.  Negative / non-finite operands and denormal sums also take the serial add.
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 16;
+constexpr unsigned long long kNoCross = ~0ull;
+constexpr int kSat = 1 << 28;
+
+struct StepFn
+{
+  int d0, d1;  // increment in units of u for an even / odd input state
+};
+__device__ __forceinline__ StepFn step_compose(StepFn f, StepFn g)  // f first, then g
+{
+  StepFn r;
+  r.d0 = min(f.d0 + ((f.d0 & 1) ? g.d1 : g.d0), kSat);
+  r.d1 = min(f.d1 + (((f.d1 + 1) & 1) ? g.d1 : g.d0), kSat);
+  return r;
+}
+// step of one operand on the grid of binade e: k and class (0 round down, 1 round up, 2 tie)
+__device__ __forceinline__ void step_classify(float w, int e, int& k, int& cls)
+{
+  const uint32_t b = __float_as_uint(w);
+  k = 0;
+  cls = 0;
+  if (b == 0u)
+    return;
+  const uint32_t ew = (b >> 23) & 0xFFu;
+  if ((b & 0x80000000u) || ew == 0xFFu)
+  {
+    k = kSat;  // negative, NaN, Inf: force the serial add
+    return;
+  }
+  if (ew == 0u)
+    return;  // denormal operand against a normal sum with e >= -100: far below u/2
+  const uint32_t m = (b & 0x7FFFFFu) | 0x800000u;
+  const int sh = e - ((int)ew - 127);
+  if (sh < 0)
+  {
+    k = kSat;  // operand above the sum's binade: certain crossing
+    return;
+  }
+  if (sh == 0)
+  {
+    k = (int)m;
+    return;
+  }
+  if (sh >= 25)
+    return;
+  k = (int)(m >> sh);
+  const uint32_t rem = m & ((1u << sh) - 1u);
+  const uint32_t half = 1u << (sh - 1);
+  cls = rem > half ? 1 : (rem == half ? 2 : 0);
+}
+__device__ __forceinline__ int step_apply(int s, int k, int cls)
+{
+  const int b = min(s + k, kSat);
+  return b + (cls == 1 ? 1 : 0) + (cls == 2 ? (b & 1) : 0);
+}
+__device__ __forceinline__ float state_value(int e, int s)  // s in [2^23, 2^24)
+{
+  return __uint_as_float(((uint32_t)(e + 127) << 23) | ((uint32_t)s & 0x7FFFFFu));
+}
+
+// mode / operands as chain_kernel.  Threshold mode: out[0] = start, out[k] = value after k adds (n = S).
+__global__ void __launch_bounds__(kScanThreads)
+    exact_scan_kernel(const float* __restrict__ src, uint32_t stride, uint32_t offset, uint64_t n, int mode, float start,
+                      float inc, float* __restrict__ prefix, float* __restrict__ total)
+{
+  __shared__ float sh_c;
+  __shared__ unsigned long long sh_i, sh_cross;
+  __shared__ int sh_s;
+  __shared__ StepFn warp_fn[kScanThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // number of adds: thresholds emit S values from S-1 adds
+  const uint64_t nadd = (mode == kChainThreshold) ? (n > 0 ? n - 1 : 0) : n;
+
+  auto operand = [&](uint64_t i) -> float {
+    if (mode == kChainThreshold)
+      return inc;
+    const float v = src[i * stride + offset];
+    if (mode == kChainSumPositive)
+      return v > 0.f ? v : 0.f;
+    return v;
+  };
+  auto emit = [&](uint64_t i, float v) {
+    if (prefix == nullptr)
+      return;
+    if (mode == kChainThreshold)
+      prefix[i + 1] = v;
+    else
+      prefix[i] = v;
+  };
+
+  if (tid == 0)
+  {
+    sh_c = start;
+    sh_i = 0;
+    if (mode == kChainThreshold && prefix != nullptr && n > 0)
+      prefix[0] = start;
+  }
+  __syncthreads();
+
+  while (true)
+  {
+    // ---- serial phase: the crossing element (or anything the integer scheme does not cover) ----------
+    if (tid == 0)
+    {
+      uint64_t i = sh_i;
+      float c = sh_c;
+      while (i < nadd)
+      {
+        const float w = operand(i);
+        const uint32_t cb = __float_as_uint(c);
+        const int ce = (int)((cb >> 23) & 0xFFu);
+        const bool c_ok = !(cb & 0x80000000u) && ce > 27 && ce < 0xFF;  // positive, normal, e >= -99
+        if (c_ok && w >= 0.f)
+        {
+          const float r = __fadd_rn(c, w);
+          if (((__float_as_uint(r) >> 23) & 0xFFu) == (uint32_t)ce)
+          {
+            // stays in the binade.  Hand over to the scan only if the binade is expected to last a while
+            // (room to the next power of two vs the current operand); otherwise a block-wide round would
+            // be spent on a handful of elements -- purely a scheduling heuristic, both paths are exact.
+            const float top = __uint_as_float((uint32_t)(ce + 1) << 23);
+            if (__fsub_rn(top, c) > w * 256.f)
+              break;
+          }
+        }
+        c = __fadd_rn(c, w);
+        emit(i, c);
+        ++i;
+      }
+      sh_c = c;
+      sh_i = i;
+    }
+    __syncthreads();
+    uint64_t base = sh_i;
+    const float c0 = sh_c;
+    if (base >= nadd)
+      break;
+    const int e = (int)((__float_as_uint(c0) >> 23) & 0xFFu) - 127;
+    int s_chunk = (int)((__float_as_uint(c0) & 0x7FFFFFu) | 0x800000u);
+
+    // ---- parallel phase: chunks of kScanThreads * kScanItems operands inside binade e --------------------
+    while (true)
+    {
+      const uint64_t idx0 = base + (uint64_t)tid * kScanItems;
+      int k[kScanItems], cls[kScanItems];
+      StepFn f{ 0, 0 };
+#pragma unroll
+      for (int j = 0; j < kScanItems; ++j)
+      {
+        k[j] = 0;
+        cls[j] = 0;
+        if (idx0 + j < nadd)
+        {
+          step_classify(operand(idx0 + j), e, k[j], cls[j]);
+          StepFn g;
+          g.d0 = min(k[j] + (cls[j] == 1 ? 1 : 0) + (cls[j] == 2 ? (k[j] & 1) : 0), kSat);
+          g.d1 = min(k[j] + (cls[j] == 1 ? 1 : 0) + (cls[j] == 2 ? ((k[j] + 1) & 1) : 0), kSat);
+          f = step_compose(f, g);
+        }
+      }
+      // inclusive scan of the per-thread functions across the block
+      StepFn incl = f;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        StepFn p;
+        p.d0 = __shfl_up_sync(0xffffffffu, incl.d0, o);
+        p.d1 = __shfl_up_sync(0xffffffffu, incl.d1, o);
+        if (lane >= o)
+          incl = step_compose(p, incl);
+      }
+      if (lane == 31)
+        warp_fn[warp] = incl;
+      if (tid == 0)
+        sh_cross = kNoCross;
+      __syncthreads();
+      if (warp == 0)
+      {
+        StepFn wf = warp_fn[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+          StepFn p;
+          p.d0 = __shfl_up_sync(0xffffffffu, wf.d0, o);
+          p.d1 = __shfl_up_sync(0xffffffffu, wf.d1, o);
+          if (lane >= o)
+            wf = step_compose(p, wf);
+        }
+        warp_fn[lane] = wf;  // inclusive over warps
+      }
+      __syncthreads();
+      // exclusive prefix function of this thread = (warps before) o (lanes before)
+      StepFn lane_excl;
+      lane_excl.d0 = __shfl_up_sync(0xffffffffu, incl.d0, 1);
+      lane_excl.d1 = __shfl_up_sync(0xffffffffu, incl.d1, 1);
+      if (lane == 0)
+        lane_excl = StepFn{ 0, 0 };
+      StepFn excl = lane_excl;
+      if (warp > 0)
+        excl = step_compose(warp_fn[warp - 1], lane_excl);
+      const StepFn block_total = warp_fn[kScanThreads / 32 - 1];
+
+      int s = min(s_chunk + ((s_chunk & 1) ? excl.d1 : excl.d0), kSat);
+      unsigned long long my_cross = kNoCross;
+      int s_before_cross = 0;
+      if (s >= (1 << 24) && idx0 < nadd)
+        my_cross = idx0;  // an earlier thread already crossed; its index is smaller and wins the min below
+#pragma unroll
+      for (int j = 0; j < kScanItems; ++j)
+      {
+        if (idx0 + j < nadd && my_cross == kNoCross)
+        {
+          const int s2 = step_apply(s, k[j], cls[j]);
+          if (s2 >= (1 << 24))
+          {
+            my_cross = idx0 + j;
+            s_before_cross = s;
+          }
+          else
+          {
+            emit(idx0 + j, state_value(e, s2));
+            s = s2;
+          }
+        }
+      }
+      if (my_cross != kNoCross)
+        atomicMin(&sh_cross, my_cross);
+      __syncthreads();
+      const unsigned long long cross = sh_cross;
+      if (cross != kNoCross)
+      {
+        // the owner of the first crossing knows the state just before it (threads that only inherited an
+        // overflowed state have larger indices)
+        if (my_cross == cross && s_before_cross != 0)
+        {
+          sh_c = state_value(e, s_before_cross);
+          sh_i = cross;
+        }
+        __syncthreads();
+        break;
+      }
+      const uint64_t chunk = (uint64_t)kScanThreads * kScanItems;
+      s_chunk = s_chunk + ((s_chunk & 1) ? block_total.d1 : block_total.d0);
+      base += chunk;
+      if (base >= nadd)
+      {
+        if (tid == 0)
+        {
+          sh_c = state_value(e, s_chunk);
+          sh_i = nadd;
+        }
+        __syncthreads();
+        break;
+      }
+      __syncthreads();  // warp_fn / sh_cross are rewritten by the next chunk
+    }
+  }
+  if (tid == 0 && total != nullptr)
+    total[0] = sh_c;
+}
+
 __device__ __forceinline__ bool into_map(const MapDev& map, float x, float y, float z)
 {
   return map.has_map && ((double)x >= map.min[0]) && ((double)x < map.max[0]) && ((double)y >= map.min[1]) &&
@@ -506,18 +778,45 @@ size_t reduce_scratch_bytes()
   return (size_t)16384 + (size_t)kRedBlocks * 7 * sizeof(double) + 256;
 }
 
-cudaError_t launch_chain_prefix(const float* particles, uint64_t n, int positive_only, float* prefix, float* total,
-                                cudaStream_t stream)
+// weights out of the AoS particle records into a dense array (coalesced operands for the scan)
+__global__ void extract_weights_kernel(const float* __restrict__ particles, uint64_t n, float* __restrict__ dense)
 {
-  chain_kernel<<<1, kChainThreads, 0, stream>>>(particles, 7, 6, n, positive_only ? kChainSumPositive : kChainSum, 0.f,
-                                                0.f, prefix, total);
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    dense[i] = particles[7 * i + 6];
+}
+
+// 0: exact parallel scan (default), 1: the serial chain kernel (kept for A/B and as the simple reference)
+static int g_chain_mode = 0;
+void set_chain_mode(int mode)
+{
+  g_chain_mode = mode;
+}
+static cudaError_t launch_chain(const float* src, uint32_t stride, uint32_t offset, uint64_t n, int mode, float start,
+                                float inc, float* prefix, float* total, cudaStream_t stream)
+{
+  if (g_chain_mode == 1)
+    chain_kernel<<<1, kChainThreads, 0, stream>>>(src, stride, offset, n, mode, start, inc, prefix, total);
+  else
+    exact_scan_kernel<<<1, kScanThreads, 0, stream>>>(src, stride, offset, n, mode, start, inc, prefix, total);
   return cudaGetLastError();
+}
+
+cudaError_t launch_chain_prefix(const float* particles, uint64_t n, int positive_only, float* prefix, float* total,
+                                float* dense_scratch, cudaStream_t stream)
+{
+  const int mode = positive_only ? kChainSumPositive : kChainSum;
+  if (dense_scratch != nullptr && n > 0 && g_chain_mode == 0)
+  {
+    extract_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(particles, n, dense_scratch);
+    return launch_chain(dense_scratch, 1, 0, n, mode, 0.f, 0.f, prefix, total, stream);
+  }
+  return launch_chain(particles, 7, 6, n, mode, 0.f, 0.f, prefix, total, stream);
 }
 
 cudaError_t launch_chain_sum_array(const float* v, uint64_t n, float* total, cudaStream_t stream)
 {
-  chain_kernel<<<1, kChainThreads, 0, stream>>>(v, 1, 0, n, kChainSum, 0.f, 0.f, nullptr, total);
-  return cudaGetLastError();
+  return launch_chain(v, 1, 0, n, kChainSum, 0.f, 0.f, nullptr, total, stream);
 }
 
 cudaError_t launch_chain_thresholds(int S, float* thr, cudaStream_t stream)
@@ -526,9 +825,7 @@ cudaError_t launch_chain_thresholds(int S, float* thr, cudaStream_t stream)
     return cudaSuccess;
   const float inteval = 1.0f / S;  // ParticleFilter.cpp:267 (IEEE f32 divide on the host)
   const float samp0 = 0.5f / S;    // ParticleFilter.cpp:268
-  chain_kernel<<<1, kChainThreads, 0, stream>>>(nullptr, 1, 0, (uint64_t)S, kChainThreshold, samp0, inteval, thr,
-                                                nullptr);
-  return cudaGetLastError();
+  return launch_chain(nullptr, 1, 0, (uint64_t)S, kChainThreshold, samp0, inteval, thr, nullptr, stream);
 }
 
 cudaError_t launch_normalize(const MapDev& map, float* particles, uint64_t n, const float* total, cudaStream_t stream)

@@ -96,6 +96,11 @@ int amcl3d_b200_device_info(int device, int* device_count, int* sm_count, int* c
 int amcl3d_b200_set_l2_fetch_granularity(int device, int bytes);
 int amcl3d_b200_get_l2_fetch_granularity(int device, int* bytes);
 
+/* How the sequential f32 recurrences of particleNormalize / resample / uniformSample are evaluated
+ * (process-wide): 0 (default) the exact parallel binade scan, 1 the plain serial chain kernel.  Both give
+ * the reference's bits; the switch exists for A/B timing and cross-checking. */
+int amcl3d_b200_set_chain_mode(int mode);
+
 /* ---- Grid3d (amcl3d/src/Grid3d.{h,cpp}, PointCloudTools.{h,cpp}) ---------------------------- */
 int amcl3d_b200_grid_create(int device, amcl3d_b200_grid_t* out);
 int amcl3d_b200_grid_destroy(amcl3d_b200_grid_t g);

@@ -362,3 +362,76 @@ def test_update_on_coded_grid_is_bit_identical(O, world_c1, lattice, sensor_dev,
     pf2.p_ = P
     pf2.update(cloud)
     assert np.array_equal(bits(pf2.p_[:, 6]), bits(ref[:, 6]))
+
+
+def _weights_cases():
+    rng = np.random.RandomState(99)
+    n = 70_000
+    cases = {
+        "gamma": rng.gamma(2.0, 1.0, n),
+        "equal_1_over_n": np.full(n, 1.0 / n),                       # after a resample: every add is a potential tie
+        "powers_of_two": 2.0 ** rng.randint(-30, 3, n),              # exact ties on every grid
+        "equal_pow2": np.full(n, 2.0 ** -14),
+        "with_zeros": np.where(rng.rand(n) < 0.7, 0.0, rng.rand(n)),
+        "huge_outliers": np.where(rng.rand(n) < 0.001, 1e6 * rng.rand(n), rng.rand(n) * 1e-3),
+        "tiny_then_big": np.concatenate([np.full(n // 2, 1e-30), rng.rand(n - n // 2)]),
+        "denormals": np.concatenate([np.full(1000, 1e-42), rng.rand(n - 1000) * 1e-36]),
+        "growing": np.exp(np.linspace(-20, 5, n)),                   # crosses a binade every few elements at the start
+        "half_ulp_ties": np.concatenate([[1.0], np.full(n - 1, 2.0 ** -24)]),
+        "single": np.array([0.37]),
+        "two": np.array([0.5, 0.5]),
+        "all_zero": np.zeros(1000),
+        "negatives_mixed": rng.normal(0.2, 1.0, 5000),               # not a weight vector: exercises the serial escape
+    }
+    return {k: v.astype(np.float32) for k, v in cases.items()}
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("name", sorted(_weights_cases()))
+def test_sequential_f32_chains_bit_exact(O, world_c1, pf, name, mode):
+    """The sequential f32 recurrences (weight sum, inclusive prefix) evaluated by the exact parallel binade scan
+    (mode 0) and by the serial chain kernel (mode 1) against the oracle's plain loops, on adversarial inputs."""
+    from amcl3d_test_b200 import api
+
+    w = _weights_cases()[name]
+    P = np.zeros((w.size, 7), np.float32)
+    P[:, :3] = np.array([10, 10, 1.0], np.float32)
+    P[:, 6] = w
+    api.set_chain_mode(mode)
+    try:
+        pf.p_ = P
+        assert np.array_equal(bits(pf.prefix()), bits(O.prefix(P))), name
+        ref = P.copy()
+        wtp = O.normalize(world_c1["map"], ref)
+        assert bits(pf.particleNormalize()) == bits(wtp), name
+        assert np.array_equal(bits(pf.p_[:, 6]), bits(ref[:, 6])), name
+    finally:
+        api.set_chain_mode(0)
+
+
+@pytest.mark.parametrize("S", [1, 2, 3, 600, 8191, 8192, 8193, 100_000, 1_000_003])
+def test_threshold_chain_bit_exact(O, world_c1, pf, S):
+    """samp_{k+1} = samp_k + 1/S as a sequential f32 chain (ParticleFilter.cpp:267-275), via uniformSample indices."""
+    rng = np.random.RandomState(S % 1000)
+    n = 5000
+    P = world_c1["T"][:1].repeat(n, 0).copy()
+    P[:, 6] = rng.gamma(2.0, 1.0, n).astype(np.float32)
+    ref_out, ref_idx, ref_k = O.uniform_sample(world_c1["map"], P.copy(), S)
+    pf.p_ = P
+    idx, emitted = pf.uniformSample(S, want_idx=True)
+    assert emitted == ref_k
+    assert np.array_equal(idx, ref_idx)
+
+
+def test_resample_one_million_bit_exact(O, world_c1, pf):
+    rng = np.random.RandomState(5)
+    n = 1_000_000
+    P = world_c1["T"][:1].repeat(n, 0).copy()
+    P[:, 6] = rng.gamma(1.5, 1.0, n).astype(np.float32)
+    ref = P.copy()
+    O.normalize(world_c1["map"], ref)
+    ref_out, ref_idx = O.resample(ref, np.float32(0.618))
+    pf.p_ = P
+    pf.particleNormalize()
+    idx = pf.resample(np.float32(0.618), want_idx=True)
+    assert np.array_equal(idx, ref_idx)

@@ -200,6 +200,10 @@ class ParticleFilter:
     def set_stream(self, cuda_stream: int | None):
         check(self._L.amcl3d_b200_pf_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
+    def set_two_phase(self, enable: bool):
+        """A/B switch of the Morton-sweep + ordered-sum update (bit-identical results either way)."""
+        check(self._L.amcl3d_b200_pf_set_two_phase(self._h, int(bool(enable))))
+
     def set_trig_mode(self, mode):
         check(self._L.amcl3d_b200_pf_set_trig_mode(self._h, mode))
 

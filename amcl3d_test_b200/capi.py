@@ -21,6 +21,7 @@ SYMBOLS = [
     "amcl3d_b200_grid_save_file", "amcl3d_b200_grid_load_file", "amcl3d_b200_grid_is_into_map",
     "amcl3d_b200_grid_cloud_weight", "amcl3d_b200_grid_device_ptr", "amcl3d_b200_grid_use_codes",
     "amcl3d_b200_pf_create", "amcl3d_b200_pf_destroy", "amcl3d_b200_pf_set_trig_mode", "amcl3d_b200_pf_set_stream",
+    "amcl3d_b200_pf_set_two_phase",
     "amcl3d_b200_pf_set_particles", "amcl3d_b200_pf_get_particles", "amcl3d_b200_pf_size",
     "amcl3d_b200_pf_bind_device", "amcl3d_b200_pf_device_ptr", "amcl3d_b200_pf_set_cloud",
     "amcl3d_b200_pf_set_cloud_device", "amcl3d_b200_pf_update", "amcl3d_b200_pf_update_cloud",
@@ -94,6 +95,7 @@ def load():
         "amcl3d_b200_pf_destroy": (i, [vp]),
         "amcl3d_b200_pf_set_trig_mode": (i, [vp, i]),
         "amcl3d_b200_pf_set_stream": (i, [vp, vp]),
+        "amcl3d_b200_pf_set_two_phase": (i, [vp, i]),
         "amcl3d_b200_pf_set_particles": (i, [vp, vp, u64]),
         "amcl3d_b200_pf_get_particles": (i, [vp, vp, u64, P(u64)]),
         "amcl3d_b200_pf_size": (i, [vp, P(u64)]),

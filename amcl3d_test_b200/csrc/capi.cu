@@ -102,6 +102,16 @@ struct amcl3d_b200_pf_s
   uint32_t npts = 0, npad = 0;
   float* d_stage = nullptr;
   uint64_t stage_cap = 0;
+  // two-phase sweep: Morton-sorted cloud, row of every original point, sort scratch, staged codes
+  float4* d_sorted = nullptr;
+  uint64_t sorted_cap = 0;
+  uint32_t* d_row_of = nullptr;
+  uint64_t row_of_cap = 0;
+  char* d_sort_scratch = nullptr;
+  uint64_t sort_scratch_cap = 0;
+  uint8_t* d_codes_staged = nullptr;
+  uint64_t codes_staged_cap = 0;
+  int two_phase = 1;  // AMCL3D_B200_TWO_PHASE=0 / amcl3d_b200_pf_set_two_phase disables
   // scratch
   float* d_prefix = nullptr;
   uint64_t prefix_cap = 0;
@@ -637,7 +647,7 @@ int amcl3d_b200_grid_cloud_weight(amcl3d_b200_grid_t g, const float* cloud, uint
   // (offsets use map.min, so pass the true min through and lift only the gate via has_map semantics):
   // the kernel gates on min/max, so use a dedicated flag value 2 = "do not gate"
   open.has_map = 2;
-  CU(launch_update(open, pf->d_p, 1, pf->d_cloud, pf->npts, pf->npad, pf->d_beacons, nullptr, trig_mode, nullptr,
+  CU(launch_update(open, pf->d_p, 1, pf->d_cloud, pf->npts, pf->npad, pf->d_beacons, nullptr, trig_mode, nullptr, nullptr,
                    pf->stream));
   pf->launches++;
   float out7[7];
@@ -660,6 +670,8 @@ int amcl3d_b200_pf_create(amcl3d_b200_grid_t g, amcl3d_b200_pf_t* out)
   if (!pf)
     return fail(AMCL3D_B200_ERR_ARG, "out of host memory");
   pf->grid = g;
+  if (const char* env = getenv("AMCL3D_B200_TWO_PHASE"))
+    pf->two_phase = atoi(env) != 0;
   cudaError_t e = cudaStreamCreateWithFlags(&pf->own_stream, cudaStreamNonBlocking);
   pf->stream = pf->own_stream;
   if (e == cudaSuccess)
@@ -699,6 +711,10 @@ int amcl3d_b200_pf_destroy(amcl3d_b200_pf_t pf)
   cudaFree(pf->d_alt);
   cudaFree(pf->d_cloud);
   cudaFree(pf->d_stage);
+  cudaFree(pf->d_sorted);
+  cudaFree(pf->d_row_of);
+  cudaFree(pf->d_sort_scratch);
+  cudaFree(pf->d_codes_staged);
   cudaFree(pf->d_prefix);
   cudaFree(pf->d_thr);
   cudaFree(pf->d_wr);
@@ -726,6 +742,14 @@ int amcl3d_b200_pf_set_trig_mode(amcl3d_b200_pf_t pf, int trig_mode)
   if (!pf || (trig_mode != AMCL3D_B200_TRIG_F64 && trig_mode != AMCL3D_B200_TRIG_F32))
     return fail(AMCL3D_B200_ERR_ARG, "bad trig mode");
   pf->trig_mode = trig_mode;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_set_two_phase(amcl3d_b200_pf_t pf, int enable)
+{
+  if (!pf)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+  pf->two_phase = enable != 0;
   return AMCL3D_B200_OK;
 }
 
@@ -812,6 +836,16 @@ static int set_cloud_common(amcl3d_b200_pf_t pf, const float* d_src, uint32_t st
   CU(ensure(pf->d_cloud, pf->cloud_cap, npad));
   CU(launch_pack_cloud(d_src, stride, npts, pf->d_cloud, npad, pf->stream));
   pf->launches += npad ? 1 : 0;
+  if (pf->two_phase && npts > 0)
+  {
+    // Morton order of this cloud for the two-phase sweep (keys + radix sort + pack: a few microseconds)
+    CU(ensure(pf->d_sorted, pf->sorted_cap, npad));
+    CU(ensure(pf->d_row_of, pf->row_of_cap, npts));
+    const size_t need = sort_cloud_scratch_bytes(npts);
+    CU(ensure(pf->d_sort_scratch, pf->sort_scratch_cap, need));
+    CU(launch_sort_cloud(d_src, stride, npts, npad, pf->d_sorted, pf->d_row_of, pf->d_sort_scratch, need, pf->stream));
+    pf->launches += 3;
+  }
   pf->npts = npts;
   pf->npad = npad;
   return AMCL3D_B200_OK;
@@ -876,11 +910,28 @@ int amcl3d_b200_pf_update(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beaco
     d_counter = pf->d_u64;
     CU(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), pf->stream));
   }
+  // two-phase sweep when it pays: enough particles to fill the machine, a u8-coded grid, staging that fits
+  TwoPhase tp{};
+  const TwoPhase* tpp = nullptr;
+  if (pf->two_phase && pf->n >= 4096 && pf->npts >= 64 && pf->d_sorted != nullptr && map.rep == kRepCode8 && map.lut_n < 255)
+  {
+    const uint64_t pitch = (pf->n + 127) & ~127ull;
+    const uint64_t bytes = pitch * pf->npad;
+    if (bytes <= (16ull << 30))
+    {
+      CU(ensure(pf->d_codes_staged, pf->codes_staged_cap, bytes));
+      tp.sorted = pf->d_sorted;
+      tp.row_of = pf->d_row_of;
+      tp.stage = pf->d_codes_staged;
+      tp.pitch = pitch;
+      tpp = &tp;
+    }
+  }
   {
     Timed t(pf);
     CU(launch_update(map, pf->d_p, (uint32_t)pf->n, pf->d_cloud, pf->npts, pf->npad, pf->d_beacons, d_wr, pf->trig_mode,
-                     d_counter, pf->stream));
-    pf->launches += pf->n ? 1 : 0;
+                     d_counter, tpp, pf->stream));
+    pf->launches += pf->n ? (tpp ? 2 : 1) : 0;
     if (nb && pf->n)
     {
       // w = alpha*wp/sum(wp) + (1-alpha)*wr/sum(wr): both sums as sequential f32 chains

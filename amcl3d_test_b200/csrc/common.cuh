@@ -103,9 +103,22 @@ struct BeaconSet
 // particles: AoS 7 floats; cloud4: (x,y,z,0) per point padded with NaN points to a multiple of 32.
 // wr_out (nullable) receives the raw range-beacon weight per particle; counter (nullable) the number
 // of evaluations that loaded a voxel.
+// Two-phase sweep state (nullptr / stage == nullptr: single-kernel path): the Morton-sorted cloud, the row of
+// every original point in that order, and the staging matrix stage[row * pitch + particle] of 1-byte codes.
+struct TwoPhase
+{
+  const float4* sorted;
+  const uint32_t* row_of;
+  uint8_t* stage;
+  size_t pitch;
+};
 cudaError_t launch_update(const MapDev& map, float* particles, uint32_t n, const float4* cloud4, uint32_t npts,
                           uint32_t npts_padded, const BeaconSet* beacons, float* wr_out, int trig_mode,
-                          unsigned long long* counter, cudaStream_t stream);
+                          unsigned long long* counter, const TwoPhase* tp, cudaStream_t stream);
+// Morton order of a strided device cloud: sorted (npts_padded float4, NaN padded) + row_of (npts)
+cudaError_t launch_sort_cloud(const float* src, uint32_t stride, uint32_t npts, uint32_t npts_padded, float4* sorted,
+                              uint32_t* row_of, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+size_t sort_cloud_scratch_bytes(uint32_t npts);
 // packs a strided cloud (device memory) into cloud4 and pads with NaN points up to npts_padded
 cudaError_t launch_pack_cloud(const float* src, uint32_t stride, uint32_t npts, float4* dst, uint32_t npts_padded,
                               cudaStream_t stream);

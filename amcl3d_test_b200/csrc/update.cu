@@ -25,6 +25,8 @@
 
 #include <math_constants.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 namespace a3d
 {
 namespace
@@ -280,11 +282,41 @@ __device__ __forceinline__ void batch_consume(const typename Raw<kRep>::type raw
   cnt += __popc(mask);
 }
 
-// one tile of `count` points (a multiple of 2*kUnroll) for one particle
-template <bool kF32Offset, int kRep>
-__device__ __forceinline__ void tile_loop(const MapDev& map, const float4* __restrict__ tile, uint32_t count,
-                                          const float r[9], const float off_f[3], const double off_d[3],
-                                          const float* __restrict__ lut_s, float& weight, int& cnt)
+// Where the gathered values of a batch go.
+//  * AccumSink: the reference's in-order f32 accumulation (Grid3d.cpp:292) -- the single-kernel path, the
+//    cloud is swept in its own order.
+//  * StageSink: two-phase path.  The cloud is swept in a spatially coherent (Morton) order so that all
+//    particles work in the same neighbourhood of the map at the same time (L2 / TLB locality), and the
+//    1-byte codes are parked in a staging matrix stage[row][particle]; ordered_sum_kernel then adds them
+//    in the ORIGINAL cloud order, so the rounding sequence -- and every bit of the weight -- is unchanged.
+template <int kRep>
+struct AccumSink
+{
+  const float* __restrict__ lut_s;
+  float weight;
+  int cnt;
+  __device__ __forceinline__ void put(const typename Raw<kRep>::type raw[kUnroll], uint32_t mask, uint32_t /*row*/)
+  {
+    batch_consume<kRep>(raw, mask, lut_s, weight, cnt);
+  }
+};
+constexpr uint32_t kStageSkip = 0xFFu;  // staged code of an evaluation that loaded nothing
+struct StageSink
+{
+  uint8_t* __restrict__ column;  // &stage[0][particle]
+  size_t pitch;                  // bytes from one row (cloud point) to the next
+  __device__ __forceinline__ void put(const uint32_t raw[kUnroll], uint32_t mask, uint32_t row)
+  {
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      column[(size_t)(row + u) * pitch] = (uint8_t)(((mask >> u) & 1u) ? raw[u] : kStageSkip);
+  }
+};
+
+// one tile of `count` points (a multiple of 2*kUnroll) for one particle; row0 = index of tile[0] in the sweep
+template <bool kF32Offset, int kRep, typename Sink>
+__device__ __forceinline__ void tile_loop(const MapDev& map, const float4* __restrict__ tile, uint32_t count, uint32_t row0,
+                                          const float r[9], const float off_f[3], const double off_d[3], Sink& sink)
 {
   typedef typename Raw<kRep>::type raw_t;
   uint64_t addr[kUnroll];
@@ -297,24 +329,69 @@ __device__ __forceinline__ void tile_loop(const MapDev& map, const float4* __res
   {
     mask_b = batch_addresses<kF32Offset, kRep>(map, tile + base, r, off_f, off_d, addr);
     batch_issue<kRep>(map, addr, mask_b, raw_b);
-    batch_consume<kRep>(raw_a, mask_a, lut_s, weight, cnt);
+    sink.put(raw_a, mask_a, row0 + base - kUnroll);
     if (base + kUnroll < count)
     {
       mask_a = batch_addresses<kF32Offset, kRep>(map, tile + base + kUnroll, r, off_f, off_d, addr);
       batch_issue<kRep>(map, addr, mask_a, raw_a);
     }
-    batch_consume<kRep>(raw_b, mask_b, lut_s, weight, cnt);
+    sink.put(raw_b, mask_b, row0 + base);
   }
+}
+
+// per-particle epilogue shared by the one- and two-phase paths
+__device__ __forceinline__ void finish_particle(float* __restrict__ particles, uint32_t i, bool inmap, float weight, int cnt,
+                                                uint32_t npts, float px, float py, float pz,
+                                                const BeaconSet* __restrict__ beacons, float* __restrict__ wr_out)
+{
+  // Grid3d.cpp:299: (n < 10) ? 0 : weight / cloud->size()   (f32 / (float)size_t)
+  float w = 0.f;
+  if (inmap && cnt >= 10)
+    w = __fdiv_rn(weight, __uint2float_rn(npts));
+  particles[(size_t)7 * i + 6] = w;
+  if (wr_out != nullptr)
+  {
+    // row R: wr = prod_b k1*exp(-k2*(|p - a_b| - r_b)^2); 0 outside the map or without beacons
+    float wr = 0.f;
+    const uint32_t nb = beacons->n;
+    if (inmap && nb > 0)
+    {
+      wr = 1.f;
+      const float k1 = beacons->k1, k2 = beacons->k2;
+      for (uint32_t b = 0; b < nb; ++b)
+      {
+        const float dx = __fsub_rn(px, beacons->ax[b]);
+        const float dy = __fsub_rn(py, beacons->ay[b]);
+        const float dz = __fsub_rn(pz, beacons->az[b]);
+        const float rr = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+        const float e = __fsub_rn(rr, beacons->r[b]);
+        wr = __fmul_rn(wr, __fmul_rn(k1, expf(__fmul_rn(__fmul_rn(-k2, e), e))));
+      }
+    }
+    wr_out[i] = wr;
+  }
+}
+__device__ __forceinline__ bool particle_gate(const MapDev& map, float px, float py, float pz)
+{
+  // Grid3d.cpp:365-372 -- f32 promoted against the f64 bounds; update() skips particles outside
+  // (has_map == 2: Grid3d::computeCloudWeight called directly, which has no such gate)
+  const bool gate = (map.has_map == 2) ||
+                    (((double)px >= map.min[0]) && ((double)px < map.max[0]) && ((double)py >= map.min[1]) &&
+                     ((double)py < map.max[1]) && ((double)pz >= map.min[2]) && ((double)pz < map.max[2]));
+  return map.has_map && map.has_grid && gate;
 }
 
 #ifndef AMCL3D_MINBLOCKS
 #define AMCL3D_MINBLOCKS 6
 #endif
-template <int kRep>
+// kStage == false: the whole update in one kernel (sweep in cloud order, accumulate in registers).
+// kStage == true : phase 1 of the two-phase path (sweep the Morton-sorted cloud, park codes in `stage`).
+template <int kRep, bool kStage>
 __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
     update_kernel(const __grid_constant__ MapDev map, float* __restrict__ particles, uint32_t n,
                   const float4* __restrict__ cloud, uint32_t npts, uint32_t npad, const BeaconSet* __restrict__ beacons,
-                  float* __restrict__ wr_out, int trig_mode, unsigned long long* __restrict__ counter)
+                  float* __restrict__ wr_out, int trig_mode, unsigned long long* __restrict__ counter,
+                  uint8_t* __restrict__ stage, size_t stage_pitch)
 {
   __shared__ __align__(128) float4 tile[kStages][kTile];
   __shared__ __align__(8) uint64_t full_bar[kStages];
@@ -335,12 +412,7 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
     pitch = p[4];
     yaw = p[5];
   }
-  // Grid3d.cpp:365-372 -- f32 promoted against the f64 bounds; update() skips particles outside
-  // (has_map == 2: Grid3d::computeCloudWeight called directly, which has no such gate)
-  const bool gate = (map.has_map == 2) ||
-                    (((double)px >= map.min[0]) && ((double)px < map.max[0]) && ((double)py >= map.min[1]) &&
-                     ((double)py < map.max[1]) && ((double)pz >= map.min[2]) && ((double)pz < map.max[2]));
-  const bool inmap = live && map.has_map && map.has_grid && gate;
+  const bool inmap = live && particle_gate(map, px, py, pz);
 
   float r[9];
   rotation(roll, pitch, yaw, trig_mode, r);
@@ -368,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
       mbar_init(&full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (kRep != kRepFloat)
+  if (kRep != kRepFloat && !kStage)
     for (uint32_t k = tid; k < map.lut_n; k += kThreads)
       lut_s[k] = map.lut[k];
   __syncthreads();
@@ -382,8 +454,8 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
     }
   }
 
-  float weight = 0.f;
-  int cnt = 0;
+  AccumSink<kRep> acc{ lut_s, 0.f, 0 };
+  StageSink park{ stage + i, stage_pitch };
   for (uint32_t t = 0; t < ntiles; ++t)
   {
     const uint32_t s = t % kStages;
@@ -392,10 +464,20 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
     const uint32_t count = min((uint32_t)kTile, npad - t * kTile);
     if (inmap)
     {
-      if (warp_f32)
-        tile_loop<true, kRep>(map, &tile[s][0], count, r, off_f, off_d, lut_s, weight, cnt);
+      if constexpr (kStage)
+      {
+        if (warp_f32)
+          tile_loop<true, kRep>(map, &tile[s][0], count, t * kTile, r, off_f, off_d, park);
+        else
+          tile_loop<false, kRep>(map, &tile[s][0], count, t * kTile, r, off_f, off_d, park);
+      }
       else
-        tile_loop<false, kRep>(map, &tile[s][0], count, r, off_f, off_d, lut_s, weight, cnt);
+      {
+        if (warp_f32)
+          tile_loop<true, kRep>(map, &tile[s][0], count, t * kTile, r, off_f, off_d, acc);
+        else
+          tile_loop<false, kRep>(map, &tile[s][0], count, t * kTile, r, off_f, off_d, acc);
+      }
     }
     __syncthreads();  // every lane is done with stage s before TMA overwrites it
     if (tid == 0 && t + kStages < ntiles)
@@ -407,36 +489,83 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
     }
   }
 
+  if (kStage)
+    return;  // ordered_sum_kernel finishes the particle
+  if (live)
+    finish_particle(particles, i, inmap, acc.weight, acc.cnt, npts, px, py, pz, beacons, wr_out);
+  if (counter != nullptr)
+  {
+    unsigned int c = (unsigned int)acc.cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((tid & 31u) == 0 && c)
+      atomicAdd(counter, (unsigned long long)c);
+  }
+}
+
+// Phase 2 of the two-phase path: thread = particle; adds lut[code] in the ORIGINAL cloud order.  row_of[j] is the
+// position of original point j in the Morton sweep.  Reads are coalesced (consecutive particles are consecutive
+// bytes of a row); each staged byte is read exactly once.
+constexpr int kSumThreads = 128;
+constexpr int kSumUnroll = 8;
+__global__ void __launch_bounds__(kSumThreads)
+    ordered_sum_kernel(const __grid_constant__ MapDev map, float* __restrict__ particles, uint32_t n,
+                       const uint8_t* __restrict__ stage, size_t stage_pitch, const uint32_t* __restrict__ row_of, uint32_t npts,
+                       const BeaconSet* __restrict__ beacons, float* __restrict__ wr_out,
+                       unsigned long long* __restrict__ counter)
+{
+  __shared__ float lut_s[256];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t i = blockIdx.x * kSumThreads + tid;
+  for (uint32_t k = tid; k < 256; k += kSumThreads)
+    lut_s[k] = k < map.lut_n ? map.lut[k] : 0.f;
+  __syncthreads();
+  const bool live = i < n;
+  float px = 0, py = 0, pz = 0;
   if (live)
   {
-    // Grid3d.cpp:299: (n < 10) ? 0 : weight / cloud->size()   (f32 / (float)size_t)
-    float w = 0.f;
-    if (inmap && cnt >= 10)
-      w = __fdiv_rn(weight, __uint2float_rn(npts));
-    particles[(size_t)7 * i + 6] = w;
-
-    if (wr_out != nullptr)
+    const float* p = particles + (size_t)7 * i;
+    px = p[0];
+    py = p[1];
+    pz = p[2];
+  }
+  const bool inmap = live && particle_gate(map, px, py, pz);
+  float weight = 0.f;
+  int cnt = 0;
+  if (inmap)
+  {
+    const uint8_t* __restrict__ column = stage + i;
+    uint32_t j = 0;
+    for (; j + kSumUnroll <= npts; j += kSumUnroll)
     {
-      // row R: wr = prod_b k1*exp(-k2*(|p - a_b| - r_b)^2); 0 outside the map or without beacons
-      float wr = 0.f;
-      const uint32_t nb = beacons->n;
-      if (inmap && nb > 0)
+      uint32_t code[kSumUnroll];
+#pragma unroll
+      for (int u = 0; u < kSumUnroll; ++u)
+        code[u] = column[(size_t)__ldg(row_of + j + u) * stage_pitch];
+#pragma unroll
+      for (int u = 0; u < kSumUnroll; ++u)
       {
-        wr = 1.f;
-        const float k1 = beacons->k1, k2 = beacons->k2;
-        for (uint32_t b = 0; b < nb; ++b)
+        const float v = lut_s[code[u]];
+        if (code[u] != kStageSkip)
         {
-          const float dx = __fsub_rn(px, beacons->ax[b]);
-          const float dy = __fsub_rn(py, beacons->ay[b]);
-          const float dz = __fsub_rn(pz, beacons->az[b]);
-          const float rr = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-          const float e = __fsub_rn(rr, beacons->r[b]);
-          wr = __fmul_rn(wr, __fmul_rn(k1, expf(__fmul_rn(__fmul_rn(-k2, e), e))));
+          weight = __fadd_rn(weight, v);  // Grid3d.cpp:292, cloud order
+          ++cnt;
         }
       }
-      wr_out[i] = wr;
+    }
+    for (; j < npts; ++j)
+    {
+      const uint32_t code = column[(size_t)__ldg(row_of + j) * stage_pitch];
+      if (code != kStageSkip)
+      {
+        weight = __fadd_rn(weight, lut_s[code]);
+        ++cnt;
+      }
     }
   }
+  if (live)
+    finish_particle(particles, i, inmap, weight, cnt, npts, px, py, pz, beacons, wr_out);
   if (counter != nullptr)
   {
     unsigned int c = (unsigned int)cnt;
@@ -445,6 +574,56 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
       c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((tid & 31u) == 0 && c)
       atomicAdd(counter, (unsigned long long)c);
+  }
+}
+
+// ---- cloud preparation --------------------------------------------------------------------------------
+// 36-bit Morton key of the sensor-frame position on a 0.25 m lattice (+-512 m); non-finite points sort last
+__global__ void morton_key_kernel(const float* __restrict__ src, uint32_t stride, uint32_t npts, unsigned long long* __restrict__ keys,
+                                  uint32_t* __restrict__ vals)
+{
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= npts)
+    return;
+  const float* p = src + (size_t)j * stride;
+  unsigned long long key = ~0ull >> 28;
+  if (isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]))
+  {
+    key = 0;
+    uint32_t q[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+    {
+      const float c = fminf(fmaxf(floorf(p[a] * 4.f) + 2048.f, 0.f), 4095.f);
+      q[a] = (uint32_t)c;
+    }
+#pragma unroll
+    for (int b = 0; b < 12; ++b)
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        key |= (unsigned long long)((q[a] >> b) & 1u) << (3 * b + a);
+  }
+  keys[j] = key;
+  vals[j] = j;
+}
+// sorted[r] = point order[r] (w = its original index as bits), row_of[order[r]] = r; NaN padding rows
+__global__ void pack_sorted_kernel(const float* __restrict__ src, uint32_t stride, uint32_t npts, const uint32_t* __restrict__ order,
+                                   float4* __restrict__ sorted, uint32_t* __restrict__ row_of, uint32_t npad)
+{
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= npad)
+    return;
+  if (r < npts)
+  {
+    const uint32_t o = order[r];
+    const float* p = src + (size_t)o * stride;
+    sorted[r] = make_float4(p[0], p[1], p[2], __uint_as_float(o));
+    row_of[o] = r;
+  }
+  else
+  {
+    const float nanv = CUDART_NAN_F;
+    sorted[r] = make_float4(nanv, nanv, nanv, 0.f);
   }
 }
 
@@ -537,34 +716,80 @@ __global__ void __launch_bounds__(256)
 
 cudaError_t launch_update(const MapDev& map, float* particles, uint32_t n, const float4* cloud4, uint32_t npts,
                           uint32_t npts_padded, const BeaconSet* beacons, float* wr_out, int trig_mode,
-                          unsigned long long* counter, cudaStream_t stream)
+                          unsigned long long* counter, const TwoPhase* tp, cudaStream_t stream)
 {
   if (n == 0)
     return cudaSuccess;
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
   if (map.rep == kRepFloat || map.codes == nullptr || map.lut_n > kMaxLutSmem)
   {
-    update_kernel<kRepFloat><<<blocks, kThreads, 0, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
-                                                              wr_out, trig_mode, counter);
+    update_kernel<kRepFloat, false><<<blocks, kThreads, 0, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
+                                                                     wr_out, trig_mode, counter, nullptr, 0);
+    return cudaGetLastError();
+  }
+  if (tp != nullptr && tp->stage != nullptr && map.rep == kRepCode8 && map.lut_n < kStageSkip)
+  {
+    // phase 1: sweep the Morton-sorted cloud, park the codes; phase 2: ordered sum
+    update_kernel<kRepCode8, true><<<blocks, kThreads, 0, stream>>>(map, particles, n, tp->sorted, npts, npts_padded, beacons,
+                                                                    nullptr, trig_mode, nullptr, tp->stage, tp->pitch);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+      return e;
+    ordered_sum_kernel<<<(n + kSumThreads - 1) / kSumThreads, kSumThreads, 0, stream>>>(
+        map, particles, n, tp->stage, tp->pitch, tp->row_of, npts, beacons, wr_out, counter);
     return cudaGetLastError();
   }
   const size_t dyn = sizeof(float) * map.lut_n;
   static bool attr_set = false;
   if (!attr_set)
   {
-    cudaError_t e = cudaFuncSetAttribute(update_kernel<kRepCode16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(update_kernel<kRepCode16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(sizeof(float) * kMaxLutSmem));
     if (e != cudaSuccess)
       return e;
     attr_set = true;
   }
   if (map.rep == kRepCode8)
-    update_kernel<kRepCode8><<<blocks, kThreads, dyn, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
-                                                                wr_out, trig_mode, counter);
+    update_kernel<kRepCode8, false><<<blocks, kThreads, dyn, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
+                                                                       wr_out, trig_mode, counter, nullptr, 0);
   else
-    update_kernel<kRepCode16><<<blocks, kThreads, dyn, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
-                                                                 wr_out, trig_mode, counter);
+    update_kernel<kRepCode16, false><<<blocks, kThreads, dyn, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
+                                                                        wr_out, trig_mode, counter, nullptr, 0);
   return cudaGetLastError();
+}
+
+cudaError_t launch_sort_cloud(const float* src, uint32_t stride, uint32_t npts, uint32_t npts_padded, float4* sorted,
+                              uint32_t* row_of, void* scratch, size_t scratch_bytes, cudaStream_t stream)
+{
+  // scratch: keys_in, keys_out (8 B each), vals_in, vals_out (4 B each), then the CUB temporaries
+  if (npts_padded == 0)
+    return cudaSuccess;
+  char* base = reinterpret_cast<char*>(scratch);
+  const size_t n8 = ((size_t)npts * 8 + 255) & ~(size_t)255, n4 = ((size_t)npts * 4 + 255) & ~(size_t)255;
+  unsigned long long* k_in = reinterpret_cast<unsigned long long*>(base);
+  unsigned long long* k_out = reinterpret_cast<unsigned long long*>(base + n8);
+  uint32_t* v_in = reinterpret_cast<uint32_t*>(base + 2 * n8);
+  uint32_t* v_out = reinterpret_cast<uint32_t*>(base + 2 * n8 + n4);
+  void* tmp = base + 2 * n8 + 2 * n4;
+  size_t tmp_bytes = scratch_bytes - (2 * n8 + 2 * n4);
+  if (npts > 0)
+  {
+    morton_key_kernel<<<(npts + 255) / 256, 256, 0, stream>>>(src, stride, npts, k_in, v_in);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, v_out, (int)npts, 0, 36, stream);
+    if (e != cudaSuccess)
+      return e;
+  }
+  pack_sorted_kernel<<<(npts_padded + 255) / 256, 256, 0, stream>>>(src, stride, npts, v_out, sorted, row_of, npts_padded);
+  return cudaGetLastError();
+}
+
+size_t sort_cloud_scratch_bytes(uint32_t npts)
+{
+  const size_t n8 = ((size_t)npts * 8 + 255) & ~(size_t)255, n4 = ((size_t)npts * 4 + 255) & ~(size_t)255;
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)(npts ? npts : 1), 0, 36);
+  return 2 * n8 + 2 * n4 + tmp + 256;
 }
 
 cudaError_t launch_pack_cloud(const float* src, uint32_t stride, uint32_t npts, float4* dst, uint32_t npts_padded,

@@ -148,6 +148,11 @@ int amcl3d_b200_grid_device_ptr(amcl3d_b200_grid_t g, void** d_prob);
 int amcl3d_b200_pf_create(amcl3d_b200_grid_t g, amcl3d_b200_pf_t* out);
 int amcl3d_b200_pf_destroy(amcl3d_b200_pf_t pf);
 int amcl3d_b200_pf_set_trig_mode(amcl3d_b200_pf_t pf, int trig_mode);
+/* enable (default) / disable the two-phase update: phase 1 sweeps the cloud in Morton order (so that all
+ * particles work in the same neighbourhood of the map at the same time) and parks 1-byte codes, phase 2 adds
+ * them in the original cloud order -- bit-identical weights, ~1.4x faster on large grids.  Takes effect at
+ * the next set_cloud.  Environment AMCL3D_B200_TWO_PHASE=0 sets the default for new handles. */
+int amcl3d_b200_pf_set_two_phase(amcl3d_b200_pf_t pf, int enable);
 /* run this handle's kernels on a caller-owned cudaStream_t (NULL = the handle's own stream) */
 int amcl3d_b200_pf_set_stream(amcl3d_b200_pf_t pf, void* cuda_stream);
 

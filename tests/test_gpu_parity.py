@@ -435,3 +435,40 @@ def test_resample_one_million_bit_exact(O, world_c1, pf):
     pf.particleNormalize()
     idx = pf.resample(np.float32(0.618), want_idx=True)
     assert np.array_equal(idx, ref_idx)
+
+
+@pytest.mark.parametrize("kind", ["T", "G"])
+def test_two_phase_update_is_bit_identical(O, world_c1, kind):
+    """>= 4096 particles on a device-built (u8-coded) grid take the two-phase path (Morton sweep + ordered sum):
+    same bits as the single-kernel path and as the oracle, same in-bounds count."""
+    from amcl3d_test_b200 import Grid3d, ParticleFilter, synth
+
+    w = world_c1
+    g = Grid3d(0)
+    mn, mx = g.computePointCloud(w["synth"].points, 0.1)
+    g.computeGrid(w["synth"].points, 0.05, sub=2)
+    assert g.info()["rep"] == 1
+    m = O.Map(mn, mx, 0.1, 0.05, prob=g.downloadGrid())
+    P = synth.make_particles(w["synth"], 5000, kind)
+    cloud = w["cloud"][:1500].copy()
+    cloud[7] = np.nan  # a skipped point in the middle of the sweep
+    ref = O.update(m, O.particles(P), cloud)
+    pf = ParticleFilter(g)
+    pf.p_ = P
+    n2 = pf.update(cloud, count=True)
+    two = pf.p_
+    assert pf.launch_count() >= 6  # pack + sort (3) + phase 1 + phase 2
+    pf.set_two_phase(False)
+    pf.p_ = P
+    n1 = pf.update(cloud, count=True)
+    one = pf.p_
+    assert n1 == n2 == O.count_in_bounds(m, O.particles(P), cloud)
+    assert np.array_equal(bits(two[:, 6]), bits(ref[:, 6]))
+    assert np.array_equal(bits(one[:, 6]), bits(ref[:, 6]))
+    # ragged sizes: particle count not a multiple of 128, cloud not a multiple of 32, fewer than 10 hits
+    pf.set_two_phase(True)
+    for n, npts in ((4097, 65), (4500, 333)):
+        ref = O.update(m, O.particles(P[:n]), cloud[:npts])
+        pf.p_ = P[:n]
+        pf.update(cloud[:npts])
+        assert np.array_equal(bits(pf.p_[:, 6]), bits(ref[:, 6])), (n, npts)

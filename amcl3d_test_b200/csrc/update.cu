@@ -32,7 +32,10 @@ namespace a3d
 namespace
 {
 #ifndef AMCL3D_THREADS
-#define AMCL3D_THREADS 128
+#define AMCL3D_THREADS 256
+#endif
+#ifndef AMCL3D_STAGE_TILE
+#define AMCL3D_STAGE_TILE 128
 #endif
 #ifndef AMCL3D_TILE
 #define AMCL3D_TILE 512
@@ -41,10 +44,12 @@ namespace
 #define AMCL3D_UNROLL 4
 #endif
 constexpr int kThreads = AMCL3D_THREADS;  // particles per CTA
-constexpr int kTile = AMCL3D_TILE;        // points per shared-memory stage (16 B each)
+constexpr int kTile = AMCL3D_TILE;        // points per shared-memory stage (16 B each), single-kernel path
+constexpr int kStageTile = AMCL3D_STAGE_TILE;  // points per block of the staging sweep = its lock-step granularity
 constexpr int kStages = 2;
 constexpr int kUnroll = AMCL3D_UNROLL;    // independent gathers per batch (two batches in flight)
-static_assert(kTile % (2 * kUnroll) == 0 && 32 % kUnroll == 0, "tiles and the 32-point padding must hold whole batch pairs");
+static_assert(kTile % (2 * kUnroll) == 0 && kStageTile % (2 * kUnroll) == 0 && 32 % (2 * kUnroll) == 0,
+              "tiles and the 32-point padding must hold whole batch pairs");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
 {
@@ -382,7 +387,10 @@ __device__ __forceinline__ bool particle_gate(const MapDev& map, float px, float
 }
 
 #ifndef AMCL3D_MINBLOCKS
-#define AMCL3D_MINBLOCKS 6
+#define AMCL3D_MINBLOCKS 3
+#endif
+#ifndef AMCL3D_STAGE_TILES
+#define AMCL3D_STAGE_TILES 1  // cloud tiles per block of the staging sweep (lock-step granularity)
 #endif
 // kStage == false: the whole update in one kernel (sweep in cloud order, accumulate in registers).
 // kStage == true : phase 1 of the two-phase path (sweep the Morton-sorted cloud, park codes in `stage`).
@@ -391,14 +399,23 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
     update_kernel(const __grid_constant__ MapDev map, float* __restrict__ particles, uint32_t n,
                   const float4* __restrict__ cloud, uint32_t npts, uint32_t npad, const BeaconSet* __restrict__ beacons,
                   float* __restrict__ wr_out, int trig_mode, unsigned long long* __restrict__ counter,
-                  uint8_t* __restrict__ stage, size_t stage_pitch)
+                  uint8_t* __restrict__ stage, size_t stage_pitch, uint32_t tiles_per_block)
 {
-  __shared__ __align__(128) float4 tile[kStages][kTile];
+  constexpr int kT = kStage ? kStageTile : kTile;
+  __shared__ __align__(128) float4 tile[kStages][kT];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   extern __shared__ float lut_s[];  // kRep != kRepFloat: the code -> f32 dictionary
 
   const uint32_t tid = threadIdx.x;
-  const uint32_t i = blockIdx.x * kThreads + tid;
+  // Block order.  Single-kernel path: one block sweeps the whole cloud for its 128 particles.  Staging path:
+  // the grid is (chunk of tiles_per_block tiles) x (particle tile) in CHUNK-MAJOR order, so the hardware block
+  // scheduler keeps every resident block inside the same one or two chunks of the Morton-sorted cloud: all
+  // particles gather from the same neighbourhood of the map at the same time (no flags, nothing to chain --
+  // the codes are only parked).
+  const uint32_t n_ptiles = (n + kThreads - 1) / kThreads;
+  const uint32_t ptile = kStage ? blockIdx.x % n_ptiles : blockIdx.x;
+  const uint32_t chunk = kStage ? blockIdx.x / n_ptiles : 0u;
+  const uint32_t i = ptile * kThreads + tid;
   const bool live = i < n;
 
   float px = 0, py = 0, pz = 0, roll = 0, pitch = 0, yaw = 0;
@@ -432,7 +449,9 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
   // warp-uniform choice of the loop flavour; lanes that are not in the map do not vote it down
   const bool warp_f32 = __all_sync(0xffffffffu, f32_exact || !inmap);
 
-  const uint32_t ntiles = (npad + kTile - 1) / kTile;
+  const uint32_t ntiles_all = (npad + kT - 1) / kT;
+  const uint32_t tile0 = chunk * tiles_per_block;                       // first tile of this block
+  const uint32_t ntiles = min(tiles_per_block, ntiles_all - tile0);     // tiles this block sweeps
   if (tid == 0)
   {
 #pragma unroll
@@ -448,9 +467,9 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
   {
     for (uint32_t t = 0; t < ntiles && t < (uint32_t)kStages; ++t)
     {
-      const uint32_t count = min((uint32_t)kTile, npad - t * kTile);
+      const uint32_t count = min((uint32_t)kT, npad - (tile0 + t) * kT);
       mbar_expect_tx(&full_bar[t], count * 16u);
-      tma_bulk_g2s(&tile[t][0], cloud + (size_t)t * kTile, count * 16u, &full_bar[t]);
+      tma_bulk_g2s(&tile[t][0], cloud + (size_t)(tile0 + t) * kT, count * 16u, &full_bar[t]);
     }
   }
 
@@ -461,31 +480,32 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
     const uint32_t s = t % kStages;
     const uint32_t parity = (t / kStages) & 1u;
     mbar_wait(&full_bar[s], parity);
-    const uint32_t count = min((uint32_t)kTile, npad - t * kTile);
+    const uint32_t row0 = (tile0 + t) * kT;
+    const uint32_t count = min((uint32_t)kT, npad - row0);
     if (inmap)
     {
       if constexpr (kStage)
       {
         if (warp_f32)
-          tile_loop<true, kRep>(map, &tile[s][0], count, t * kTile, r, off_f, off_d, park);
+          tile_loop<true, kRep>(map, &tile[s][0], count, row0, r, off_f, off_d, park);
         else
-          tile_loop<false, kRep>(map, &tile[s][0], count, t * kTile, r, off_f, off_d, park);
+          tile_loop<false, kRep>(map, &tile[s][0], count, row0, r, off_f, off_d, park);
       }
       else
       {
         if (warp_f32)
-          tile_loop<true, kRep>(map, &tile[s][0], count, t * kTile, r, off_f, off_d, acc);
+          tile_loop<true, kRep>(map, &tile[s][0], count, row0, r, off_f, off_d, acc);
         else
-          tile_loop<false, kRep>(map, &tile[s][0], count, t * kTile, r, off_f, off_d, acc);
+          tile_loop<false, kRep>(map, &tile[s][0], count, row0, r, off_f, off_d, acc);
       }
     }
     __syncthreads();  // every lane is done with stage s before TMA overwrites it
     if (tid == 0 && t + kStages < ntiles)
     {
-      const uint32_t tn = t + kStages;
-      const uint32_t cn = min((uint32_t)kTile, npad - tn * kTile);
+      const uint32_t tn = tile0 + t + kStages;
+      const uint32_t cn = min((uint32_t)kT, npad - tn * kT);
       mbar_expect_tx(&full_bar[s], cn * 16u);
-      tma_bulk_g2s(&tile[s][0], cloud + (size_t)tn * kTile, cn * 16u, &full_bar[s]);
+      tma_bulk_g2s(&tile[s][0], cloud + (size_t)tn * kT, cn * 16u, &full_bar[s]);
     }
   }
 
@@ -724,14 +744,18 @@ cudaError_t launch_update(const MapDev& map, float* particles, uint32_t n, const
   if (map.rep == kRepFloat || map.codes == nullptr || map.lut_n > kMaxLutSmem)
   {
     update_kernel<kRepFloat, false><<<blocks, kThreads, 0, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
-                                                                     wr_out, trig_mode, counter, nullptr, 0);
+                                                                     wr_out, trig_mode, counter, nullptr, 0, 0xFFFFFFFFu);
     return cudaGetLastError();
   }
   if (tp != nullptr && tp->stage != nullptr && map.rep == kRepCode8 && map.lut_n < kStageSkip)
   {
     // phase 1: sweep the Morton-sorted cloud, park the codes; phase 2: ordered sum
-    update_kernel<kRepCode8, true><<<blocks, kThreads, 0, stream>>>(map, particles, n, tp->sorted, npts, npts_padded, beacons,
-                                                                    nullptr, trig_mode, nullptr, tp->stage, tp->pitch);
+    const uint32_t ntiles = (npts_padded + kStageTile - 1) / kStageTile;
+    const uint32_t tpb = AMCL3D_STAGE_TILES;
+    const uint32_t chunks = (ntiles + tpb - 1) / tpb;
+    update_kernel<kRepCode8, true><<<blocks * chunks, kThreads, 0, stream>>>(map, particles, n, tp->sorted, npts, npts_padded,
+                                                                             beacons, nullptr, trig_mode, nullptr, tp->stage,
+                                                                             tp->pitch, tpb);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
       return e;
@@ -751,10 +775,10 @@ cudaError_t launch_update(const MapDev& map, float* particles, uint32_t n, const
   }
   if (map.rep == kRepCode8)
     update_kernel<kRepCode8, false><<<blocks, kThreads, dyn, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
-                                                                       wr_out, trig_mode, counter, nullptr, 0);
+                                                                       wr_out, trig_mode, counter, nullptr, 0, 0xFFFFFFFFu);
   else
     update_kernel<kRepCode16, false><<<blocks, kThreads, dyn, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
-                                                                        wr_out, trig_mode, counter, nullptr, 0);
+                                                                        wr_out, trig_mode, counter, nullptr, 0, 0xFFFFFFFFu);
   return cudaGetLastError();
 }
 

@@ -156,6 +156,7 @@ void refresh_map(amcl3d_b200_grid_t g)
       eps = 0.5f;
     m.eps[a] = eps;
   }
+  m.band = 0.5f - fmaxf(fmaxf(m.eps[0], m.eps[1]), m.eps[2]);
   m.step_z = (uint64_t)m.size[0] * (uint64_t)m.size[1];
   m.n_cells = (uint64_t)m.size[0] * (uint64_t)m.size[1] * (uint64_t)m.size[2];
   m.prob = g->d_prob;

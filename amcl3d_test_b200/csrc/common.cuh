@@ -20,6 +20,7 @@ struct MapDev
   float size_up[3];   // smallest f32 >= (max - min): for f32 x,  x < (double)size  <=>  x < size_up
   float eps[3];       // half-width of the "too close to a voxel face for the f32 quotient" band
   float rinv_f;       // (float)(1.0 / resol)
+  float band;         // 0.5 - max(eps): |frac(v*rinv_f) - 0.5| < band  <=>  the f32 voxel index is exact on that axis
   uint32_t size[3];
   uint64_t step_z;    // size_x * size_y in 64 bits (equals the reference's u32 value below 2^32 cells)
   uint64_t n_cells;

@@ -122,24 +122,19 @@ __device__ __forceinline__ void rotation(float roll, float pitch, float yaw, int
   }
 }
 
-// floor(fl64(v / resol)) for 0 <= v < size_up, three exact tiers (see header comment)
-__device__ __forceinline__ uint32_t voxel_of(float v, float rinv_f, float eps, double rinv, double resol)
+// Voxel index floor(fl64(v / resol)) for 0 <= v < size_up (see header comment).  Fast tier: k = floor(v*rinv_f) in
+// f32, valid whenever the f32 quotient is farther than eps from an integer (eps bounds its error).  The caller
+// tests the three axes with ONE predicate; voxel_exact() is the rare out-of-line tier: f64 product with a 1e-9
+// band, then the real f64 division.
+__device__ __noinline__ uint32_t voxel_exact(float v, double rinv, double resol)
 {
-  const float q = __fmul_rn(v, rinv_f);
-  const float kf = floorf(q);
-  const float fr = __fsub_rn(q, kf);
-  uint32_t k = (uint32_t)kf;
-  if (fr < eps || fr > __fsub_rn(1.0f, eps))
-  {
-    const double vd = (double)v;
-    const double qd = __dmul_rn(vd, rinv);
-    double kd = floor(qd);
-    const double frd = qd - kd;
-    if (frd < 1e-9 || frd > 1.0 - 1e-9)
-      kd = floor(__ddiv_rn(vd, resol));
-    k = (uint32_t)kd;
-  }
-  return k;
+  const double vd = (double)v;
+  const double qd = __dmul_rn(vd, rinv);
+  double kd = floor(qd);
+  const double frd = qd - kd;
+  if (frd < 1e-9 || frd > 1.0 - 1e-9)
+    kd = floor(__ddiv_rn(vd, resol));
+  return (uint32_t)kd;
 }
 
 template <bool kF32Offset>
@@ -208,7 +203,9 @@ struct Raw<kRepFloat>
   typedef float type;  // the cell itself
 };
 
-// returns the bit mask of evaluations that pass every bounds test; addr[u] = element index of their voxel
+// returns the bit mask of evaluations that pass every bounds test; addr[u] = element index of their voxel.
+// Branch-free on the fast path: everything is computed for every point and masked; the only branch is the rare
+// "some axis is within eps of a voxel face" fix-up.
 template <bool kF32Offset, int kRep>
 __device__ __forceinline__ uint32_t batch_addresses(const MapDev& map, const float4* __restrict__ pts, const float r[9],
                                                     const float off_f[3], const double off_d[3], uint64_t addr[kUnroll])
@@ -217,6 +214,8 @@ __device__ __forceinline__ uint32_t batch_addresses(const MapDev& map, const flo
 #pragma unroll
   for (int u = 0; u < kUnroll; ++u)
     pt[u] = pts[u];  // broadcast LDS.128, issued back to back
+  const float rinv_f = map.rinv_f;
+  const float band = map.band;  // 0.5 - max eps
   uint32_t mask = 0;
 #pragma unroll
   for (int u = 0; u < kUnroll; ++u)
@@ -231,18 +230,21 @@ __device__ __forceinline__ uint32_t batch_addresses(const MapDev& map, const flo
     // Grid3d.cpp:279-280 (NaN fails every comparison, like the reference)
     bool in = (nx >= 0.f) & (nx < map.size_up[0]) & (ny >= 0.f) & (ny < map.size_up[1]) & (nz >= 0.f) &
               (nz < map.size_up[2]);
-    uint64_t a = 0;
-    if (in)
+    // Grid3d.cpp:282-284, fast tier on all three axes at once
+    const float qx = __fmul_rn(nx, rinv_f), qy = __fmul_rn(ny, rinv_f), qz = __fmul_rn(nz, rinv_f);
+    const float kx = floorf(qx), ky = floorf(qy), kz = floorf(qz);
+    const float dev = fmaxf(fmaxf(fabsf(__fsub_rn(__fsub_rn(qx, kx), 0.5f)), fabsf(__fsub_rn(__fsub_rn(qy, ky), 0.5f))),
+                            fabsf(__fsub_rn(__fsub_rn(qz, kz), 0.5f)));
+    uint32_t ix = (uint32_t)kx, iy = (uint32_t)ky, iz = (uint32_t)kz;
+    if (in && !(dev < band))  // rare: within eps of a voxel face on some axis -> exact tiers
     {
-      // Grid3d.cpp:282-288
-      const uint32_t ix = voxel_of(nx, map.rinv_f, map.eps[0], map.rinv, map.resol);
-      const uint32_t iy = voxel_of(ny, map.rinv_f, map.eps[1], map.rinv, map.resol);
-      const uint32_t iz = voxel_of(nz, map.rinv_f, map.eps[2], map.rinv, map.resol);
-      in = (ix < map.size[0]) & (iy < map.size[1]) & (iz < map.size[2]);  // Grid3d.cpp:286 (and :290)
-      a = voxel_address<kRep>(map, ix, iy, iz);
+      ix = voxel_exact(nx, map.rinv, map.resol);
+      iy = voxel_exact(ny, map.rinv, map.resol);
+      iz = voxel_exact(nz, map.rinv, map.resol);
     }
+    in = in & (ix < map.size[0]) & (iy < map.size[1]) & (iz < map.size[2]);  // Grid3d.cpp:286 (and :290)
+    addr[u] = voxel_address<kRep>(map, ix, iy, iz);
     mask |= in ? (1u << u) : 0u;
-    addr[u] = a;
   }
   return mask;
 }

@@ -916,8 +916,8 @@ int amcl3d_b200_pf_update(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beaco
   const TwoPhase* tpp = nullptr;
   if (pf->two_phase && pf->n >= 4096 && pf->npts >= 64 && pf->d_sorted != nullptr && map.rep == kRepCode8 && map.lut_n < 255)
   {
-    const uint64_t pitch = (pf->n + 127) & ~127ull;
-    const uint64_t bytes = pitch * pf->npad;
+    const uint64_t pitch = stage_tile_width();  // bytes per staged row of one particle tile (= particles per block)
+    const uint64_t bytes = ((pf->n + pitch - 1) / pitch) * pitch * pf->npad;
     if (bytes <= (16ull << 30))
     {
       CU(ensure(pf->d_codes_staged, pf->codes_staged_cap, bytes));

@@ -105,7 +105,8 @@ struct BeaconSet
 // wr_out (nullable) receives the raw range-beacon weight per particle; counter (nullable) the number
 // of evaluations that loaded a voxel.
 // Two-phase sweep state (nullptr / stage == nullptr: single-kernel path): the Morton-sorted cloud, the row of
-// every original point in that order, and the staging matrix stage[row * pitch + particle] of 1-byte codes.
+// every original point in that order, and the staging buffer stage[(tile * npad + row) * pitch + lane] of 1-byte codes
+// (pitch = stage_tile_width() particles per tile).
 struct TwoPhase
 {
   const float4* sorted;
@@ -120,6 +121,7 @@ cudaError_t launch_update(const MapDev& map, float* particles, uint32_t n, const
 cudaError_t launch_sort_cloud(const float* src, uint32_t stride, uint32_t npts, uint32_t npts_padded, float4* sorted,
                               uint32_t* row_of, void* scratch, size_t scratch_bytes, cudaStream_t stream);
 size_t sort_cloud_scratch_bytes(uint32_t npts);
+uint32_t stage_tile_width();  // particles per block of the staging layout [particle tile][row][lane]
 // packs a strided cloud (device memory) into cloud4 and pads with NaN points up to npts_padded
 cudaError_t launch_pack_cloud(const float* src, uint32_t stride, uint32_t npts, float4* dst, uint32_t npts_padded,
                               cudaStream_t stream);

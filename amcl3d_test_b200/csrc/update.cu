@@ -208,12 +208,16 @@ struct Raw<kRepFloat>
 // "some axis is within eps of a voxel face" fix-up.
 template <bool kF32Offset, int kRep>
 __device__ __forceinline__ uint32_t batch_addresses(const MapDev& map, const float4* __restrict__ pts, const float r[9],
-                                                    const float off_f[3], const double off_d[3], uint64_t addr[kUnroll])
+                                                    const float off_f[3], const double off_d[3], uint64_t addr[kUnroll],
+                                                    uint32_t orow[kUnroll])
 {
   float4 pt[kUnroll];
 #pragma unroll
   for (int u = 0; u < kUnroll; ++u)
+  {
     pt[u] = pts[u];  // broadcast LDS.128, issued back to back
+    orow[u] = __float_as_uint(pt[u].w);  // staging sweep: index of this point in the caller's cloud order
+  }
   const float rinv_f = map.rinv_f;
   const float band = map.band;  // 0.5 - max eps
   uint32_t mask = 0;
@@ -294,15 +298,16 @@ __device__ __forceinline__ void batch_consume(const typename Raw<kRep>::type raw
 //    cloud is swept in its own order.
 //  * StageSink: two-phase path.  The cloud is swept in a spatially coherent (Morton) order so that all
 //    particles work in the same neighbourhood of the map at the same time (L2 / TLB locality), and the
-//    1-byte codes are parked in a staging matrix stage[row][particle]; ordered_sum_kernel then adds them
-//    in the ORIGINAL cloud order, so the rounding sequence -- and every bit of the weight -- is unchanged.
+//    1-byte codes are parked at the point's ORIGINAL row of a staging buffer stage[tile][row][lane];
+//    ordered_sum_kernel then streams the rows front to back, i.e. adds in the original cloud order, so the
+//    rounding sequence -- and every bit of the weight -- is unchanged.
 template <int kRep>
 struct AccumSink
 {
   const float* __restrict__ lut_s;
   float weight;
   int cnt;
-  __device__ __forceinline__ void put(const typename Raw<kRep>::type raw[kUnroll], uint32_t mask, uint32_t /*row*/)
+  __device__ __forceinline__ void put(const typename Raw<kRep>::type raw[kUnroll], uint32_t mask, const uint32_t* /*orow*/)
   {
     batch_consume<kRep>(raw, mask, lut_s, weight, cnt);
   }
@@ -310,39 +315,40 @@ struct AccumSink
 constexpr uint32_t kStageSkip = 0xFFu;  // staged code of an evaluation that loaded nothing
 struct StageSink
 {
-  uint8_t* __restrict__ column;  // &stage[0][particle]
-  size_t pitch;                  // bytes from one row (cloud point) to the next
-  __device__ __forceinline__ void put(const uint32_t raw[kUnroll], uint32_t mask, uint32_t row)
+  uint8_t* __restrict__ column;  // &stage[tile][0][lane]
+  size_t pitch;                  // bytes from one row (cloud point, ORIGINAL order) to the next
+  __device__ __forceinline__ void put(const uint32_t raw[kUnroll], uint32_t mask, const uint32_t orow[kUnroll])
   {
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u)
-      column[(size_t)(row + u) * pitch] = (uint8_t)(((mask >> u) & 1u) ? raw[u] : kStageSkip);
+      column[(size_t)orow[u] * pitch] = (uint8_t)(((mask >> u) & 1u) ? raw[u] : kStageSkip);
   }
 };
 
 // one tile of `count` points (a multiple of 2*kUnroll) for one particle; row0 = index of tile[0] in the sweep
 template <bool kF32Offset, int kRep, typename Sink>
-__device__ __forceinline__ void tile_loop(const MapDev& map, const float4* __restrict__ tile, uint32_t count, uint32_t row0,
+__device__ __forceinline__ void tile_loop(const MapDev& map, const float4* __restrict__ tile, uint32_t count, uint32_t /*row0*/,
                                           const float r[9], const float off_f[3], const double off_d[3], Sink& sink)
 {
   typedef typename Raw<kRep>::type raw_t;
   uint64_t addr[kUnroll];
   raw_t raw_a[kUnroll], raw_b[kUnroll];
+  uint32_t row_a[kUnroll], row_b[kUnroll];
   uint32_t mask_a, mask_b;
-  mask_a = batch_addresses<kF32Offset, kRep>(map, tile, r, off_f, off_d, addr);
+  mask_a = batch_addresses<kF32Offset, kRep>(map, tile, r, off_f, off_d, addr, row_a);
   batch_issue<kRep>(map, addr, mask_a, raw_a);
 #pragma unroll 1
   for (uint32_t base = kUnroll; base < count; base += 2 * kUnroll)
   {
-    mask_b = batch_addresses<kF32Offset, kRep>(map, tile + base, r, off_f, off_d, addr);
+    mask_b = batch_addresses<kF32Offset, kRep>(map, tile + base, r, off_f, off_d, addr, row_b);
     batch_issue<kRep>(map, addr, mask_b, raw_b);
-    sink.put(raw_a, mask_a, row0 + base - kUnroll);
+    sink.put(raw_a, mask_a, row_a);
     if (base + kUnroll < count)
     {
-      mask_a = batch_addresses<kF32Offset, kRep>(map, tile + base + kUnroll, r, off_f, off_d, addr);
+      mask_a = batch_addresses<kF32Offset, kRep>(map, tile + base + kUnroll, r, off_f, off_d, addr, row_a);
       batch_issue<kRep>(map, addr, mask_a, raw_a);
     }
-    sink.put(raw_b, mask_b, row0 + base);
+    sink.put(raw_b, mask_b, row_b);
   }
 }
 
@@ -476,7 +482,9 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
   }
 
   AccumSink<kRep> acc{ lut_s, 0.f, 0 };
-  StageSink park{ stage + i, stage_pitch };
+  // staging layout: [particle tile][row][lane] -- each particle tile owns one contiguous npad x kThreads block,
+  // so phase 2 (rows visited in original-cloud order, i.e. at random) stays inside a couple of 2 MB pages
+  StageSink park{ stage + (size_t)ptile * stage_pitch * npad + tid, stage_pitch };
   for (uint32_t t = 0; t < ntiles; ++t)
   {
     const uint32_t s = t % kStages;
@@ -526,23 +534,46 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
   }
 }
 
-// Phase 2 of the two-phase path: thread = particle; adds lut[code] in the ORIGINAL cloud order.  row_of[j] is the
-// position of original point j in the Morton sweep.  Reads are coalesced (consecutive particles are consecutive
-// bytes of a row); each staged byte is read exactly once.
-constexpr int kSumThreads = 128;
-constexpr int kSumUnroll = 8;
+// Phase 2 of the two-phase path: thread = particle, block = one particle tile of the staging layout.  The rows of
+// the tile are in the caller's cloud order, so the block simply STREAMS its contiguous npad x kThreads bytes front
+// to back (TMA bulk copies into a two-stage shared-memory ring) and every thread adds lut[code] of its column in
+// order -- the reference's rounding sequence (Grid3d.cpp:292).  Each staged byte is read exactly once.
+constexpr int kSumThreads = kThreads;
+constexpr int kSumRows = 64;  // rows per ring stage: 64 x 256 B = 16 KB
 __global__ void __launch_bounds__(kSumThreads)
     ordered_sum_kernel(const __grid_constant__ MapDev map, float* __restrict__ particles, uint32_t n,
-                       const uint8_t* __restrict__ stage, size_t stage_pitch, const uint32_t* __restrict__ row_of, uint32_t npts,
+                       const uint8_t* __restrict__ stage, uint32_t npts, uint32_t npad,
                        const BeaconSet* __restrict__ beacons, float* __restrict__ wr_out,
                        unsigned long long* __restrict__ counter)
 {
+  __shared__ __align__(128) uint8_t ring[2][kSumRows * kSumThreads];
+  __shared__ __align__(8) uint64_t full_bar[2];
   __shared__ float lut_s[256];
   const uint32_t tid = threadIdx.x;
   const uint32_t i = blockIdx.x * kSumThreads + tid;
   for (uint32_t k = tid; k < 256; k += kSumThreads)
     lut_s[k] = k < map.lut_n ? map.lut[k] : 0.f;
+  if (tid == 0)
+  {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+  const uint8_t* __restrict__ src = stage + (size_t)blockIdx.x * kSumThreads * npad;
+  const uint32_t nchunks = (npts + kSumRows - 1) / kSumRows;
+  auto issue = [&](uint32_t c) {
+    const uint32_t rows = min((uint32_t)kSumRows, npad - c * kSumRows);  // npad is a multiple of 32: bytes % 16 == 0
+    mbar_expect_tx(&full_bar[c & 1], rows * kSumThreads);
+    tma_bulk_g2s(&ring[c & 1][0], src + (size_t)c * kSumRows * kSumThreads, rows * kSumThreads, &full_bar[c & 1]);
+  };
+  if (tid == 0)
+  {
+    if (nchunks > 0)
+      issue(0);
+    if (nchunks > 1)
+      issue(1);
+  }
   const bool live = i < n;
   float px = 0, py = 0, pz = 0;
   if (live)
@@ -555,47 +586,39 @@ __global__ void __launch_bounds__(kSumThreads)
   const bool inmap = live && particle_gate(map, px, py, pz);
   float weight = 0.f;
   int cnt = 0;
-  if (inmap)
+  for (uint32_t c = 0; c < nchunks; ++c)
   {
-    const uint8_t* __restrict__ column = stage + i;
-    uint32_t j = 0;
-    for (; j + kSumUnroll <= npts; j += kSumUnroll)
+    mbar_wait(&full_bar[c & 1], (c >> 1) & 1u);
+    const uint32_t rows = min((uint32_t)kSumRows, npts - c * kSumRows);
+    if (inmap)
     {
-      uint32_t code[kSumUnroll];
-#pragma unroll
-      for (int u = 0; u < kSumUnroll; ++u)
-        code[u] = column[(size_t)__ldg(row_of + j + u) * stage_pitch];
-#pragma unroll
-      for (int u = 0; u < kSumUnroll; ++u)
+      const uint8_t* col = &ring[c & 1][tid];
+#pragma unroll 8
+      for (uint32_t rr = 0; rr < rows; ++rr)
       {
-        const float v = lut_s[code[u]];
-        if (code[u] != kStageSkip)
+        const uint32_t code = col[rr * kSumThreads];
+        const float v = lut_s[code];
+        if (code != kStageSkip)
         {
           weight = __fadd_rn(weight, v);  // Grid3d.cpp:292, cloud order
           ++cnt;
         }
       }
     }
-    for (; j < npts; ++j)
-    {
-      const uint32_t code = column[(size_t)__ldg(row_of + j) * stage_pitch];
-      if (code != kStageSkip)
-      {
-        weight = __fadd_rn(weight, lut_s[code]);
-        ++cnt;
-      }
-    }
+    __syncthreads();
+    if (tid == 0 && c + 2 < nchunks)
+      issue(c + 2);
   }
   if (live)
     finish_particle(particles, i, inmap, weight, cnt, npts, px, py, pz, beacons, wr_out);
   if (counter != nullptr)
   {
-    unsigned int c = (unsigned int)cnt;
+    unsigned int cc = (unsigned int)cnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
-      c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((tid & 31u) == 0 && c)
-      atomicAdd(counter, (unsigned long long)c);
+      cc += __shfl_xor_sync(0xffffffffu, cc, o);
+    if ((tid & 31u) == 0 && cc)
+      atomicAdd(counter, (unsigned long long)cc);
   }
 }
 
@@ -645,7 +668,7 @@ __global__ void pack_sorted_kernel(const float* __restrict__ src, uint32_t strid
   else
   {
     const float nanv = CUDART_NAN_F;
-    sorted[r] = make_float4(nanv, nanv, nanv, 0.f);
+    sorted[r] = make_float4(nanv, nanv, nanv, __uint_as_float(r));  // parks its skip code in a padding row (>= npts)
   }
 }
 
@@ -762,7 +785,7 @@ cudaError_t launch_update(const MapDev& map, float* particles, uint32_t n, const
     if (e != cudaSuccess)
       return e;
     ordered_sum_kernel<<<(n + kSumThreads - 1) / kSumThreads, kSumThreads, 0, stream>>>(
-        map, particles, n, tp->stage, tp->pitch, tp->row_of, npts, beacons, wr_out, counter);
+        map, particles, n, tp->stage, npts, npts_padded, beacons, wr_out, counter);
     return cudaGetLastError();
   }
   const size_t dyn = sizeof(float) * map.lut_n;
@@ -807,6 +830,11 @@ cudaError_t launch_sort_cloud(const float* src, uint32_t stride, uint32_t npts, 
   }
   pack_sorted_kernel<<<(npts_padded + 255) / 256, 256, 0, stream>>>(src, stride, npts, v_out, sorted, row_of, npts_padded);
   return cudaGetLastError();
+}
+
+uint32_t stage_tile_width()
+{
+  return (uint32_t)kThreads;
 }
 
 size_t sort_cloud_scratch_bytes(uint32_t npts)

@@ -102,11 +102,9 @@ struct amcl3d_b200_pf_s
   uint32_t npts = 0, npad = 0;
   float* d_stage = nullptr;
   uint64_t stage_cap = 0;
-  // two-phase sweep: Morton-sorted cloud, row of every original point, sort scratch, staged codes
+  // two-phase sweep: Morton-sorted cloud, sort scratch, staged codes
   float4* d_sorted = nullptr;
   uint64_t sorted_cap = 0;
-  uint32_t* d_row_of = nullptr;
-  uint64_t row_of_cap = 0;
   char* d_sort_scratch = nullptr;
   uint64_t sort_scratch_cap = 0;
   uint8_t* d_codes_staged = nullptr;
@@ -713,7 +711,6 @@ int amcl3d_b200_pf_destroy(amcl3d_b200_pf_t pf)
   cudaFree(pf->d_cloud);
   cudaFree(pf->d_stage);
   cudaFree(pf->d_sorted);
-  cudaFree(pf->d_row_of);
   cudaFree(pf->d_sort_scratch);
   cudaFree(pf->d_codes_staged);
   cudaFree(pf->d_prefix);
@@ -841,10 +838,9 @@ static int set_cloud_common(amcl3d_b200_pf_t pf, const float* d_src, uint32_t st
   {
     // Morton order of this cloud for the two-phase sweep (keys + radix sort + pack: a few microseconds)
     CU(ensure(pf->d_sorted, pf->sorted_cap, npad));
-    CU(ensure(pf->d_row_of, pf->row_of_cap, npts));
     const size_t need = sort_cloud_scratch_bytes(npts);
     CU(ensure(pf->d_sort_scratch, pf->sort_scratch_cap, need));
-    CU(launch_sort_cloud(d_src, stride, npts, npad, pf->d_sorted, pf->d_row_of, pf->d_sort_scratch, need, pf->stream));
+    CU(launch_sort_cloud(d_src, stride, npts, npad, pf->d_sorted, pf->d_sort_scratch, need, pf->stream));
     pf->launches += 3;
   }
   pf->npts = npts;
@@ -922,7 +918,6 @@ int amcl3d_b200_pf_update(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beaco
     {
       CU(ensure(pf->d_codes_staged, pf->codes_staged_cap, bytes));
       tp.sorted = pf->d_sorted;
-      tp.row_of = pf->d_row_of;
       tp.stage = pf->d_codes_staged;
       tp.pitch = pitch;
       tpp = &tp;

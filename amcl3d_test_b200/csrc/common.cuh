@@ -104,22 +104,21 @@ struct BeaconSet
 // particles: AoS 7 floats; cloud4: (x,y,z,0) per point padded with NaN points to a multiple of 32.
 // wr_out (nullable) receives the raw range-beacon weight per particle; counter (nullable) the number
 // of evaluations that loaded a voxel.
-// Two-phase sweep state (nullptr / stage == nullptr: single-kernel path): the Morton-sorted cloud, the row of
-// every original point in that order, and the staging buffer stage[(tile * npad + row) * pitch + lane] of 1-byte codes
-// (pitch = stage_tile_width() particles per tile).
+// Two-phase sweep state (nullptr / stage == nullptr: single-kernel path): the Morton-sorted cloud (w = index of
+// the point in the caller's order) and the staging buffer stage[(tile * npad + row) * pitch + lane] of 1-byte
+// codes, rows in the caller's order, pitch = stage_tile_width() particles per tile.
 struct TwoPhase
 {
   const float4* sorted;
-  const uint32_t* row_of;
   uint8_t* stage;
   size_t pitch;
 };
 cudaError_t launch_update(const MapDev& map, float* particles, uint32_t n, const float4* cloud4, uint32_t npts,
                           uint32_t npts_padded, const BeaconSet* beacons, float* wr_out, int trig_mode,
                           unsigned long long* counter, const TwoPhase* tp, cudaStream_t stream);
-// Morton order of a strided device cloud: sorted (npts_padded float4, NaN padded) + row_of (npts)
+// Morton order of a strided device cloud: sorted (npts_padded float4, NaN padded)
 cudaError_t launch_sort_cloud(const float* src, uint32_t stride, uint32_t npts, uint32_t npts_padded, float4* sorted,
-                              uint32_t* row_of, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+                              void* scratch, size_t scratch_bytes, cudaStream_t stream);
 size_t sort_cloud_scratch_bytes(uint32_t npts);
 uint32_t stage_tile_width();  // particles per block of the staging layout [particle tile][row][lane]
 // packs a strided cloud (device memory) into cloud4 and pads with NaN points up to npts_padded

@@ -651,9 +651,9 @@ __global__ void morton_key_kernel(const float* __restrict__ src, uint32_t stride
   keys[j] = key;
   vals[j] = j;
 }
-// sorted[r] = point order[r] (w = its original index as bits), row_of[order[r]] = r; NaN padding rows
+// sorted[r] = point order[r], w = its index in the caller's order (as bits); NaN padding rows point at rows >= npts
 __global__ void pack_sorted_kernel(const float* __restrict__ src, uint32_t stride, uint32_t npts, const uint32_t* __restrict__ order,
-                                   float4* __restrict__ sorted, uint32_t* __restrict__ row_of, uint32_t npad)
+                                   float4* __restrict__ sorted, uint32_t npad)
 {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= npad)
@@ -663,7 +663,6 @@ __global__ void pack_sorted_kernel(const float* __restrict__ src, uint32_t strid
     const uint32_t o = order[r];
     const float* p = src + (size_t)o * stride;
     sorted[r] = make_float4(p[0], p[1], p[2], __uint_as_float(o));
-    row_of[o] = r;
   }
   else
   {
@@ -808,7 +807,7 @@ cudaError_t launch_update(const MapDev& map, float* particles, uint32_t n, const
 }
 
 cudaError_t launch_sort_cloud(const float* src, uint32_t stride, uint32_t npts, uint32_t npts_padded, float4* sorted,
-                              uint32_t* row_of, void* scratch, size_t scratch_bytes, cudaStream_t stream)
+                              void* scratch, size_t scratch_bytes, cudaStream_t stream)
 {
   // scratch: keys_in, keys_out (8 B each), vals_in, vals_out (4 B each), then the CUB temporaries
   if (npts_padded == 0)
@@ -828,7 +827,7 @@ cudaError_t launch_sort_cloud(const float* src, uint32_t stride, uint32_t npts, 
     if (e != cudaSuccess)
       return e;
   }
-  pack_sorted_kernel<<<(npts_padded + 255) / 256, 256, 0, stream>>>(src, stride, npts, v_out, sorted, row_of, npts_padded);
+  pack_sorted_kernel<<<(npts_padded + 255) / 256, 256, 0, stream>>>(src, stride, npts, v_out, sorted, npts_padded);
   return cudaGetLastError();
 }
 

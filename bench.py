@@ -44,7 +44,7 @@ WORKLOADS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
@@ -62,6 +62,19 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(workload, kind, n_local, n_pts):
+    """dram__bytes_read+write of the two launches of one update, from the committed ncu --set full capture of this
+    very workload (profiles/r1_traffic.json); None for any other workload."""
+    p = ROOT / "profiles" / "r1_traffic.json"
+    try:
+        d = json.loads(p.read_text())
+        if d.get("workload") == f"{workload} {kind} {n_local}x{n_pts}":
+            return float(d["per_update_total_dram_bytes"])
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -107,7 +120,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.01)
 
     def stop(self):
         self._halt.set()
@@ -393,6 +406,23 @@ def run_b200(args):
     h2d = int(pin_p.numel() * 4 + pin_c.numel() * 4)
     d2h = int(pin_out.numel() * 4 + 28)
 
+    # ---- secondary: the other particle distribution of SURVEY 8(d) on the same grid (update only, not the headline) ----
+    other = None
+    if world == 1:
+        kind2 = "G" if args.particles == "T" else "T"
+        P2 = synth.make_particles(sm, n_local, kind2)
+        pf.p_ = P2
+        pf.set_cloud(cloud)
+        n_in2 = pf.update(count=True)
+        t2 = []
+        for _ in range(5):
+            pf.update()
+            t2.append(pf.last_kernel_ms())
+        u2 = float(np.median(t2))
+        other = {"particles_kind": kind2, "update_ms": u2, "update_evals_per_sec": n_local * n_pts / (u2 * 1e-3),
+                 "in_bounds_fraction": n_in2 / (n_local * n_pts),
+                 "roofline_frac": n_in2 * 32.0 / (u2 * 1e-3) / 1e9 / measured_peaks()[0]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -417,8 +447,8 @@ def run_b200(args):
         "update_ms": upd, "resample_mean_ms": ms_step - upd,
         "update_evals_per_sec": n_local * n_pts / (upd * 1e-3) * world,
         "roofline": {
-            "bound": "hbm", "kernel": "update_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src,
+            "bound": "hbm", "kernel": "update = update_kernel<code8,stage> (phase 1 gather) + ordered_sum_kernel (phase 2)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": ncu_traffic(args.workload, args.particles, n_local, n_pts), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": n_in * 32,
             "note": "32 B sector per in-bounds particle x point evaluation (SURVEY 8(d)); duration = CUDA events around the kernel on its launch stream",
         },
@@ -428,6 +458,8 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "setup_s": time.time() - t_setup,
     }
+    if other is not None:
+        line["secondary"] = other
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(args.workload, args.particles, args.cpu_seconds)

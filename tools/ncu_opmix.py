@@ -12,7 +12,10 @@ for r in rows[2:]:
     toks = src.split()
     op = toks[1] if toks and toks[0].startswith("@") else (toks[0] if toks else "?")
     op = op.split(".")[0]
-    n = int(r[ci["Instructions Executed"]] or 0)
+    try:
+        n = int(r[ci["Instructions Executed"]] or 0)
+    except ValueError:
+        break
     mix[op] += n; tot += n
 print("total warp instructions", tot)
 for op, n in mix.most_common(40):

@@ -198,7 +198,15 @@ class ParticleFilter:
         return p.value or 0, int(n.value)
 
     def set_stream(self, cuda_stream: int | None):
-        check(self._L.amcl3d_b200_pf_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """Run this handle's kernels on a caller-owned stream.  None = the handle's own stream; 0 (torch's default
+        stream is the legacy NULL stream) is passed as cudaStreamLegacy so that work really is ordered with it."""
+        if cuda_stream is None:
+            handle = 0
+        elif cuda_stream == 0:
+            handle = 1  # cudaStreamLegacy
+        else:
+            handle = cuda_stream
+        check(self._L.amcl3d_b200_pf_set_stream(self._h, C.c_void_p(handle)))
 
     def set_two_phase(self, enable: bool):
         """A/B switch of the Morton-sweep + ordered-sum update (bit-identical results either way)."""
@@ -233,6 +241,24 @@ class ParticleFilter:
         c = C.c_uint64(0)
         check(self._L.amcl3d_b200_pf_update(self._h, arr, nb, float(alpha), float(sigma), C.byref(c) if count else None))
         return int(c.value) if count else None
+
+    @staticmethod
+    def _beacon_array(beacons):
+        pos, rng = beacons
+        arr = (capi.Beacon * len(rng))()
+        for k in range(len(rng)):
+            for a in range(3):
+                arr[k].position[a] = float(pos[k][a])
+            arr[k].range = float(rng[k])
+        return arr, len(rng)
+
+    def update_split(self, beacons, sigma, d_wr_out: int):
+        """update() with the range fusion left to the caller: raw cloud weight in p_, raw range weight in d_wr_out."""
+        arr, nb = self._beacon_array(beacons)
+        check(self._L.amcl3d_b200_pf_update_split(self._h, arr, nb, float(sigma), C.c_void_p(d_wr_out), None))
+
+    def fuse_range(self, d_wr: int, alpha):
+        check(self._L.amcl3d_b200_pf_fuse_range(self._h, C.c_void_p(d_wr), float(alpha)))
 
     def particleNormalize(self) -> np.float32:
         wtp = C.c_float(0)

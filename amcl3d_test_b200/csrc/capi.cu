@@ -874,8 +874,21 @@ int amcl3d_b200_pf_set_cloud_device(amcl3d_b200_pf_t pf, const void* d_cloud, ui
   return set_cloud_common(pf, reinterpret_cast<const float*>(d_cloud), stride, npts);
 }
 
-int amcl3d_b200_pf_update(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beacons, uint32_t nb, float alpha, float sigma,
-                          uint64_t* in_bounds)
+static int fuse_range_async(amcl3d_b200_pf_t pf, const float* d_wr, float alpha)
+{
+  // w = alpha*wp/sum(wp) + (1-alpha)*wr/sum(wr): both sums as sequential f32 chains
+  CU(ensure(pf->d_dense, pf->dense_cap, pf->n));
+  CU(launch_chain_prefix(pf->d_p, pf->n, 0, nullptr, pf->d_scalars + 0, pf->d_dense, pf->stream));
+  CU(launch_chain_sum_array(d_wr, pf->n, pf->d_scalars + 1, pf->stream));
+  CU(launch_fuse_range(pf->d_p, d_wr, pf->n, pf->d_scalars + 0, pf->d_scalars + 1, alpha, pf->stream));
+  pf->launches += 4;
+  return AMCL3D_B200_OK;
+}
+
+// d_wr_ext != nullptr: raw range weights go there and the fusion is left to the caller (multi-GPU: the sums
+// of the fusion are global, so it runs after the all-gather)
+static int update_impl(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beacons, uint32_t nb, float alpha, float sigma,
+                       uint64_t* in_bounds, float* d_wr_ext)
 {
   if (!pf || (nb && !beacons) || nb > (uint32_t)kMaxBeacons)
     return fail(AMCL3D_B200_ERR_ARG, "bad beacons");
@@ -898,8 +911,13 @@ int amcl3d_b200_pf_update(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beaco
     }
     CU(cudaMemcpyAsync(pf->d_beacons, &bs, sizeof(bs), cudaMemcpyHostToDevice, pf->stream));
     CU(cudaStreamSynchronize(pf->stream));  // bs lives on this stack frame
-    CU(ensure(pf->d_wr, pf->wr_cap, pf->n));
-    d_wr = pf->d_wr;
+    if (d_wr_ext != nullptr)
+      d_wr = d_wr_ext;
+    else
+    {
+      CU(ensure(pf->d_wr, pf->wr_cap, pf->n));
+      d_wr = pf->d_wr;
+    }
   }
   unsigned long long* d_counter = nullptr;
   if (in_bounds)
@@ -928,15 +946,9 @@ int amcl3d_b200_pf_update(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beaco
     CU(launch_update(map, pf->d_p, (uint32_t)pf->n, pf->d_cloud, pf->npts, pf->npad, pf->d_beacons, d_wr, pf->trig_mode,
                      d_counter, tpp, pf->stream));
     pf->launches += pf->n ? (tpp ? 2 : 1) : 0;
-    if (nb && pf->n)
-    {
-      // w = alpha*wp/sum(wp) + (1-alpha)*wr/sum(wr): both sums as sequential f32 chains
-      CU(ensure(pf->d_dense, pf->dense_cap, pf->n));
-      CU(launch_chain_prefix(pf->d_p, pf->n, 0, nullptr, pf->d_scalars + 0, pf->d_dense, pf->stream));
-      CU(launch_chain_sum_array(pf->d_wr, pf->n, pf->d_scalars + 1, pf->stream));
-      CU(launch_fuse_range(pf->d_p, pf->d_wr, pf->n, pf->d_scalars + 0, pf->d_scalars + 1, alpha, pf->stream));
-      pf->launches += 3;
-    }
+    if (nb && pf->n && d_wr_ext == nullptr)
+      if (int rc = fuse_range_async(pf, pf->d_wr, alpha))
+        return rc;
   }
   if (in_bounds)
   {
@@ -947,6 +959,36 @@ int amcl3d_b200_pf_update(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beaco
   }
   else
     CU(cudaStreamSynchronize(pf->stream));
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_update(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beacons, uint32_t nb, float alpha, float sigma,
+                          uint64_t* in_bounds)
+{
+  return update_impl(pf, beacons, nb, alpha, sigma, in_bounds, nullptr);
+}
+
+int amcl3d_b200_pf_update_split(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beacons, uint32_t nb, float sigma,
+                                void* d_wr_out, uint64_t* in_bounds)
+{
+  if (nb && !d_wr_out)
+    return fail(AMCL3D_B200_ERR_ARG, "d_wr_out is NULL");
+  return update_impl(pf, beacons, nb, 1.f, sigma, in_bounds, reinterpret_cast<float*>(d_wr_out));
+}
+
+int amcl3d_b200_pf_fuse_range(amcl3d_b200_pf_t pf, const void* d_wr, float alpha)
+{
+  if (!pf || !d_wr)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  if (pf->n)
+  {
+    Timed t(pf);
+    if (int rc = fuse_range_async(pf, reinterpret_cast<const float*>(d_wr), alpha))
+      return rc;
+  }
+  CU(cudaStreamSynchronize(pf->stream));
   return AMCL3D_B200_OK;
 }
 

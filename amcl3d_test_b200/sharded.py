@@ -71,6 +71,15 @@ class ShardedFilter:
     def resample(self, u01: float):
         """update() must have run.  Global ParticleFilter::particleNormalize + resample, bit-exact."""
         self.gather()
+        if getattr(self.shard, "wr_local", None) is not None:
+            # range-beacon fusion needs the GLOBAL sums of both weights: gather the raw range weights too, fuse on
+            # the full set (every rank, redundantly), then normalise as usual
+            if self.world == 1:
+                self.shard.wr_full.copy_(self.shard.wr_local)
+            else:
+                assert self.n_total % self.world == 0, "beacon fusion across ranks needs equal blocks"
+                dist.all_gather_into_tensor(self.shard.wr_full, self.shard.wr_local, group=self.group)
+            self.shard.fuse_full()
         wtp = self.shard.normalize_full()
         self.shard.resample_full(u01, self.lo, self.hi)
         return wtp
@@ -108,8 +117,23 @@ class CudaShard:
     def set_cloud(self, cloud):
         self.pf_local.set_cloud(cloud)
 
+    wr_local = None
+
+    def set_beacons(self, beacons, alpha, sigma):
+        """Range-only beacon weighting (row R): (positions (nb,3), ranges (nb,)), alpha, sigma.  The range weight is
+        evaluated in the update kernel; the fusion runs on the gathered set (global sums)."""
+        self.beacons, self.alpha, self.sigma = beacons, alpha, sigma
+        self.wr_local = torch.zeros(self.local.shape[0], dtype=torch.float32, device=self.device)
+        self.wr_full = torch.zeros(self.full.shape[0], dtype=torch.float32, device=self.device)
+
     def update(self):
-        self.pf_local.update()
+        if self.wr_local is not None:
+            self.pf_local.update_split(self.beacons, self.sigma, self.wr_local.data_ptr())
+        else:
+            self.pf_local.update()
+
+    def fuse_full(self):
+        self.pf_full.fuse_range(self.wr_full.data_ptr(), self.alpha)
 
     def normalize_full(self):
         return self.pf_full.particleNormalize()

@@ -38,7 +38,12 @@ WORKLOADS = {
     "C3-small": ((50.0, 50.0, 10.0), 0.05, 100_000, 10_000, 22.0),
     "C4": ((100.0, 100.0, 20.0), 0.05, 1_000_000, 20_000, 30.0),  # particles are the TOTAL here (strong)
     "C1": ((20.0, 20.0, 5.0), 0.1, 600, 2_000, 12.0),
+    # config 5 with the grid size BASELINE.json quotes (~2.6 GB replica = 4000 x 4000 x 40 voxels, i.e. 4 m tall):
+    # cloud + 8 UWB range beacons fused, 1 M particles in total (strong).  The literal 400 x 400 x 40 m box is 25.6 GB.
+    "C5s": ((400.0, 400.0, 4.0), 0.1, 1_000_000, 20_000, 30.0),
 }
+STRONG = {"C4", "C5s"}
+BEACONS = {"C5s"}
 
 
 def parse():
@@ -301,7 +306,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=device)
 
     extent, resol, n_per_gpu, n_pts, radius = WORKLOADS[args.workload]
-    strong = args.workload == "C4"
+    strong = args.workload in STRONG
     n_total = n_per_gpu if strong else n_per_gpu * world
     lo = (n_total // world) * rank
     n_local = n_total // world
@@ -326,6 +331,8 @@ def run_b200(args):
     filt = ShardedFilter(shard, n_total)
     backup = torch.from_numpy(P).to(device)
     shard.set_cloud(cloud)
+    if args.workload in BEACONS:
+        shard.set_beacons(synth.make_beacons(sm, 8), 0.5, 0.53)  # sigma = sensor_range, alpha (amcl3d.launch:83, amcl3d_floam.launch:30)
     stream = torch.cuda.current_stream(device)
 
     def step():
@@ -379,7 +386,10 @@ def run_b200(args):
 
     def e2e_step():
         pf.p_ = pin_p.numpy()               # H2D particles
-        pf.update(pin_c.numpy())            # H2D cloud + K3
+        if args.workload in BEACONS:
+            pf.update(pin_c.numpy(), beacons=shard.beacons, alpha=0.5, sigma=0.53)
+        else:
+            pf.update(pin_c.numpy())        # H2D cloud + K3
         pf.particleNormalize()
         pf.resample(u01)
         got = pf.p_                         # D2H resampled set

@@ -153,7 +153,8 @@ int amcl3d_b200_pf_set_trig_mode(amcl3d_b200_pf_t pf, int trig_mode);
  * them in the original cloud order -- bit-identical weights, ~1.4x faster on large grids.  Takes effect at
  * the next set_cloud.  Environment AMCL3D_B200_TWO_PHASE=0 sets the default for new handles. */
 int amcl3d_b200_pf_set_two_phase(amcl3d_b200_pf_t pf, int enable);
-/* run this handle's kernels on a caller-owned cudaStream_t (NULL = the handle's own stream) */
+/* run this handle's kernels on a caller-owned cudaStream_t (NULL = the handle's own non-blocking stream; pass
+ * cudaStreamLegacy / cudaStreamPerThread explicitly to order with the default stream) */
 int amcl3d_b200_pf_set_stream(amcl3d_b200_pf_t pf, void* cuda_stream);
 
 /* p_ mirror: host <-> device copies of the particle set */
@@ -177,6 +178,13 @@ int amcl3d_b200_pf_set_cloud_device(amcl3d_b200_pf_t pf, const void* d_cloud, ui
  * particle x point evaluations that loaded a voxel. */
 int amcl3d_b200_pf_update(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beacons, uint32_t nb, float alpha,
                           float sigma, uint64_t* in_bounds);
+/* The same update with the fusion left to the caller: p_[i].w receives the raw cloud weight and d_wr_out (DEVICE,
+ * n floats) the raw range weight.  Multi-GPU callers all-gather both, then call amcl3d_b200_pf_fuse_range on the
+ * gathered set so that the two sums of the fusion are global. */
+int amcl3d_b200_pf_update_split(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beacons, uint32_t nb, float sigma,
+                                void* d_wr_out, uint64_t* in_bounds);
+/* w = alpha*w/sum(w) + (1-alpha)*wr/sum(wr) over the handle's particle set, d_wr = DEVICE array of n range weights */
+int amcl3d_b200_pf_fuse_range(amcl3d_b200_pf_t pf, const void* d_wr, float alpha);
 /* convenience: set_cloud + update */
 int amcl3d_b200_pf_update_cloud(amcl3d_b200_pf_t pf, const float* cloud, uint32_t stride, uint32_t npts);
 

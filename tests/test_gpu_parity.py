@@ -472,3 +472,24 @@ def test_two_phase_update_is_bit_identical(O, world_c1, kind):
         pf.p_ = P[:n]
         pf.update(cloud[:npts])
         assert np.array_equal(bits(pf.p_[:, 6]), bits(ref[:, 6])), (n, npts)
+
+
+def test_range_split_then_fuse_equals_fused_update(world_c1, pf):
+    """update_split + fuse_range (what the multi-GPU path runs after the all-gather) == the fused single call."""
+    import torch
+
+    from amcl3d_test_b200 import synth
+
+    w = world_c1
+    beacons = synth.make_beacons(w["synth"], 8)
+    pf.p_ = w["T"]
+    pf.update(w["cloud"], beacons=beacons, alpha=0.5, sigma=0.53)
+    fused = pf.p_
+    wr = torch.zeros(w["T"].shape[0], dtype=torch.float32, device="cuda")
+    pf.p_ = w["T"]
+    pf.set_cloud(w["cloud"])
+    pf.update_split(beacons, 0.53, wr.data_ptr())
+    raw = pf.p_
+    assert (wr > 0).sum().item() > 500 and not np.array_equal(raw[:, 6], fused[:, 6])
+    pf.fuse_range(wr.data_ptr(), 0.5)
+    assert np.array_equal(bits(pf.p_), bits(fused))

@@ -49,6 +49,21 @@ def main():
         out_local.view(np.uint32), ref_out[lo:hi].view(np.uint32))
     ref_mean = pf.getMean()
     ok = ok and np.allclose(mean[:6], ref_mean[:6], rtol=1e-5, atol=1e-6)
+    # same with the range-beacon weight fused in (global sums of the fusion across ranks)
+    beacons = synth.make_beacons(sm, 8)
+    shard.set_beacons(beacons, 0.5, 0.53)
+    shard.local.copy_(torch.from_numpy(P[lo:hi]).to(dev))
+    f.update()
+    f.resample(0.37)
+    out_b = shard.local.cpu().numpy().copy()
+    pf.p_ = P
+    pf.update(cloud, beacons=beacons, alpha=0.5, sigma=0.53)
+    pf.particleNormalize()
+    pf.resample(0.37)
+    ok_b = np.array_equal(out_b.view(np.uint32), pf.p_[lo:hi].view(np.uint32))
+    if not ok_b:
+        print(f"rank {rank}: beacon-fused resample differs from 1 GPU")
+    ok = ok and ok_b
     t = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

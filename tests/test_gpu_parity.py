@@ -493,3 +493,50 @@ def test_range_split_then_fuse_equals_fused_update(world_c1, pf):
     assert (wr > 0).sum().item() > 500 and not np.array_equal(raw[:, 6], fused[:, 6])
     pf.fuse_range(wr.data_ptr(), 0.5)
     assert np.array_equal(bits(pf.p_), bits(fused))
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16])
+def test_random_worlds_full_pipeline(O, seed):
+    """Random map extent / resolution / origin shift / cloud / pose spread: update (single-kernel and two-phase),
+    normalise, resample, uniformSample and mean on the GPU against the oracle, all bit-identical."""
+    from amcl3d_test_b200 import Grid3d, ParticleFilter, synth
+
+    rng = np.random.RandomState(seed)
+    extent = tuple(np.round(rng.uniform(4.0, 12.0, 3), 1))
+    resol = [0.05, 0.1, 0.2, 0.3][seed % 4]
+    sm = synth.make_map(extent, resol, seed=seed)
+    shift = rng.uniform(-50, 50, 3) if seed % 2 else np.zeros(3)
+    pts = (sm.points.astype(np.float64) + shift).astype(np.float32)
+    g = Grid3d(0)
+    mn, mx = g.computePointCloud(pts, resol)
+    omn, omx = O.compute_bounds(pts)
+    assert np.array_equal(mn, omn) and np.array_equal(mx, omx)
+    sensor_dev = [0.05, 0.1][seed % 2]
+    g.computeGrid(pts, sensor_dev, mode=[O.GRID_QUIRK, O.GRID_GAUSSIAN, O.GRID_SPLAT][seed % 3], sub=2)
+    m = O.Map(mn, mx, resol, sensor_dev, prob=g.downloadGrid())
+    assert g.info()["size"] == m.size
+    n = int(rng.choice([700, 4096, 6000]))
+    n_pts = int(rng.randint(30, 2500))
+    cloud = rng.normal(0, max(extent) / 4, (n_pts, 3)).astype(np.float32)
+    P = np.zeros((n, 7), np.float32)
+    P[:, :3] = (mn - 0.5 + rng.uniform(0, 1, (n, 3)) * (mx - mn + 1.0)).astype(np.float32)
+    P[:, 3:5] = rng.normal(0, 0.3, (n, 2))
+    P[:, 5] = rng.uniform(-np.pi, np.pi, n)
+    pf = ParticleFilter(g)
+    pf.p_ = P
+    n_in = pf.update(cloud, count=True)
+    W = O.update(m, O.particles(P), cloud)
+    assert np.array_equal(bits(pf.p_), bits(W))
+    assert n_in == O.count_in_bounds(m, O.particles(P), cloud)
+    assert bits(pf.particleNormalize()) == bits(O.normalize(m, W))
+    assert np.array_equal(bits(pf.p_), bits(W))
+    u01 = np.float32(rng.uniform())
+    out, idx_ref = O.resample(W, u01)
+    idx = pf.resample(u01, want_idx=True)
+    assert np.array_equal(idx, idx_ref) and np.array_equal(bits(pf.p_), bits(out))
+    assert np.array_equal(bits(pf.getMean(exact=True)), bits(O.mean(out)))
+    pf.p_ = W
+    S = int(rng.randint(1, 2 * n))
+    out, idx_ref, k = O.uniform_sample(m, W.copy(), S)
+    idx, emitted = pf.uniformSample(S, want_idx=True)
+    assert emitted == k and np.array_equal(idx, idx_ref) and np.array_equal(bits(pf.p_), bits(out))

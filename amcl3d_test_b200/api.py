@@ -299,6 +299,24 @@ class ParticleFilter:
         nz = _f32(noise6)
         check(self._L.amcl3d_b200_pf_predict(self._h, d.ctypes.data_as(C.POINTER(C.c_double)), nz.ctypes.data))
 
+    # ---- MonteCarloLocalization steps around the path (amcl3d.cpp) ------------------------------------------
+    def computeSampleNum(self, cnt_per_grid=3, min_resamp=150, max_resamp=800) -> int:
+        out = C.c_int(0)
+        check(self._L.amcl3d_b200_pf_compute_sample_num(self._h, cnt_per_grid, min_resamp, max_resamp, C.byref(out)))
+        return out.value
+
+    def updateSampleHeight(self, keyposes) -> np.float32:
+        kp = _f32(keyposes)
+        dh = C.c_float(0)
+        check(self._L.amcl3d_b200_pf_update_sample_height(self._h, kp.ctypes.data, kp.shape[0], C.byref(dh)))
+        return np.float32(dh.value)
+
+    def PFResample(self, weight_multiply, min_resamp, max_resamp, keyposes) -> int:
+        kp = _f32(keyposes)
+        out = C.c_int(0)
+        check(self._L.amcl3d_b200_pf_resample_step(self._h, int(weight_multiply), min_resamp, max_resamp, kp.ctypes.data, kp.shape[0], C.byref(out)))
+        return out.value
+
     def prefix(self) -> np.ndarray:
         n = self.size()
         out = np.empty(n, np.float32)

@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libamcl3d_b200.so"
-SOURCES = ["update.cu", "pfops.cu", "gridbuild.cu", "capi.cu"]
+SOURCES = ["update.cu", "pfops.cu", "gridbuild.cu", "mcl.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
@@ -76,7 +76,7 @@ def build_host(verbose: bool = False, force: bool = False) -> Path:
     build_native()
     root = PKG.parent
     cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
-    srcs = [PKG / "host" / n for n in ("Grid3d.cpp", "ParticleFilter.cpp", "map_io.cpp")]
+    srcs = [PKG / "host" / n for n in ("Grid3d.cpp", "ParticleFilter.cpp", "amcl3d.cpp", "map_io.cpp")]
     hdrs = list((root / "include").rglob("*.h")) + [PKG / "host" / "map_io.h"]
     common = [cxx, "-std=c++14", "-O2", "-fPIC", "-Wall", f"-I{root / 'include'}", f"-I{PKG / 'host'}"]
     if force or _stale(HOST_LIB, [*srcs, *hdrs, LIB]):

@@ -29,6 +29,7 @@ SYMBOLS = [
     "amcl3d_b200_pf_normalize", "amcl3d_b200_pf_scale_by_max", "amcl3d_b200_pf_resample",
     "amcl3d_b200_pf_uniform_sample", "amcl3d_b200_pf_mean", "amcl3d_b200_pf_best", "amcl3d_b200_pf_predict",
     "amcl3d_b200_pf_prefix", "amcl3d_b200_pf_last_kernel_ms", "amcl3d_b200_pf_launch_count",
+    "amcl3d_b200_pf_compute_sample_num", "amcl3d_b200_pf_update_sample_height", "amcl3d_b200_pf_resample_step",
     "amcl3d_b200_bench_gather",
 ]
 
@@ -116,6 +117,9 @@ def load():
         "amcl3d_b200_pf_best": (i, [vp, vp]),
         "amcl3d_b200_pf_predict": (i, [vp, f64p, vp]),
         "amcl3d_b200_pf_prefix": (i, [vp, P(vp), vp, u64]),
+        "amcl3d_b200_pf_compute_sample_num": (i, [vp, i, i, i, P(i)]),
+        "amcl3d_b200_pf_update_sample_height": (i, [vp, vp, u64, P(f32)]),
+        "amcl3d_b200_pf_resample_step": (i, [vp, i, i, i, vp, u64, P(i)]),
         "amcl3d_b200_pf_last_kernel_ms": (i, [vp, P(f32)]),
         "amcl3d_b200_pf_launch_count": (i, [vp, P(u64)]),
         "amcl3d_b200_bench_gather": (i, [vp, u64, u32, u32, i, P(f32), P(u64)]),

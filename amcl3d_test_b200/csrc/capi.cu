@@ -1241,6 +1241,139 @@ int amcl3d_b200_pf_prefix(amcl3d_b200_pf_t pf, void** d_prefix, float* host_out,
   return AMCL3D_B200_OK;
 }
 
+/* ---- callers of the path: MonteCarloLocalization (amcl3d/src/amcl3d.cpp) ------------------------------------ */
+
+// amcl3d.cpp:242-288
+int amcl3d_b200_pf_compute_sample_num(amcl3d_b200_pf_t pf, int cnt_per_grid, int min_resamp, int max_resamp, int* sample_num)
+{
+  if (!pf || !sample_num)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  // computeBoundary (amcl3d.cpp:222-241): all zeros for an empty set, else min / max over the set
+  float lo[3] = { 0.f, 0.f, 0.f }, hi[3] = { 0.f, 0.f, 0.f };
+  uint32_t* d_keys = reinterpret_cast<uint32_t*>(pf->d_u64 + 2);  // 6 x u32 inside the u64 scratch
+  if (pf->n)
+  {
+    Timed t(pf);
+    CU(launch_particle_bounds(pf->d_p, pf->n, d_keys, pf->stream));
+    pf->launches += 1;
+  }
+  if (pf->n)
+  {
+    uint32_t keys[6];
+    CU(cudaMemcpyAsync(keys, d_keys, sizeof(keys), cudaMemcpyDeviceToHost, pf->stream));
+    CU(cudaStreamSynchronize(pf->stream));
+    for (int a = 0; a < 6; ++a)
+    {
+      const uint32_t k = keys[a];
+      const uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+      float f;
+      memcpy(&f, &b, 4);
+      (a < 3 ? lo[a] : hi[a - 3]) = f;
+    }
+  }
+  float xyz_step = 0.2;
+  float theta_step = 8.0;
+  int xwidth = std::ceil((hi[0] - lo[0]) / xyz_step) + 1;
+  int ywidth = std::ceil((hi[1] - lo[1]) / xyz_step) + 1;
+  int zwidth = std::ceil((hi[2] - lo[2]) / xyz_step) + 1;
+  int theta = std::ceil((M_PI * 2 / theta_step * 180)) + 1;
+  if (xwidth * ywidth * zwidth == 0)
+  {
+    *sample_num = min_resamp;
+    return AMCL3D_B200_OK;
+  }
+  else if (xwidth * ywidth * zwidth > 1e3)
+  {
+    *sample_num = max_resamp;
+    return AMCL3D_B200_OK;
+  }
+  const size_t cells = (size_t)xwidth * ywidth * zwidth * theta;
+  const size_t words = (cells + 31) / 32;
+  uint32_t* d_bits = nullptr;
+  CU(cudaMalloc(&d_bits, words * sizeof(uint32_t)));
+  int cnt = 0;
+  cudaError_t e = launch_sample_bins(pf->d_p, pf->n, lo[0], lo[1], lo[2], xwidth, ywidth, zwidth, theta, d_bits, words, pf->d_int + 1,
+                                     pf->stream);
+  pf->launches += 1;
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(&cnt, pf->d_int + 1, sizeof(int), cudaMemcpyDeviceToHost, pf->stream);
+  if (e == cudaSuccess)
+    e = cudaStreamSynchronize(pf->stream);
+  cudaFree(d_bits);
+  if (e != cudaSuccess)
+    return fail_cuda(e, "computeSampleNum");
+  int s = cnt * cnt_per_grid;
+  if (s < min_resamp)
+    s = min_resamp;
+  if (s > max_resamp)
+    s = max_resamp;
+  *sample_num = s;
+  return AMCL3D_B200_OK;
+}
+
+// amcl3d.cpp:295-321: mean (sequential f32, like getMean), nearest keypose to (mean.x, mean.y, 0), z += its z - mean.z
+int amcl3d_b200_pf_update_sample_height(amcl3d_b200_pf_t pf, const float* keyposes_xyz, uint64_t nkey, float* delta_h)
+{
+  if (!pf || !keyposes_xyz || nkey == 0)
+    return fail(AMCL3D_B200_ERR_ARG, "no keyposes");
+  float mean7[7];
+  int rc = amcl3d_b200_pf_mean(pf, /*exact=*/1, mean7);
+  if (rc)
+    return rc;
+  // the kd-tree query of the reference is an exact 1-NN (FLANN L2_Simple<float>, f32 accumulation in x,y,z order)
+  const float q[3] = { mean7[0], mean7[1], 0.f };
+  float best = INFINITY;
+  uint64_t bi = 0;
+  for (uint64_t k = 0; k < nkey; ++k)
+  {
+    float result = 0.f, diff;
+    diff = q[0] - keyposes_xyz[3 * k];
+    result += diff * diff;
+    diff = q[1] - keyposes_xyz[3 * k + 1];
+    result += diff * diff;
+    diff = q[2] - keyposes_xyz[3 * k + 2];
+    result += diff * diff;
+    if (result < best)
+    {
+      best = result;
+      bi = k;
+    }
+  }
+  const float dh = keyposes_xyz[3 * bi + 2] - mean7[2];
+  {
+    Timed t(pf);
+    CU(launch_shift_z(pf->d_p, pf->n, dh, pf->stream));
+    pf->launches += pf->n ? 1 : 0;
+  }
+  CU(cudaStreamSynchronize(pf->stream));
+  if (delta_h)
+    *delta_h = dh;
+  return AMCL3D_B200_OK;
+}
+
+// amcl3d.cpp:192-203 (computeSampleNum is called with its default cnt_per_grid = 3, amcl3d.h)
+int amcl3d_b200_pf_resample_step(amcl3d_b200_pf_t pf, int weight_multiply, int min_resamp, int max_resamp,
+                                 const float* keyposes_xyz, uint64_t nkey, int* new_size)
+{
+  if (!pf)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+  int rc = AMCL3D_B200_OK;
+  if (weight_multiply)
+    rc = amcl3d_b200_pf_scale_by_max(pf);
+  int sample_num = 0;
+  if (!rc)
+    rc = amcl3d_b200_pf_compute_sample_num(pf, 3, min_resamp, max_resamp, &sample_num);
+  if (!rc)
+    rc = amcl3d_b200_pf_uniform_sample(pf, sample_num, 0, 0, nullptr, nullptr, nullptr);
+  if (!rc && keyposes_xyz && nkey)
+    rc = amcl3d_b200_pf_update_sample_height(pf, keyposes_xyz, nkey, nullptr);
+  if (!rc && new_size)
+    *new_size = sample_num;
+  return rc;
+}
+
 int amcl3d_b200_pf_last_kernel_ms(amcl3d_b200_pf_t pf, float* ms)
 {
   if (!pf || !ms)

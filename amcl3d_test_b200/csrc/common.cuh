@@ -159,6 +159,14 @@ size_t reduce_scratch_bytes();
 cudaError_t launch_predict(float* particles, uint64_t n, const double* delta6_dev, const float* noise6,
                            cudaStream_t stream);
 
+// ---- callers of the path (mcl.cu) ----------------------------------------------------------------
+// ordered-uint keys of min (0..2) and max (3..5) of x,y,z over the particle set
+cudaError_t launch_particle_bounds(const float* particles, uint64_t n, uint32_t* keys6, cudaStream_t stream);
+// occupied (x,y,z,yaw) bins of computeSampleNum -> count[0]
+cudaError_t launch_sample_bins(const float* particles, uint64_t n, float xmin, float ymin, float zmin, int xwidth, int ywidth,
+                               int zwidth, int theta, uint32_t* bits, size_t bits_words, int* count, cudaStream_t stream);
+cudaError_t launch_shift_z(float* particles, uint64_t n, float delta_h, cudaStream_t stream);
+
 // ---- grid build (gridbuild.cu) ------------------------------------------------------------------
 cudaError_t launch_bounds(const float* xyz, uint32_t stride, uint64_t n, float* out6 /*min3,max3*/,
                           cudaStream_t stream);

@@ -217,6 +217,19 @@ int amcl3d_b200_pf_best(amcl3d_b200_pf_t pf, float out7[7]);
  * particle in draw order x,y,z,roll,pitch,yaw (what ranGaussian returned), HOST memory */
 int amcl3d_b200_pf_predict(amcl3d_b200_pf_t pf, const double delta[6], const float* noise6);
 
+/* ---- the direct callers of the path: MonteCarloLocalization (amcl3d/src/amcl3d.cpp) ---------- */
+/* computeSampleNum (amcl3d.cpp:242-288, computeBoundary :222-241): occupied 0.2 m x yaw bins of the particle
+ * set times cnt_per_grid, clamped to [min_resamp, max_resamp] */
+int amcl3d_b200_pf_compute_sample_num(amcl3d_b200_pf_t pf, int cnt_per_grid, int min_resamp, int max_resamp,
+                                      int* sample_num);
+/* updateSampleHeight + getMapHeight (amcl3d.cpp:295-321): z += z(keypose nearest to (mean.x, mean.y, 0)) - mean.z;
+ * keyposes_xyz = nkey x 3 HOST floats (Grid3d::keyposes_3d); delta_h optional */
+int amcl3d_b200_pf_update_sample_height(amcl3d_b200_pf_t pf, const float* keyposes_xyz, uint64_t nkey, float* delta_h);
+/* PFResample (amcl3d.cpp:192-203): [addParticleWeight] -> computeSampleNum(3) -> uniformSample -> updateSampleHeight
+ * (skipped when no keyposes are given), particles never leave the device; new_size optional */
+int amcl3d_b200_pf_resample_step(amcl3d_b200_pf_t pf, int weight_multiply, int min_resamp, int max_resamp,
+                                 const float* keyposes_xyz, uint64_t nkey, int* new_size);
+
 /* sequential f32 inclusive prefix of the current weights (ParticleFilter.cpp:259-264), for tests and
  * for multi-GPU callers: DEVICE pointer valid until the next call on the handle */
 int amcl3d_b200_pf_prefix(amcl3d_b200_pf_t pf, void** d_prefix, float* host_out, uint64_t cap);

@@ -344,6 +344,111 @@ int orc_uniform_sample(const orc_map* m, orc_particle* p, uint64_t n, int S, orc
   return k;
 }
 
+/* amcl3d/src/amcl3d.cpp:222-241 */
+static void compute_boundary(const orc_particle* p, uint64_t n, float* xmin, float* ymin, float* zmin, float* xmax, float* ymax,
+                             float* zmax)
+{
+  *xmin = *xmax = *ymin = *ymax = *zmin = *zmax = 0.0;
+  if (n == 0)
+    return;
+  *xmin = *xmax = p[0].x;
+  *ymin = *ymax = p[0].y;
+  *zmin = *zmax = p[0].z;
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    const orc_particle _p = p[i];
+    *xmax = *xmax > _p.x ? *xmax : _p.x;
+    *xmin = *xmin > _p.x ? _p.x : *xmin;
+    *ymax = *ymax > _p.y ? *ymax : _p.y;
+    *ymin = *ymin > _p.y ? _p.y : *ymin;
+    *zmax = *zmax > _p.z ? *zmax : _p.z;
+    *zmin = *zmin > _p.z ? _p.z : *zmin;
+  }
+}
+
+/* amcl3d/src/amcl3d.cpp:242-288 */
+int orc_compute_sample_num(const orc_particle* p, uint64_t n, int cnt_per_grid, int min_resamp, int max_resamp)
+{
+  float xyz_step = 0.2;
+  float theta_step = 8.0;
+  float xmin, xmax, ymin, ymax, zmin, zmax;
+  compute_boundary(p, n, &xmin, &ymin, &zmin, &xmax, &ymax, &zmax);
+  int xwidth = ceilf((xmax - xmin) / xyz_step) + 1; /* std::ceil(float) -> float, +1, truncated to int */
+  int ywidth = ceilf((ymax - ymin) / xyz_step) + 1;
+  int zwidth = ceilf((zmax - zmin) / xyz_step) + 1;
+  int theta = ceil((M_PI * 2 / theta_step * 180)) + 1;
+  if (xwidth * ywidth * zwidth == 0)
+    return min_resamp;
+  else if (xwidth * ywidth * zwidth > 1e3)
+    return max_resamp;
+  const size_t cells = (size_t)xwidth * ywidth * zwidth * theta;
+  unsigned char* grid = (unsigned char*)calloc(cells, 1);
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    const orc_particle _p = p[i];
+    int x = (_p.x - xmin) / xyz_step;
+    int y = (_p.y - ymin) / xyz_step;
+    int z = (_p.z - zmin) / xyz_step;
+    int t = (_p.yaw - (-M_PI)) / theta_step;
+    if (x >= 0 && x < xwidth && y >= 0 && y < ywidth && z >= 0 && z < zwidth && t >= 0 && y < theta)
+    {
+      if (t < theta) /* the reference writes out of bounds here (UB); not counted */
+        grid[(((size_t)x * ywidth + y) * zwidth + z) * theta + t] = 1;
+    }
+  }
+  int cnt = 0;
+  for (size_t c = 0; c < cells; ++c)
+    cnt += grid[c] ? 1 : 0;
+  free(grid);
+  int sample_num = cnt * cnt_per_grid;
+  if (sample_num < min_resamp)
+    return min_resamp;
+  if (sample_num > max_resamp)
+    return max_resamp;
+  return sample_num;
+}
+
+/* amcl3d/src/amcl3d.cpp:295-321; the kd-tree query is an exact 1-NN with FLANN L2_Simple<float> distances */
+float orc_update_sample_height(orc_particle* p, uint64_t n, const float* keyposes, uint64_t nk)
+{
+  orc_particle pt;
+  orc_mean(p, n, &pt);
+  const float q[3] = { pt.x, pt.y, 0.f };
+  float best = FLT_MAX;
+  uint64_t bi = 0;
+  for (uint64_t k = 0; k < nk; ++k)
+  {
+    float result = 0.f, diff;
+    diff = q[0] - keyposes[3 * k];
+    result += diff * diff;
+    diff = q[1] - keyposes[3 * k + 1];
+    result += diff * diff;
+    diff = q[2] - keyposes[3 * k + 2];
+    result += diff * diff;
+    if (result < best)
+    {
+      best = result;
+      bi = k;
+    }
+  }
+  const float delta_h = keyposes[3 * bi + 2] - pt.z;
+  for (uint64_t i = 0; i < n; ++i)
+    p[i].z += delta_h;
+  return delta_h;
+}
+
+/* amcl3d/src/amcl3d.cpp:192-203; computeSampleNum() is called with its default cnt_per_grid = 3 (amcl3d.h) */
+int orc_pf_resample_step(const orc_map* m, orc_particle* p, uint64_t n, int weight_multiply, int min_resamp, int max_resamp,
+                         const float* keyposes, uint64_t nk, orc_particle* out)
+{
+  if (weight_multiply)
+    orc_scale_by_max(p, n);
+  int sample_num = orc_compute_sample_num(p, n, 3, min_resamp, max_resamp);
+  orc_uniform_sample(m, p, n, sample_num, out, NULL);
+  orc_update_sample_height(out, (uint64_t)sample_num, keyposes, nk);
+  return sample_num;
+}
+
 /* amcl3d/src/ParticleFilter.cpp:198-216 */
 void orc_mean(const orc_particle* p, uint64_t n, orc_particle* mean)
 {

@@ -99,6 +99,16 @@ int orc_uniform_sample(const orc_map* m, orc_particle* p, uint64_t n, int S, orc
 void orc_mean(const orc_particle* p, uint64_t n, orc_particle* mean);
 /* ParticleFilter::getBestParticle, ParticleFilter.cpp:218-228 */
 void orc_best(const orc_particle* p, uint64_t n, orc_particle* best);
+/* MonteCarloLocalization::computeSampleNum, amcl3d.cpp:242-288 (with computeBoundary :222-241): occupied
+ * 0.2 m x yaw bins times cnt_per_grid, clamped to [min_resamp, max_resamp].  The reference indexes its yaw
+ * axis unchecked (`y < theta` typo, :268); a yaw bin >= theta (|yaw| > 1100 rad) is not counted here. */
+int orc_compute_sample_num(const orc_particle* p, uint64_t n, int cnt_per_grid, int min_resamp, int max_resamp);
+/* MonteCarloLocalization::updateSampleHeight + getMapHeight, amcl3d.cpp:295-321: z += (z of the keypose nearest
+ * to (mean.x, mean.y, 0)) - mean.z.  keyposes: nk x 3 floats.  Returns delta_h. */
+float orc_update_sample_height(orc_particle* p, uint64_t n, const float* keyposes, uint64_t nk);
+/* MonteCarloLocalization::PFResample, amcl3d.cpp:192-203; out must hold max_resamp particles; returns new size */
+int orc_pf_resample_step(const orc_map* m, orc_particle* p, uint64_t n, int weight_multiply, int min_resamp, int max_resamp,
+                         const float* keyposes, uint64_t nk, orc_particle* out);
 /* sequential f32 inclusive prefix (ParticleFilter.cpp:259-264) -- exposed for the scan tests */
 void orc_prefix(const orc_particle* p, uint64_t n, float* out);
 

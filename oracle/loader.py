@@ -142,6 +142,9 @@ def lib():
         "orc_mean": (None, [vp, C.c_uint64, vp]),
         "orc_best": (None, [vp, C.c_uint64, vp]),
         "orc_prefix": (None, [vp, C.c_uint64, f32p]),
+        "orc_compute_sample_num": (C.c_int, [vp, C.c_uint64, C.c_int, C.c_int, C.c_int]),
+        "orc_update_sample_height": (C.c_float, [vp, C.c_uint64, f32p, C.c_uint64]),
+        "orc_pf_resample_step": (C.c_int, [mp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int, f32p, C.c_uint64, vp]),
         "orc_reloc_pose": (None, [vp, C.c_uint64, f32p, f32p, f32p, vp]),
         "orc_predict": (None, [vp, C.c_uint64, f64p, f32p]),
         "orc_compute_grid_nn": (C.c_int, [mp, f32p, C.c_uint32, C.c_uint64, C.c_int, f32p, C.c_int]),
@@ -252,6 +255,22 @@ def prefix(p):
     out = np.zeros(p.shape[0], np.float32)
     lib().orc_prefix(p.ctypes.data, p.shape[0], _fp(out))
     return out
+
+
+def compute_sample_num(p, cnt_per_grid=3, min_resamp=150, max_resamp=800) -> int:
+    return int(lib().orc_compute_sample_num(p.ctypes.data, p.shape[0], cnt_per_grid, min_resamp, max_resamp))
+
+
+def update_sample_height(p, keyposes) -> np.float32:
+    kp = _as_f32(keyposes, 3)
+    return np.float32(lib().orc_update_sample_height(p.ctypes.data, p.shape[0], _fp(kp), kp.shape[0]))
+
+
+def pf_resample_step(m: Map, p, weight_multiply, min_resamp, max_resamp, keyposes):
+    kp = _as_f32(keyposes, 3)
+    out = np.zeros((max(max_resamp, 1), 7), np.float32)
+    n = lib().orc_pf_resample_step(C.byref(m.c), p.ctypes.data, p.shape[0], int(weight_multiply), min_resamp, max_resamp, _fp(kp), kp.shape[0], out.ctypes.data)
+    return out[:n].copy()
 
 
 def reloc_pose(n, init, dev, noise):
@@ -399,6 +418,16 @@ def ref():
         "ref_pf_reloc_pose": (None, [vp, C.c_uint32, C.c_int, f32p, f32p, f32p]),
         "ref_pf_predict": (None, [vp, C.c_uint32, f64p, f64p, f32p]),
         "ref_trig_width": (C.c_int, []),
+        "ref_mcl_create": (vp, [vp, f32p, C.c_uint64]),
+        "ref_mcl_destroy": (None, [vp]),
+        "ref_mcl_set": (None, [vp, f32p, C.c_uint64]),
+        "ref_mcl_size": (C.c_uint64, [vp]),
+        "ref_mcl_get": (None, [vp, f32p]),
+        "ref_mcl_set_particle_num": (None, [vp, C.c_int, C.c_int]),
+        "ref_mcl_add_particle_weight": (None, [vp]),
+        "ref_mcl_compute_sample_num": (C.c_int, [vp, C.c_int]),
+        "ref_mcl_update_sample_height": (None, [vp]),
+        "ref_mcl_pf_resample": (None, [vp, C.c_int]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -512,6 +541,40 @@ class RefPF:
         noise = np.zeros(max(6 * n, 1), np.float32)
         ref().ref_pf_predict(self.h, int(seed), delta.ctypes.data_as(C.POINTER(C.c_double)), nd.ctypes.data_as(C.POINTER(C.c_double)), _fp(noise))
         return noise[: 6 * n]
+
+
+class RefMCL:
+    """amcl3d::MonteCarloLocalization of the compiled reference (amcl3d.cpp) bound to a RefGrid + keyposes."""
+
+    def __init__(self, grid: RefGrid, keyposes):
+        kp = _as_f32(keyposes, 3)
+        self.grid = grid
+        self.h = ref().ref_mcl_create(grid.h, _fp(kp), kp.shape[0])
+
+    def set(self, p):
+        p = np.ascontiguousarray(p, np.float32)
+        ref().ref_mcl_set(self.h, _fp(p), p.shape[0])
+
+    def get(self):
+        n = int(ref().ref_mcl_size(self.h))
+        out = np.zeros((n, 7), np.float32)
+        ref().ref_mcl_get(self.h, _fp(out))
+        return out
+
+    def set_particle_num(self, mx, mn):
+        ref().ref_mcl_set_particle_num(self.h, int(mx), int(mn))
+
+    def add_particle_weight(self):
+        ref().ref_mcl_add_particle_weight(self.h)
+
+    def compute_sample_num(self, cnt_per_grid=3):
+        return int(ref().ref_mcl_compute_sample_num(self.h, int(cnt_per_grid)))
+
+    def update_sample_height(self):
+        ref().ref_mcl_update_sample_height(self.h)
+
+    def pf_resample(self, weight_multiply):
+        ref().ref_mcl_pf_resample(self.h, int(weight_multiply))
 
 
 def ref_compute_grid(xyz, resol, sensor_dev, which=0, bounds=None):

@@ -16,7 +16,7 @@
 // the reference keeps its RNG and the .grid reader/writer private; the harness needs to seed the
 // former and call the latter (all standard headers are already included above)
 #define private public
-#include "ParticleFilter.h"
+#include "amcl3d.h"
 #undef private
 
 using amcl3d::Grid3d;
@@ -281,6 +281,62 @@ void ref_pf_predict(void* pfv, uint32_t seed, const double delta[6], const doubl
   pf->predict(delta[0], delta[1], delta[2], delta[3], delta[4], delta[5], noise_dev[0], noise_dev[1], noise_dev[2],
               noise_dev[3], noise_dev[4], noise_dev[5]);
 }
+// ---- MonteCarloLocalization (amcl3d.cpp): the direct callers of the path ---------------------------------------
+void* ref_mcl_create(void* grid, const float* keyposes_xyz, uint64_t nkey)
+{
+  amcl3d::MonteCarloLocalization* m = new amcl3d::MonteCarloLocalization(g_logger);
+  if (grid)
+  {
+    delete m->grid3d_;
+    m->grid3d_ = static_cast<Grid3d*>(grid);
+  }
+  m->grid3d_->keyposes_3d = make_cloud(keyposes_xyz, 3, nkey);
+  m->kdtree_keypose_3d_.reset(new pcl::KdTreeFLANN<PointType>());
+  m->kdtree_keypose_3d_->setInputCloud(m->grid3d_->keyposes_3d);
+  return m;
+}
+void ref_mcl_destroy(void* m)
+{
+  delete static_cast<amcl3d::MonteCarloLocalization*>(m);
+}
+void ref_mcl_set(void* mv, const float* aos7, uint64_t n)
+{
+  auto* m = static_cast<amcl3d::MonteCarloLocalization*>(mv);
+  m->p_.resize(n);
+  if (n)
+    std::memcpy(m->p_.data(), aos7, n * sizeof(Particle));
+}
+uint64_t ref_mcl_size(void* mv)
+{
+  return static_cast<amcl3d::MonteCarloLocalization*>(mv)->p_.size();
+}
+void ref_mcl_get(void* mv, float* aos7)
+{
+  auto* m = static_cast<amcl3d::MonteCarloLocalization*>(mv);
+  if (!m->p_.empty())
+    std::memcpy(aos7, m->p_.data(), m->p_.size() * sizeof(Particle));
+}
+void ref_mcl_set_particle_num(void* mv, int max_sample, int min_sample)
+{
+  static_cast<amcl3d::MonteCarloLocalization*>(mv)->setParticleNum(max_sample, min_sample);
+}
+void ref_mcl_add_particle_weight(void* mv)
+{
+  static_cast<amcl3d::MonteCarloLocalization*>(mv)->addParticleWeight();
+}
+int ref_mcl_compute_sample_num(void* mv, int cnt_per_grid)
+{
+  return static_cast<amcl3d::MonteCarloLocalization*>(mv)->computeSampleNum(cnt_per_grid);
+}
+void ref_mcl_update_sample_height(void* mv)
+{
+  static_cast<amcl3d::MonteCarloLocalization*>(mv)->updateSampleHeight();
+}
+void ref_mcl_pf_resample(void* mv, int weight_multiply)
+{
+  static_cast<amcl3d::MonteCarloLocalization*>(mv)->PFResample(weight_multiply != 0);
+}
+
 // which trig overload did `const auto sr = sin(roll)` (Grid3d.cpp:240) bind to in THIS build?
 // Returns 8 for double, 4 for float.  Mirrors the same unqualified call with the same headers visible.
 int ref_trig_width()

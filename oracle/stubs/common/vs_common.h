@@ -31,6 +31,15 @@ inline double toc(const char* name)
 {
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - tic_table()[name]).count();
 }
+template <typename T>
+inline T clip(T v, T lo, T hi)
+{
+  return v < lo ? lo : (v > hi ? hi : v);
+}
+inline double rad2deg(double r)
+{
+  return r * 57.29577951308232;
+}
 }  // namespace VSCOMMON
 
 #define LOG_INFO(...) do { } while (0)

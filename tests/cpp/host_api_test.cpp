@@ -8,7 +8,7 @@
 #include <string>
 #include <vector>
 
-#include "amcl3d/ParticleFilter.h"
+#include "amcl3d/amcl3d.h"
 #include "../../amcl3d_test_b200/host/map_io.h"
 
 using namespace amcl3d;
@@ -216,6 +216,34 @@ int main(int argc, char** argv)
     PointCloudInfo::Ptr pc = computePointCloud(map_cloud, resol);
     Grid3dInfo::Ptr gi2 = computeGrid2(pc, sensor_dev);
     dump("free_compute_grid2", reinterpret_cast<const float*>(gi2->grid.data()), gi2->grid.size(), 1);
+  }
+  // MonteCarloLocalization: the callers of the path (amcl3d.cpp:165-321)
+  {
+    MonteCarloLocalization mcl(log);
+    if (!mcl.grid3d_->openCloud(map_cloud, sensor_dev, resol, "", AMCL3D_B200_GRID_QUIRK))
+      return 5;
+    mcl.grid3d_->keyposes_3d.reset(new pcl::PointCloud<PointType>());
+    for (int k = 0; k < 12; ++k)
+    {
+      PointType kp;
+      kp.x = 0.7f * k;
+      kp.y = 6.5f - 0.5f * k;
+      kp.z = 0.1f * (k % 4);
+      mcl.grid3d_->keyposes_3d->push_back(kp);
+    }
+    dump_cloud("mcl_keyposes", *mcl.grid3d_->keyposes_3d);
+    mcl.setParticleNum(400, 150);
+    mcl.p_ = weighted;
+    dump_scalar("mcl_sample_num", (float)mcl.computeSampleNum());
+    mcl.p_ = weighted;
+    mcl.updateSampleHeight();
+    dump_particles("mcl_after_height", mcl.p_);
+    mcl.p_ = weighted;
+    mcl.PFResample(true);
+    dump_particles("mcl_after_pfresample", mcl.p_);
+    PointType h = mcl.getMapHeight(P[0].x, P[0].y);
+    const float hv[3] = { h.x, h.y, h.z };
+    dump("mcl_map_height", hv, 1, 3);
   }
   g_out.close();
   std::printf("host_api_test ok\n");

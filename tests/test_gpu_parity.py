@@ -540,3 +540,34 @@ def test_random_worlds_full_pipeline(O, seed):
     out, idx_ref, k = O.uniform_sample(m, W.copy(), S)
     idx, emitted = pf.uniformSample(S, want_idx=True)
     assert emitted == k and np.array_equal(idx, idx_ref) and np.array_equal(bits(pf.p_), bits(out))
+
+
+@pytest.mark.parametrize("kind,spread", [("T", 1.0), ("T", 0.2), ("T", 0.05), ("G", 1.0)])
+def test_mcl_resample_step(O, world_c1, pf, kind, spread):
+    """The callers of the path (amcl3d.cpp): computeSampleNum, updateSampleHeight and a whole PFResample step on the
+    device against the oracle (itself bit-identical to the reference's compiled amcl3d.cpp, test_oracle_golden.py)."""
+    from amcl3d_test_b200 import synth
+
+    w = world_c1
+    rng = np.random.RandomState(3)
+    kp = (rng.uniform(0, 1, (40, 3)) * [20, 20, 2]).astype(np.float32)
+    P = w[kind].copy()
+    gt = synth.gt_pose(w["synth"].extent, w["synth"].resol)
+    P[:, :6] = gt + (P[:, :6] - gt) * spread
+    W = O.update(w["map"], O.particles(P), w["cloud"])
+    for cpg in (3, 9):
+        pf.p_ = W
+        assert pf.computeSampleNum(cpg, 150, 800) == O.compute_sample_num(W, cpg, 150, 800)
+    pf.p_ = W
+    Z = W.copy()
+    dh_ref = O.update_sample_height(Z, kp)
+    assert bits(pf.updateSampleHeight(kp)) == bits(dh_ref)
+    assert np.array_equal(bits(pf.p_), bits(Z))
+    for wm in (0, 1):
+        pf.p_ = W
+        out = O.pf_resample_step(w["map"], W.copy(), wm, 150, 800, kp)
+        assert pf.PFResample(wm, 150, 800, kp) == out.shape[0]
+        assert np.array_equal(bits(pf.p_), bits(out))
+    # empty set: computeBoundary gives zeros -> widths 1 -> one cell, zero count -> min_resamp
+    pf.p_ = np.zeros((0, 7), np.float32)
+    assert pf.computeSampleNum(3, 150, 800) == O.compute_sample_num(np.zeros((0, 7), np.float32), 3, 150, 800) == 150

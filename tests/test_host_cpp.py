@@ -24,6 +24,9 @@ def test_host_library_builds_and_exports_the_reference_surface():
         "amcl3d::ParticleFilter::resample()", "amcl3d::ParticleFilter::uniformSample(int&)", "amcl3d::ParticleFilter::getMean()",
         "amcl3d::ParticleFilter::getBestParticle()", "amcl3d::ParticleFilter::setParticleNum(int, int)",
         "amcl3d::computePointCloud(", "amcl3d::computeGrid(", "amcl3d::computeGrid2(",
+        "amcl3d::MonteCarloLocalization::PFResample(bool)", "amcl3d::MonteCarloLocalization::computeSampleNum(int)",
+        "amcl3d::MonteCarloLocalization::updateSampleHeight()", "amcl3d::MonteCarloLocalization::RelocPose(",
+        "amcl3d::MonteCarloLocalization::PFMove(", "amcl3d::MonteCarloLocalization::getMapHeight(",
     ]:
         assert sym in out, sym
 
@@ -115,6 +118,13 @@ def test_cpp_classes_match_the_oracle(O, tmp_path):
     assert (work / "cloud.grid").stat().st_size == 20 + 4 * fm.n_cells
     rc, size, cached, devv = O.load_grid(work / "cloud.grid", 0.05)
     assert rc == 0 and size == fm.size and np.array_equal(bits(cached), bits(d["open_grid"].reshape(-1)))
+    # MonteCarloLocalization steps (amcl3d.cpp) through the C++ class
+    kp = d["mcl_keyposes"]
+    assert int(d["mcl_sample_num"][0, 0]) == O.compute_sample_num(W, 3, 150, 400)
+    Z = W.copy()
+    O.update_sample_height(Z, kp)
+    assert np.array_equal(bits(d["mcl_after_height"]), bits(Z))
+    assert np.array_equal(bits(d["mcl_after_pfresample"]), bits(O.pf_resample_step(m, W.copy(), 1, 150, 400, kp)))
     # free-function builders
     ref2 = O.compute_grid2(m, sm.points)
     assert np.allclose(d["free_compute_grid2"].reshape(-1), ref2, rtol=1e-6, atol=1e-30)

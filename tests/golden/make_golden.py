@@ -150,6 +150,36 @@ def main():
     np.savez_compressed(HERE / "ref_grid_case.npz", points=pts, size=np.array(g0["size"]), min=g0["min"], max=g0["max"],
                         compute_grid=g0["prob"], compute_grid2=g2["prob"], off_points=off, off_size=np.array(g2b["size"]),
                         off_min=g2b["min"], off_max=g2b["max"], off_compute_grid2=g2b["prob"])
+    # ---- callers of the path: amcl3d.cpp addParticleWeight / computeSampleNum / updateSampleHeight / PFResample
+    out = {}
+    kp = (np.random.RandomState(3).uniform(0, 1, (40, 3)) * [8, 8, 2]).astype(np.float32)
+    out["keyposes"] = kp
+    gt = synth.gt_pose(sm.extent, sm.resol)
+    for kind, spread in (("T", 1.0), ("T", 0.2), ("T", 0.05), ("G", 1.0)):
+        P = synth.make_particles(sm, 300, kind)
+        P[:, :6] = gt + (P[:, :6] - gt) * np.float32(spread)
+        pf = O.RefPF(rg)
+        pf.set(P)
+        pf.update(cloud_s)
+        W = pf.get()
+        tag = f"{kind}_{spread}"
+        mcl = O.RefMCL(rg, kp)
+        mcl.set(W)
+        mcl.add_particle_weight()
+        out[f"{tag}_scaled"] = mcl.get()[:, 6].copy()
+        for cpg in (3, 9):
+            mcl.set(W)
+            mcl.set_particle_num(800, 150)
+            out[f"{tag}_sample_num_{cpg}"] = np.int32(mcl.compute_sample_num(cpg))
+        mcl.set(W)
+        mcl.update_sample_height()
+        out[f"{tag}_height"] = mcl.get()[:, 2].copy()
+        for wm in (0, 1):
+            mcl.set(W)
+            mcl.set_particle_num(800, 150)
+            mcl.pf_resample(wm)
+            out[f"{tag}_pfresample_{wm}"] = mcl.get()
+    np.savez_compressed(HERE / "ref_mcl_case.npz", **out)
     for f in sorted(HERE.glob("*.np*")):
         print(f.name, f.stat().st_size)
 

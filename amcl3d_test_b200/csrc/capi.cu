@@ -243,8 +243,8 @@ int amcl3d_b200_device_info(int device, int* device_count, int* sm_count, int* c
 
 int amcl3d_b200_set_chain_mode(int mode)
 {
-  if (mode != 0 && mode != 1)
-    return fail(AMCL3D_B200_ERR_ARG, "chain mode must be 0 or 1");
+  if (mode < 0 || mode > 2)
+    return fail(AMCL3D_B200_ERR_ARG, "chain mode must be 0, 1 or 2");
   set_chain_mode(mode);
   return AMCL3D_B200_OK;
 }
@@ -842,6 +842,7 @@ static int set_cloud_common(amcl3d_b200_pf_t pf, const float* d_src, uint32_t st
     CU(ensure(pf->d_sort_scratch, pf->sort_scratch_cap, need));
     CU(launch_sort_cloud(d_src, stride, npts, npad, pf->d_sorted, pf->d_sort_scratch, need, pf->stream));
     pf->launches += 3;
+    pf->launches += chain_extra_launches_take();
   }
   pf->npts = npts;
   pf->npad = npad;
@@ -877,11 +878,12 @@ int amcl3d_b200_pf_set_cloud_device(amcl3d_b200_pf_t pf, const void* d_cloud, ui
 static int fuse_range_async(amcl3d_b200_pf_t pf, const float* d_wr, float alpha)
 {
   // w = alpha*wp/sum(wp) + (1-alpha)*wr/sum(wr): both sums as sequential f32 chains
-  CU(ensure(pf->d_dense, pf->dense_cap, pf->n));
+  CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(pf->n)));
   CU(launch_chain_prefix(pf->d_p, pf->n, 0, nullptr, pf->d_scalars + 0, pf->d_dense, pf->stream));
-  CU(launch_chain_sum_array(d_wr, pf->n, pf->d_scalars + 1, pf->stream));
+  CU(launch_chain_sum_array(d_wr, pf->n, pf->d_scalars + 1, pf->d_dense, pf->stream));
   CU(launch_fuse_range(pf->d_p, d_wr, pf->n, pf->d_scalars + 0, pf->d_scalars + 1, alpha, pf->stream));
   pf->launches += 4;
+  pf->launches += chain_extra_launches_take();
   return AMCL3D_B200_OK;
 }
 
@@ -1002,10 +1004,11 @@ int amcl3d_b200_pf_update_cloud(amcl3d_b200_pf_t pf, const float* cloud, uint32_
 
 static int normalize_async(amcl3d_b200_pf_t pf)
 {
-  CU(ensure(pf->d_dense, pf->dense_cap, pf->n));
+  CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(pf->n)));
   CU(launch_chain_prefix(pf->d_p, pf->n, 1, nullptr, pf->d_scalars + 0, pf->d_dense, pf->stream));
   CU(launch_normalize(pf->grid->map, pf->d_p, pf->n, pf->d_scalars + 0, pf->stream));
   pf->launches += pf->n ? 2 : 1;
+  pf->launches += chain_extra_launches_take();
   return AMCL3D_B200_OK;
 }
 
@@ -1039,6 +1042,7 @@ int amcl3d_b200_pf_scale_by_max(amcl3d_b200_pf_t pf)
     CU(launch_max_weight(pf->d_p, pf->n, pf->d_scalars + 2, pf->d_u64 + 1, pf->d_scratch, pf->stream));
     CU(launch_scale_by_max(pf->d_p, pf->n, pf->d_scalars + 2, pf->stream));
     pf->launches += 3;
+    pf->launches += chain_extra_launches_take();
   }
   CU(cudaStreamSynchronize(pf->stream));
   return AMCL3D_B200_OK;
@@ -1080,7 +1084,7 @@ int amcl3d_b200_pf_resample(amcl3d_b200_pf_t pf, float u01, uint64_t m0, uint64_
     return rc;
   const uint64_t cnt = m1 - m0;
   CU(ensure(pf->d_prefix, pf->prefix_cap, n));
-  CU(ensure(pf->d_dense, pf->dense_cap, n));
+  CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(n)));
   float* out = reinterpret_cast<float*>(d_out);
   if (!out)
   {
@@ -1098,6 +1102,7 @@ int amcl3d_b200_pf_resample(amcl3d_b200_pf_t pf, float u01, uint64_t m0, uint64_
     CU(launch_chain_prefix(pf->d_p, n, 0, pf->d_prefix, nullptr, pf->d_dense, pf->stream));
     CU(launch_resample_search(pf->d_p, pf->d_prefix, n, u01, m0, m1, out, d_idx, pf->stream));
     pf->launches += 2;
+    pf->launches += chain_extra_launches_take();
   }
   if (!d_out)
     if (int rc = adopt_alt(pf, n))
@@ -1125,7 +1130,7 @@ int amcl3d_b200_pf_uniform_sample(amcl3d_b200_pf_t pf, int sample_num, uint64_t 
     return rc;
   const uint64_t cnt = k1 - k0;
   CU(ensure(pf->d_prefix, pf->prefix_cap, n));
-  CU(ensure(pf->d_dense, pf->dense_cap, n));
+  CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(n > (uint64_t)S ? n : (uint64_t)S)));
   CU(ensure(pf->d_thr, pf->thr_cap, S));
   float* out = reinterpret_cast<float*>(d_out);
   if (!out)
@@ -1144,10 +1149,11 @@ int amcl3d_b200_pf_uniform_sample(amcl3d_b200_pf_t pf, int sample_num, uint64_t 
     if (int rc = normalize_async(pf))  // ParticleFilter.cpp:258
       return rc;
     CU(launch_chain_prefix(pf->d_p, n, 0, pf->d_prefix, nullptr, pf->d_dense, pf->stream));
-    CU(launch_chain_thresholds(sample_num, pf->d_thr, pf->stream));
+    CU(launch_chain_thresholds(sample_num, pf->d_thr, pf->d_dense, pf->stream));
     CU(launch_uniform_search(pf->d_p, pf->d_prefix, n, pf->d_thr, sample_num, k0, k1, out, d_idx, pf->stream));
     CU(launch_count_emitted(pf->d_thr, sample_num, pf->d_prefix, n, pf->d_int, pf->stream));
     pf->launches += 4;
+    pf->launches += chain_extra_launches_take();
   }
   if (!d_out)
     if (int rc = adopt_alt(pf, S))
@@ -1188,6 +1194,7 @@ int amcl3d_b200_pf_best(amcl3d_b200_pf_t pf, float out7[7])
     Timed t(pf);
     CU(launch_max_weight(pf->d_p, pf->n, pf->d_scalars + 2, pf->d_u64 + 1, pf->d_scratch, pf->stream));
     pf->launches += 2;
+    pf->launches += chain_extra_launches_take();
   }
   unsigned long long arg = ~0ull;
   CU(cudaMemcpyAsync(&arg, pf->d_u64 + 1, sizeof(arg), cudaMemcpyDeviceToHost, pf->stream));
@@ -1227,11 +1234,12 @@ int amcl3d_b200_pf_prefix(amcl3d_b200_pf_t pf, void** d_prefix, float* host_out,
   if (int rc = use_device(pf->grid->device))
     return rc;
   CU(ensure(pf->d_prefix, pf->prefix_cap, pf->n));
-  CU(ensure(pf->d_dense, pf->dense_cap, pf->n));
+  CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(pf->n)));
   {
     Timed t(pf);
     CU(launch_chain_prefix(pf->d_p, pf->n, 0, pf->d_prefix, nullptr, pf->d_dense, pf->stream));
     pf->launches += 1;
+    pf->launches += chain_extra_launches_take();
   }
   if (host_out && pf->n)
     CU(cudaMemcpyAsync(host_out, pf->d_prefix, sizeof(float) * pf->n, cudaMemcpyDeviceToHost, pf->stream));
@@ -1258,6 +1266,7 @@ int amcl3d_b200_pf_compute_sample_num(amcl3d_b200_pf_t pf, int cnt_per_grid, int
     Timed t(pf);
     CU(launch_particle_bounds(pf->d_p, pf->n, d_keys, pf->stream));
     pf->launches += 1;
+    pf->launches += chain_extra_launches_take();
   }
   if (pf->n)
   {
@@ -1297,6 +1306,7 @@ int amcl3d_b200_pf_compute_sample_num(amcl3d_b200_pf_t pf, int cnt_per_grid, int
   cudaError_t e = launch_sample_bins(pf->d_p, pf->n, lo[0], lo[1], lo[2], xwidth, ywidth, zwidth, theta, d_bits, words, pf->d_int + 1,
                                      pf->stream);
   pf->launches += 1;
+  pf->launches += chain_extra_launches_take();
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(&cnt, pf->d_int + 1, sizeof(int), cudaMemcpyDeviceToHost, pf->stream);
   if (e == cudaSuccess)

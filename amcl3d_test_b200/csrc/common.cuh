@@ -131,16 +131,18 @@ cudaError_t launch_gather_bench(const float* cells, uint64_t window, uint32_t bl
 // serial f32 chain over w (stride 7 floats): prefix[i] (nullable) = sequential inclusive prefix starting
 // from 0; positive_only: add only w > 0 (particleNormalize).  total[0] receives the final value.
 cudaError_t launch_chain_prefix(const float* particles, uint64_t n, int positive_only, float* prefix, float* total,
-                                float* dense_scratch /* n floats, nullable */, cudaStream_t stream);
+                                float* dense_scratch /* chain_scratch_floats(n), nullable */, cudaStream_t stream);
 // thresholds samp_0 = 0.5f/S, samp_{k+1} = samp_k + 1.0f/S (sequential f32 chain)
-cudaError_t launch_chain_thresholds(int S, float* thr, cudaStream_t stream);
+cudaError_t launch_chain_thresholds(int S, float* thr, float* scratch /* chain_scratch_floats(S), nullable */, cudaStream_t stream);
 // w = total>0 ? w/total : 0 ; w = 0 outside the map
 cudaError_t launch_normalize(const MapDev& map, float* particles, uint64_t n, const float* total, cudaStream_t stream);
 // range fusion: w = alpha*wp/sum_p + (1-alpha)*wr/sum_r (sums: sequential f32 chains)
 cudaError_t launch_fuse_range(float* particles, const float* wr, uint64_t n, const float* sum_p, const float* sum_r,
                               float alpha, cudaStream_t stream);
-void set_chain_mode(int mode);  // 0 exact parallel scan, 1 serial chain
-cudaError_t launch_chain_sum_array(const float* v, uint64_t n, float* total, cudaStream_t stream);
+void set_chain_mode(int mode);  // 0 exact scan over many CTAs, 1 serial chain, 2 exact scan on one CTA
+uint64_t chain_scratch_floats(uint64_t n);  // dense operands + per-tile bookkeeping of the many-CTA scan
+uint32_t chain_extra_launches_take();       // kernels launched by the chain calls beyond one each, since the last take
+cudaError_t launch_chain_sum_array(const float* v, uint64_t n, float* total, float* scratch, cudaStream_t stream);
 // max weight (and first arg-max with w > 0) -> out_max[0], out_arg[0] (UINT64_MAX if none)
 cudaError_t launch_max_weight(const float* particles, uint64_t n, float* out_max, unsigned long long* out_arg,
                               void* scratch, cudaStream_t stream);

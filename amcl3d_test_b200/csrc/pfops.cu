@@ -141,8 +141,15 @@ __global__ void __launch_bounds__(kChainThreads)
 // 2^(e+1) (a binade crossing: at most a few dozen per array) is redone with a real f32 add and the scan
 // restarts on the coarser grid.  Negative / non-finite operands and denormal sums also take the serial add.
 constexpr int kScanThreads = 1024;
-constexpr int kScanItems = 16;
-constexpr unsigned long long kNoCross = ~0ull;
+constexpr int kScanItems = 8;
+constexpr float kHandOver = 128.f;  // serial run-up while fewer than about this many adds remain in the binade
+// operands / results of one chunk pass through shared memory so that global traffic is coalesced while every
+// thread still owns kScanItems consecutive elements; one pad word per kScanItems keeps both views conflict-free
+__device__ __forceinline__ int stage_slot(int i)
+{
+  return i + (i >> 3);
+}
+constexpr int kStageWords = kScanThreads * kScanItems + kScanThreads;
 constexpr int kSat = 1 << 28;
 
 struct StepFn
@@ -156,151 +163,200 @@ __device__ __forceinline__ StepFn step_compose(StepFn f, StepFn g)  // f first, 
   r.d1 = min(f.d1 + (((f.d1 + 1) & 1) ? g.d1 : g.d0), kSat);
   return r;
 }
-// step of one operand on the grid of binade e: k and class (0 round down, 1 round up, 2 tie)
-__device__ __forceinline__ void step_classify(float w, int e, int& k, int& cls)
+// Step of one operand on the grid of binade e, branch-free.  With w = (k + f)*u the code packs
+//   k (bits 2..), h = [f >= 1/2] (bit 1), st = [f is neither 0 nor 1/2] (bit 0);
+// the add then is  s' = s + k + (h & (st | (s + k))), the last term being round-to-nearest-even.
+// Negative / non-finite operands and operands above the binade get kBadCode (k saturates: a forced "crossing"
+// that hands the element to the serial add).  Zeros and denormals (far below u/2 for e >= -99) code as 0.
+constexpr uint32_t kBadCode = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t step_code(uint32_t b, int e)
 {
-  const uint32_t b = __float_as_uint(w);
-  k = 0;
-  cls = 0;
-  if (b == 0u)
-    return;
   const uint32_t ew = (b >> 23) & 0xFFu;
-  if ((b & 0x80000000u) || ew == 0xFFu)
-  {
-    k = kSat;  // negative, NaN, Inf: force the serial add
-    return;
-  }
-  if (ew == 0u)
-    return;  // denormal operand against a normal sum with e >= -100: far below u/2
-  const uint32_t m = (b & 0x7FFFFFu) | 0x800000u;
-  const int sh = e - ((int)ew - 127);
-  if (sh < 0)
-  {
-    k = kSat;  // operand above the sum's binade: certain crossing
-    return;
-  }
-  if (sh == 0)
-  {
-    k = (int)m;
-    return;
-  }
-  if (sh >= 25)
-    return;
-  k = (int)(m >> sh);
-  const uint32_t rem = m & ((1u << sh) - 1u);
-  const uint32_t half = 1u << (sh - 1);
-  cls = rem > half ? 1 : (rem == half ? 2 : 0);
+  const int sh = e + 127 - (int)ew;
+  const uint32_t m2 = ew ? (((b & 0x7FFFFFu) | 0x800000u) << 1) : 0u;
+  const uint32_t shc = (uint32_t)min(max(sh, 0), 31);
+  const uint32_t t = m2 >> shc;
+  const uint32_t low = m2 & ((1u << shc) - 1u);
+  const bool bad = (b & 0x80000000u) || ew == 0xFFu || sh < 0;
+  return bad ? kBadCode : ((t << 1) | (low != 0u ? 1u : 0u));
 }
-__device__ __forceinline__ int step_apply(int s, int k, int cls)
+__device__ __forceinline__ int step_apply(int s, uint32_t code)
 {
-  const int b = min(s + k, kSat);
-  return b + (cls == 1 ? 1 : 0) + (cls == 2 ? (b & 1) : 0);
+  const int t = min(s + (int)(code >> 2), kSat);
+  return t + (int)((code >> 1) & (code | (uint32_t)t) & 1u);
 }
+// the StepFn of a run of codes: follow an even and an odd virtual state through it
+struct StepPair
+{
+  int a = 0, b = 1;
+  __device__ __forceinline__ void push(uint32_t code)
+  {
+    a = step_apply(a, code);
+    b = step_apply(b, code);
+  }
+  __device__ __forceinline__ StepFn fn() const
+  {
+    return StepFn{ min(a, kSat), min(b - 1, kSat) };
+  }
+};
 __device__ __forceinline__ float state_value(int e, int s)  // s in [2^23, 2^24)
 {
   return __uint_as_float(((uint32_t)(e + 127) << 23) | ((uint32_t)s & 0x7FFFFFu));
 }
 
-// mode / operands as chain_kernel.  Threshold mode: out[0] = start, out[k] = value after k adds (n = S).
-__global__ void __launch_bounds__(kScanThreads)
-    exact_scan_kernel(const float* __restrict__ src, uint32_t stride, uint32_t offset, uint64_t n, int mode, float start,
-                      float inc, float* __restrict__ prefix, float* __restrict__ total)
+// The operands of one chain: element i lives at src[i*stride + offset] (sum modes) or is the constant inc
+// (threshold mode, where the value after add i goes to prefix[i+1]).
+struct ChainOps
 {
-  __shared__ float sh_c;
-  __shared__ unsigned long long sh_i, sh_cross;
-  __shared__ int sh_s;
-  __shared__ StepFn warp_fn[kScanThreads / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // number of adds: thresholds emit S values from S-1 adds
-  const uint64_t nadd = (mode == kChainThreshold) ? (n > 0 ? n - 1 : 0) : n;
-
-  auto operand = [&](uint64_t i) -> float {
+  const float* src;
+  uint32_t stride, offset;
+  int mode;
+  float inc;
+  float* prefix;
+  __device__ __forceinline__ float operand(uint64_t i) const
+  {
     if (mode == kChainThreshold)
       return inc;
     const float v = src[i * stride + offset];
     if (mode == kChainSumPositive)
       return v > 0.f ? v : 0.f;
     return v;
-  };
-  auto emit = [&](uint64_t i, float v) {
+  }
+  __device__ __forceinline__ void emit(uint64_t i, float v) const
+  {
     if (prefix == nullptr)
       return;
     if (mode == kChainThreshold)
       prefix[i + 1] = v;
     else
       prefix[i] = v;
-  };
-
-  if (tid == 0)
-  {
-    sh_c = start;
-    sh_i = 0;
-    if (mode == kChainThreshold && prefix != nullptr && n > 0)
-      prefix[0] = start;
   }
-  __syncthreads();
+};
 
-  while (true)
+// Block-wide (kScanThreads threads): performs adds [begin, nadd) of the chain starting from state `start`,
+// emits the running values and returns the final state to every thread.
+//
+// One chunk of kScanThreads*kScanItems operands at a time is staged in shared memory (coalesced), turned into
+// running values in place, and written back coalesced.  Inside a chunk three kinds of pass alternate until every
+// slot holds its result:
+//   serial  lane 0 adds element by element (real f32 adds, operands from shared memory) -- the crossing element,
+//           anything the integer scheme does not cover, and the run-up while the binade is about to end anyway;
+//   zero    while the state is +0, leading +0 operands leave it there: find the first other operand in parallel;
+//   binade  the integer step scan of the remaining slots on the grid of the current binade, up to the first
+//           element whose result leaves it.
+__device__ float scan_range(const ChainOps& ops, uint64_t begin, uint64_t nadd, float start, float* stage /* [kStageWords] shared */)
+{
+  __shared__ float sh_c;
+  __shared__ int sh_pos, sh_cross;
+  __shared__ StepFn warp_fn[kScanThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kChunkLen = kScanThreads * kScanItems;
+  constexpr int kNone = 0x7fffffff;
+
+  float c = start;
+  for (uint64_t base = begin; base < nadd; base += kChunkLen)
   {
-    // ---- serial phase: the crossing element (or anything the integer scheme does not cover) ----------
+    const int len = (int)min((uint64_t)kChunkLen, nadd - base);
+    __syncthreads();  // the previous chunk's (or call's) readers are done with stage / sh_*
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j)
+    {
+      const int i = j * kScanThreads + tid;
+      if (i < len)
+        stage[stage_slot(i)] = ops.operand(base + i);
+    }
     if (tid == 0)
     {
-      uint64_t i = sh_i;
-      float c = sh_c;
-      while (i < nadd)
-      {
-        const float w = operand(i);
-        const uint32_t cb = __float_as_uint(c);
-        const int ce = (int)((cb >> 23) & 0xFFu);
-        const bool c_ok = !(cb & 0x80000000u) && ce > 27 && ce < 0xFF;  // positive, normal, e >= -99
-        if (c_ok && w >= 0.f)
-        {
-          const float r = __fadd_rn(c, w);
-          if (((__float_as_uint(r) >> 23) & 0xFFu) == (uint32_t)ce)
-          {
-            // stays in the binade.  Hand over to the scan only if the binade is expected to last a while
-            // (room to the next power of two vs the current operand); otherwise a block-wide round would
-            // be spent on a handful of elements -- purely a scheduling heuristic, both paths are exact.
-            const float top = __uint_as_float((uint32_t)(ce + 1) << 23);
-            if (__fsub_rn(top, c) > w * 256.f)
-              break;
-          }
-        }
-        c = __fadd_rn(c, w);
-        emit(i, c);
-        ++i;
-      }
+      sh_pos = 0;
       sh_c = c;
-      sh_i = i;
     }
     __syncthreads();
-    uint64_t base = sh_i;
-    const float c0 = sh_c;
-    if (base >= nadd)
-      break;
-    const int e = (int)((__float_as_uint(c0) >> 23) & 0xFFu) - 127;
-    int s_chunk = (int)((__float_as_uint(c0) & 0x7FFFFFu) | 0x800000u);
 
-    // ---- parallel phase: chunks of kScanThreads * kScanItems operands inside binade e --------------------
     while (true)
     {
-      const uint64_t idx0 = base + (uint64_t)tid * kScanItems;
-      int k[kScanItems], cls[kScanItems];
-      StepFn f{ 0, 0 };
+      // ---- serial pass ---------------------------------------------------------------------------------
+      if (tid == 0)
+      {
+        int i = sh_pos;
+        float cc = sh_c;
+        while (i < len)
+        {
+          const float w = stage[stage_slot(i)];
+          const uint32_t cb = __float_as_uint(cc);
+          const int ce = (int)((cb >> 23) & 0xFFu);
+          const bool c_ok = !(cb & 0x80000000u) && ce > 27 && ce < 0xFF;  // positive, normal, e >= -99
+          if (c_ok && w >= 0.f)
+          {
+            const float top = __uint_as_float((uint32_t)(ce + 1) << 23);
+            if (__fadd_rn(cc, w) < top)
+            {
+              // stays in the binade.  Hand over to the scan only if the binade is expected to last a while
+              // (room to the next power of two vs the current operand); otherwise a block-wide pass would
+              // be spent on a handful of elements -- purely a scheduling heuristic, both paths are exact.
+              if (__fsub_rn(top, cc) > w * kHandOver)
+                break;
+              // run-up to the end of the binade: plain adds until the sum would reach `top` (or an operand
+              // needs the general step below), then look again
+              const int limit = min(len, i + 2 * (int)kHandOver);
+              for (; i < limit; ++i)
+              {
+                const float v = stage[stage_slot(i)];
+                const float r = __fadd_rn(cc, v);
+                if (!(v >= 0.f) || !(r < top))
+                  break;
+                cc = r;
+                stage[stage_slot(i)] = r;
+              }
+              continue;
+            }
+          }
+          else if (cb == 0u && __float_as_uint(w) == 0u)
+            break;  // zero pass
+          cc = __fadd_rn(cc, w);
+          stage[stage_slot(i)] = cc;
+          ++i;
+        }
+        sh_pos = i;
+        sh_c = cc;
+        sh_cross = kNone;
+      }
+      __syncthreads();
+      const int pos = sh_pos;
+      const float c0 = sh_c;
+      if (pos >= len)
+        break;
+      const int i0 = tid * kScanItems;
+
+      if (__float_as_uint(c0) == 0u)
+      {
+        // ---- zero pass: slots [pos, first other operand) already hold their result (+0) ----------------
+        int first = kNone;
+#pragma unroll
+        for (int j = kScanItems - 1; j >= 0; --j)
+          if (i0 + j >= pos && i0 + j < len && __float_as_uint(stage[stage_slot(i0 + j)]) != 0u)
+            first = i0 + j;
+        if (first != kNone)
+          atomicMin(&sh_cross, first);
+        __syncthreads();
+        if (tid == 0)
+          sh_pos = min(sh_cross, len);
+        __syncthreads();
+        continue;
+      }
+
+      // ---- binade pass ---------------------------------------------------------------------------------
+      const int e = (int)((__float_as_uint(c0) >> 23) & 0xFFu) - 127;
+      const int s0 = (int)((__float_as_uint(c0) & 0x7FFFFFu) | 0x800000u);
+      uint32_t code[kScanItems];
+      StepPair run;
 #pragma unroll
       for (int j = 0; j < kScanItems; ++j)
       {
-        k[j] = 0;
-        cls[j] = 0;
-        if (idx0 + j < nadd)
-        {
-          step_classify(operand(idx0 + j), e, k[j], cls[j]);
-          StepFn g;
-          g.d0 = min(k[j] + (cls[j] == 1 ? 1 : 0) + (cls[j] == 2 ? (k[j] & 1) : 0), kSat);
-          g.d1 = min(k[j] + (cls[j] == 1 ? 1 : 0) + (cls[j] == 2 ? ((k[j] + 1) & 1) : 0), kSat);
-          f = step_compose(f, g);
-        }
+        const bool live = i0 + j >= pos && i0 + j < len;
+        code[j] = live ? step_code(__float_as_uint(stage[stage_slot(i0 + j)]), e) : 0u;
+        run.push(code[j]);
       }
+      const StepFn f = run.fn();
       // inclusive scan of the per-thread functions across the block
       StepFn incl = f;
 #pragma unroll
@@ -314,8 +370,6 @@ __global__ void __launch_bounds__(kScanThreads)
       }
       if (lane == 31)
         warp_fn[warp] = incl;
-      if (tid == 0)
-        sh_cross = kNoCross;
       __syncthreads();
       if (warp == 0)
       {
@@ -343,63 +397,531 @@ __global__ void __launch_bounds__(kScanThreads)
         excl = step_compose(warp_fn[warp - 1], lane_excl);
       const StepFn block_total = warp_fn[kScanThreads / 32 - 1];
 
-      int s = min(s_chunk + ((s_chunk & 1) ? excl.d1 : excl.d0), kSat);
-      unsigned long long my_cross = kNoCross;
-      int s_before_cross = 0;
-      if (s >= (1 << 24) && idx0 < nadd)
-        my_cross = idx0;  // an earlier thread already crossed; its index is smaller and wins the min below
+      int s = min(s0 + ((s0 & 1) ? excl.d1 : excl.d0), kSat);
+      int my_cross = kNone, s_before_cross = 0;
+      if (s >= (1 << 24) && i0 + kScanItems > pos && i0 < len)
+        my_cross = max(i0, pos);  // an earlier thread already crossed; its index is smaller and wins the min below
 #pragma unroll
       for (int j = 0; j < kScanItems; ++j)
       {
-        if (idx0 + j < nadd && my_cross == kNoCross)
+        if (i0 + j >= pos && i0 + j < len && my_cross == kNone)
         {
-          const int s2 = step_apply(s, k[j], cls[j]);
+          const int s2 = step_apply(s, code[j]);
           if (s2 >= (1 << 24))
           {
-            my_cross = idx0 + j;
+            my_cross = i0 + j;
             s_before_cross = s;
           }
           else
           {
-            emit(idx0 + j, state_value(e, s2));
+            stage[stage_slot(i0 + j)] = state_value(e, s2);  // own slot: nobody else reads it
             s = s2;
           }
         }
       }
-      if (my_cross != kNoCross)
+      if (my_cross != kNone)
         atomicMin(&sh_cross, my_cross);
       __syncthreads();
-      const unsigned long long cross = sh_cross;
-      if (cross != kNoCross)
+      const int cross = sh_cross;
+      if (cross != kNone)
       {
         // the owner of the first crossing knows the state just before it (threads that only inherited an
-        // overflowed state have larger indices)
+        // overflowed state have larger indices); lane 0 redoes that element with a real add
         if (my_cross == cross && s_before_cross != 0)
         {
           sh_c = state_value(e, s_before_cross);
-          sh_i = cross;
+          sh_pos = cross;
         }
-        __syncthreads();
-        break;
       }
-      const uint64_t chunk = (uint64_t)kScanThreads * kScanItems;
-      s_chunk = s_chunk + ((s_chunk & 1) ? block_total.d1 : block_total.d0);
-      base += chunk;
-      if (base >= nadd)
+      else if (tid == 0)
       {
-        if (tid == 0)
-        {
-          sh_c = state_value(e, s_chunk);
-          sh_i = nadd;
-        }
-        __syncthreads();
-        break;
+        sh_c = state_value(e, s0 + ((s0 & 1) ? block_total.d1 : block_total.d0));
+        sh_pos = len;
       }
-      __syncthreads();  // warp_fn / sh_cross are rewritten by the next chunk
+      __syncthreads();
+    }
+    c = sh_c;
+    if (ops.prefix != nullptr)
+    {
+#pragma unroll
+      for (int j = 0; j < kScanItems; ++j)
+      {
+        const int i = j * kScanThreads + tid;
+        if (i < len)
+          ops.emit(base + i, stage[stage_slot(i)]);
+      }
+    }
+  }
+  __syncthreads();
+  return c;
+}
+
+// single-CTA form (chain mode 2, and arrays of a tile or two).  Threshold mode: out[0] = start, out[k] = value
+// after k adds (n = S).
+__global__ void __launch_bounds__(kScanThreads)
+    exact_scan_kernel(const float* __restrict__ src, uint32_t stride, uint32_t offset, uint64_t n, int mode, float start,
+                      float inc, float* __restrict__ prefix, float* __restrict__ total)
+{
+  const ChainOps ops{ src, stride, offset, mode, inc, prefix };
+  const uint64_t nadd = (mode == kChainThreshold) ? (n > 0 ? n - 1 : 0) : n;  // S thresholds from S-1 adds
+  if (threadIdx.x == 0 && mode == kChainThreshold && prefix != nullptr && n > 0)
+    prefix[0] = start;
+  __shared__ float stage[kStageWords];
+  const float c = scan_range(ops, 0, nadd, start, stage);
+  if (threadIdx.x == 0 && total != nullptr)
+    total[0] = c;
+}
+
+// ---- the same recurrence over many CTAs -----------------------------------------------------------------
+// A run of operands acts on the incoming state as one StepFn as long as the state stays inside a binade whose
+// exponent is known.  tile_sum / tile_fn evaluate that function in parallel for every sub-tile of kSubLen operands
+// (one warp each) and, composed, for every tile of kTile operands -- for the three binades around a guess (the
+// f64 sum of everything before the sub-tile).  resolve_kernel then walks the tiles serially in O(1) each; in a
+// tile where that fails (the state leaves the binade inside it: a few dozen tiles per array) it walks the
+// sub-tiles in O(1) each and redoes the one that holds the crossing with real f32 adds.  emit_kernel finally
+// derives every sub-tile's exact incoming state the same way and turns the operands into running values with
+// one warp-wide integer scan per sub-tile.  Nothing here is approximate: a guess that misses only costs time
+// (serial adds, or the block-wide scan_range when a whole tile is off).
+constexpr uint64_t kTile = (uint64_t)kScanThreads * kScanItems;
+constexpr int kSubTiles = kScanThreads / 32;
+constexpr int kSubLen = 32 * kScanItems;
+constexpr int kCand = 3;
+constexpr int kNoGuess = -100000;
+constexpr int kMaxSerialSubTiles = 8;
+struct __align__(16) TileFn
+{
+  int g;         // candidate c covers binade g - 1 + c; kNoGuess: look at the sub-tiles
+  int identity;  // every operand is +0: the state passes through whatever it is
+  int d[kCand][2];
+};
+struct __align__(16) TileSubFn
+{
+  StepFn f[kCand][kSubTiles];
+  int g[kSubTiles];
+};
+constexpr int kSubWords = sizeof(TileSubFn) / 4;
+
+__global__ void __launch_bounds__(kScanThreads) tile_sum_kernel(ChainOps ops, uint64_t nadd, double* __restrict__ tile_sum)
+{
+  const uint64_t begin = (uint64_t)blockIdx.x * kTile;
+  double s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j)
+  {
+    const uint64_t i = begin + (uint64_t)j * kScanThreads + threadIdx.x;
+    if (i < nadd)
+      s += (double)ops.operand(i);
+  }
+  __shared__ double sh[kScanThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0)
+    sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    double v = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w)
+      v += sh[w];
+    tile_sum[blockIdx.x] = v;
+  }
+}
+
+__device__ __forceinline__ int guess_binade(double v)
+{
+  const uint32_t gb = __float_as_uint((float)v);
+  const int ge = (int)((gb >> 23) & 0xFFu);
+  return (!(gb & 0x80000000u) && ge > 28 && ge < 0xFE) ? ge - 127 : kNoGuess;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+    tile_fn_kernel(ChainOps ops, uint64_t nadd, float start, const double* __restrict__ tile_sum, TileFn* __restrict__ fns,
+                   TileSubFn* __restrict__ subs)
+{
+  __shared__ double sh_red[kSubTiles], sh_wsum[kSubTiles];
+  __shared__ int sh_g[kSubTiles], sh_nonzero;
+  __shared__ StepFn sh_fn[kCand][kSubTiles];
+  __shared__ float stage[kStageWords];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t t = blockIdx.x, begin = t * kTile;
+  int nonzero = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j)
+  {
+    const int i = j * kScanThreads + tid;
+    const float w = (begin + i < nadd) ? ops.operand(begin + i) : 0.f;
+    nonzero |= (__float_as_uint(w) != 0u);
+    stage[stage_slot(i)] = w;
+  }
+  // f64 sum of everything before this tile
+  double before = 0;
+  if (ops.mode == kChainThreshold)
+    before = (tid == 0) ? (double)ops.inc * (double)begin : 0.0;
+  else
+    for (uint64_t k = tid; k < t; k += kScanThreads)
+      before += tile_sum[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    before += __shfl_xor_sync(0xffffffffu, before, o);
+  if (lane == 0)
+    sh_red[warp] = before;
+  if (tid == 0)
+    sh_nonzero = 0;
+  __syncthreads();
+  // f64 sum of each sub-tile (warp w owns operands [w*kSubLen, (w+1)*kSubLen) of the tile)
+  uint32_t wb[kScanItems];
+  double mine = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j)
+  {
+    const float w = stage[stage_slot(tid * kScanItems + j)];
+    wb[j] = __float_as_uint(w);
+    mine += (double)w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if (lane == 0)
+    sh_wsum[warp] = mine;
+  if (nonzero)
+    sh_nonzero = 1;
+  __syncthreads();
+  if (warp == 0)
+  {
+    // guess per sub-tile: the binade of (start + everything before it) evaluated in f64
+    double base = (double)start;
+    for (int w = 0; w < kSubTiles; ++w)
+      base += sh_red[w];
+    const double v = sh_wsum[lane];
+    double incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      const double p = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o)
+        incl += p;
+    }
+    sh_g[lane] = guess_binade(base + (incl - v));
+  }
+  __syncthreads();
+  const int g = sh_g[warp];
+
+  StepPair run[kCand];
+  if (g != kNoGuess)
+  {
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j)
+    {
+#pragma unroll
+      for (int c = 0; c < kCand; ++c)
+        run[c].push(step_code(wb[j], g - 1 + c));  // slots beyond nadd hold +0: no step
+    }
+  }
+  // ordered reduction: lane i ends with the composition of lanes [i, i + 2o)
+#pragma unroll
+  for (int c = 0; c < kCand; ++c)
+  {
+    StepFn v = run[c].fn();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      StepFn r;
+      r.d0 = __shfl_down_sync(0xffffffffu, v.d0, o);
+      r.d1 = __shfl_down_sync(0xffffffffu, v.d1, o);
+      if (lane + o < 32)
+        v = step_compose(v, r);
+    }
+    if (lane == 0)
+    {
+      sh_fn[c][warp] = v;
+      subs[t].f[c][warp] = v;
+    }
+  }
+  if (lane == 0)
+    subs[t].g[warp] = g;
+  __syncthreads();
+  if (warp == 0)
+  {
+    // the tile as a whole has a function only if all its sub-tiles were evaluated for the same binades
+    const int g0 = sh_g[0];
+    const bool uniform = __all_sync(0xffffffffu, sh_g[lane] == g0) && g0 != kNoGuess;
+    TileFn out;
+    out.g = uniform ? g0 : kNoGuess;
+    out.identity = sh_nonzero ? 0 : 1;
+#pragma unroll
+    for (int c = 0; c < kCand; ++c)
+    {
+      StepFn v = sh_fn[c][lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        StepFn r;
+        r.d0 = __shfl_down_sync(0xffffffffu, v.d0, o);
+        r.d1 = __shfl_down_sync(0xffffffffu, v.d1, o);
+        if (lane + o < 32)
+          v = step_compose(v, r);
+      }
+      out.d[c][0] = v.d0;
+      out.d[c][1] = v.d1;
+    }
+    if (lane == 0)
+      fns[t] = out;
+  }
+}
+
+// which candidate of a run guessed at g covers state c (-1: none / the integer scheme does not apply); s = the
+// state's integer mantissa
+__device__ __forceinline__ int candidate_of(float c, int g, int& s)
+{
+  const uint32_t cb = __float_as_uint(c);
+  const int ce = (int)((cb >> 23) & 0xFFu);
+  s = (int)((cb & 0x7FFFFFu) | 0x800000u);
+  if (g == kNoGuess || (cb & 0x80000000u) || ce <= 27 || ce == 0xFF)
+    return -1;
+  const int idx = (ce - 127) - (g - 1);
+  return (idx < 0 || idx >= kCand) ? -1 : idx;
+}
+// O(1) application of a run to the state; false if the state would leave the binade (or an operand needs the
+// real add)
+__device__ __forceinline__ bool fn_apply(int d0, int d1, int s, float& c)
+{
+  const int d = (s & 1) ? d1 : d0;
+  if (d >= kSat || s + d >= (1 << 24))
+    return false;
+  c = __uint_as_float((__float_as_uint(c) & 0x7F800000u) | ((uint32_t)(s + d) & 0x7FFFFFu));
+  return true;
+}
+
+// One thread walks the sub-tiles of a staged tile from state c.  A sub-tile whose function applies costs O(1);
+// otherwise its operands are added one by one (kept: the running values replace them in `stage`, and the
+// sub-tile is marked finished).  sub_state (nullable) receives every sub-tile's incoming state.  Stops early,
+// returning the sub-tile index, once more than kMaxSerialSubTiles needed the adds (the caller then switches to
+// the block-wide scan); returns kSubTiles when the tile is through.
+__device__ int walk_sub_tiles(const TileSubFn& sub, float* stage, int len, bool keep, float& c, float* sub_state,
+                              int* sub_done)
+{
+  int serial_left = kMaxSerialSubTiles;
+  for (int u = 0; u < kSubTiles; ++u)
+  {
+    if (sub_state)
+    {
+      sub_state[u] = c;
+      sub_done[u] = 0;
+    }
+    if (u * kSubLen >= len)
+      continue;
+    int s;
+    const int idx = candidate_of(c, sub.g[u], s);
+    if (idx >= 0 && fn_apply(sub.f[idx][u].d0, sub.f[idx][u].d1, s, c))
+      continue;
+    if (serial_left-- == 0)
+      return u;
+    const int i1 = min((u + 1) * kSubLen, len);
+    float cc = c;
+    for (int i = u * kSubLen; i < i1; i += 8)  // sub-tiles start on a multiple of 8: one pad-free run of slots
+    {
+      float v[8];
+      const int slot = stage_slot(i);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        v[k] = (i + k < i1) ? stage[slot + k] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+      {
+        if (i + k < i1)
+          cc = __fadd_rn(cc, v[k]);
+        v[k] = cc;
+      }
+      if (keep)
+      {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (i + k < i1)
+            stage[slot + k] = v[k];
+      }
+    }
+    if (keep)
+      sub_done[u] = 1;
+    c = cc;
+  }
+  return kSubTiles;
+}
+
+__device__ __forceinline__ void stage_tile(const ChainOps& ops, uint64_t tbeg, int len, const TileSubFn* src, float* stage,
+                                           TileSubFn* sh_sub)
+{
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j)
+  {
+    const int i = j * kScanThreads + tid;
+    if (i < len)
+      stage[stage_slot(i)] = ops.operand(tbeg + i);
+  }
+  if (tid < kSubWords)
+    reinterpret_cast<int*>(sh_sub)[tid] = reinterpret_cast<const int*>(src)[tid];
+}
+
+constexpr int kResolveBatch = 256;
+__global__ void __launch_bounds__(kScanThreads)
+    resolve_kernel(ChainOps ops, uint64_t nadd, float start, const TileFn* __restrict__ fns,
+                   const TileSubFn* __restrict__ subs, uint64_t ntiles, float* __restrict__ state_in,
+                   float* __restrict__ total)
+{
+  __shared__ TileFn sh_tiles[kResolveBatch];
+  __shared__ TileSubFn sh_sub;
+  __shared__ float stage[kStageWords];
+  __shared__ unsigned long long sh_t;
+  __shared__ float sh_state;
+  __shared__ int sh_u;
+  const int tid = threadIdx.x;
+  ChainOps quiet = ops;  // the prefix is written by emit_kernel
+  quiet.prefix = nullptr;
+  float c = start;
+  if (tid == 0 && ops.mode == kChainThreshold && ops.prefix != nullptr)
+    ops.prefix[0] = start;
+  for (uint64_t b0 = 0; b0 < ntiles; b0 += kResolveBatch)
+  {
+    const uint64_t bend = min(b0 + (uint64_t)kResolveBatch, ntiles);
+    __syncthreads();
+    for (uint64_t k = b0 + tid; k < bend; k += kScanThreads)
+      sh_tiles[k - b0] = fns[k];
+    __syncthreads();
+    uint64_t t = b0;
+    while (true)
+    {
+      if (tid == 0)
+      {
+        while (t < bend)
+        {
+          state_in[t] = c;
+          const TileFn& f = sh_tiles[t - b0];
+          if (!f.identity)
+          {
+            int s;
+            const int idx = candidate_of(c, f.g, s);
+            if (idx < 0 || !fn_apply(f.d[idx][0], f.d[idx][1], s, c))
+              break;
+          }
+          ++t;
+        }
+        sh_t = t;
+        sh_state = c;
+      }
+      __syncthreads();
+      t = sh_t;
+      c = sh_state;
+      if (t >= bend)
+        break;
+      // ---- tile t needs a closer look: stage it and walk its sub-tiles --------------------------------
+      const uint64_t tbeg = t * kTile;
+      const int len = (int)min(kTile, nadd - tbeg);
+      stage_tile(ops, tbeg, len, subs + t, stage, &sh_sub);
+      __syncthreads();
+      if (tid == 0)
+      {
+        sh_u = walk_sub_tiles(sh_sub, stage, len, false, c, nullptr, nullptr);
+        sh_state = c;
+      }
+      __syncthreads();
+      c = sh_state;
+      const int u = sh_u;
+      if (u < kSubTiles)
+        c = scan_range(quiet, tbeg + (uint64_t)u * kSubLen, tbeg + len, c, stage);  // the guess is of no use here
+      ++t;
+      __syncthreads();
     }
   }
   if (tid == 0 && total != nullptr)
-    total[0] = sh_c;
+    total[0] = c;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+    emit_kernel(ChainOps ops, uint64_t nadd, const TileFn* __restrict__ fns, const TileSubFn* __restrict__ subs,
+                const float* __restrict__ state_in)
+{
+  __shared__ TileSubFn sh_sub;
+  __shared__ float stage[kStageWords];
+  __shared__ float sub_state[kSubTiles];
+  __shared__ int sub_done[kSubTiles];
+  __shared__ int sh_u;
+  __shared__ float sh_state;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t t = blockIdx.x, tbeg = t * kTile;
+  const int len = (int)min(kTile, nadd - tbeg);
+  float c = state_in[t];
+  if (fns[t].identity)
+  {
+    // a tile of +0 operands: every running value is the incoming state
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j)
+    {
+      const int i = j * kScanThreads + tid;
+      if (i < len)
+        ops.emit(tbeg + i, c);
+    }
+    return;
+  }
+  stage_tile(ops, tbeg, len, subs + t, stage, &sh_sub);
+  __syncthreads();
+  if (tid == 0)
+  {
+    sh_u = walk_sub_tiles(sh_sub, stage, len, true, c, sub_state, sub_done);
+    sh_state = c;
+  }
+  __syncthreads();
+  const int u_stop = sh_u;
+  // one warp per sub-tile: the state provably stays inside its binade, so a single integer scan gives all values
+  if (warp < u_stop && warp * kSubLen < len && !sub_done[warp])
+  {
+    const float c0 = sub_state[warp];
+    const int e = (int)((__float_as_uint(c0) >> 23) & 0xFFu) - 127;
+    const int s0 = (int)((__float_as_uint(c0) & 0x7FFFFFu) | 0x800000u);
+    const int i0 = tid * kScanItems;
+    uint32_t code[kScanItems];
+    StepPair run;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j)
+    {
+      code[j] = (i0 + j < len) ? step_code(__float_as_uint(stage[stage_slot(i0 + j)]), e) : 0u;
+      run.push(code[j]);
+    }
+    StepFn incl = run.fn();
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+      StepFn p;
+      p.d0 = __shfl_up_sync(0xffffffffu, incl.d0, o);
+      p.d1 = __shfl_up_sync(0xffffffffu, incl.d1, o);
+      if (lane >= o)
+        incl = step_compose(p, incl);
+    }
+    StepFn excl;
+    excl.d0 = __shfl_up_sync(0xffffffffu, incl.d0, 1);
+    excl.d1 = __shfl_up_sync(0xffffffffu, incl.d1, 1);
+    if (lane == 0)
+      excl = StepFn{ 0, 0 };
+    int s = s0 + ((s0 & 1) ? excl.d1 : excl.d0);
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j)
+    {
+      s = step_apply(s, code[j]);
+      if (i0 + j < len)
+        stage[stage_slot(i0 + j)] = state_value(e, s);
+    }
+  }
+  __syncthreads();
+  const int done_len = min(u_stop * kSubLen, len);
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j)
+  {
+    const int i = j * kScanThreads + tid;
+    if (i < done_len)
+      ops.emit(tbeg + i, stage[stage_slot(i)]);
+  }
+  if (u_stop < kSubTiles)
+    scan_range(ops, tbeg + (uint64_t)u_stop * kSubLen, tbeg + len, sh_state, stage);  // the guess is of no use here
 }
 
 __device__ __forceinline__ bool into_map(const MapDev& map, float x, float y, float z)
@@ -786,46 +1308,87 @@ __global__ void extract_weights_kernel(const float* __restrict__ particles, uint
     dense[i] = particles[7 * i + 6];
 }
 
-// 0: exact parallel scan (default), 1: the serial chain kernel (kept for A/B and as the simple reference)
+// 0: exact scan over many CTAs (default), 1: the serial chain kernel, 2: the exact scan on one CTA.
+// All three give the reference's bits; 1 and 2 are kept for A/B timing and cross-checking.
 static int g_chain_mode = 0;
 void set_chain_mode(int mode)
 {
   g_chain_mode = mode;
 }
-static cudaError_t launch_chain(const float* src, uint32_t stride, uint32_t offset, uint64_t n, int mode, float start,
-                                float inc, float* prefix, float* total, cudaStream_t stream)
+static thread_local uint32_t g_chain_extra = 0;
+uint32_t chain_extra_launches_take()
 {
+  const uint32_t v = g_chain_extra;
+  g_chain_extra = 0;
+  return v;
+}
+uint64_t chain_scratch_floats(uint64_t n)
+{
+  const uint64_t ntiles = (n + kTile - 1) / kTile + 1;
+  const uint64_t meta = ntiles * (sizeof(TileSubFn) + sizeof(TileFn) + sizeof(double) + sizeof(float)) + 256;
+  return ((n + 63) / 64) * 64 + meta / sizeof(float);
+}
+static cudaError_t launch_chain(const float* src, uint32_t stride, uint32_t offset, uint64_t n, int mode, float start,
+                                float inc, float* prefix, float* total, void* meta, cudaStream_t stream)
+{
+  const uint64_t nadd = (mode == kChainThreshold) ? (n > 0 ? n - 1 : 0) : n;
   if (g_chain_mode == 1)
     chain_kernel<<<1, kChainThreads, 0, stream>>>(src, stride, offset, n, mode, start, inc, prefix, total);
-  else
+  else if (g_chain_mode == 2 || meta == nullptr || nadd <= 2 * kTile)
     exact_scan_kernel<<<1, kScanThreads, 0, stream>>>(src, stride, offset, n, mode, start, inc, prefix, total);
+  else
+  {
+    const uint64_t ntiles = (nadd + kTile - 1) / kTile;
+    char* m = reinterpret_cast<char*>(meta);
+    TileSubFn* subs = reinterpret_cast<TileSubFn*>(m);
+    m += ntiles * sizeof(TileSubFn);
+    TileFn* fns = reinterpret_cast<TileFn*>(m);
+    m += ntiles * sizeof(TileFn);
+    double* sums = reinterpret_cast<double*>(m);
+    m += ntiles * sizeof(double);
+    float* state_in = reinterpret_cast<float*>(m);
+    const ChainOps ops{ src, stride, offset, mode, inc, prefix };
+    if (mode != kChainThreshold)
+      tile_sum_kernel<<<(unsigned)ntiles, kScanThreads, 0, stream>>>(ops, nadd, sums);
+    tile_fn_kernel<<<(unsigned)ntiles, kScanThreads, 0, stream>>>(ops, nadd, start, sums, fns, subs);
+    resolve_kernel<<<1, kScanThreads, 0, stream>>>(ops, nadd, start, fns, subs, ntiles, state_in, total);
+    if (prefix != nullptr)
+      emit_kernel<<<(unsigned)ntiles, kScanThreads, 0, stream>>>(ops, nadd, fns, subs, state_in);
+    g_chain_extra += (mode != kChainThreshold ? 2 : 1) + (prefix != nullptr ? 1 : 0);
+  }
   return cudaGetLastError();
+}
+static void* chain_meta(float* dense_scratch, uint64_t n)
+{
+  return dense_scratch ? reinterpret_cast<void*>(dense_scratch + ((n + 63) / 64) * 64) : nullptr;
 }
 
 cudaError_t launch_chain_prefix(const float* particles, uint64_t n, int positive_only, float* prefix, float* total,
                                 float* dense_scratch, cudaStream_t stream)
 {
   const int mode = positive_only ? kChainSumPositive : kChainSum;
-  if (dense_scratch != nullptr && n > 0 && g_chain_mode == 0)
+  if (dense_scratch != nullptr && n > 0 && g_chain_mode != 1)
   {
     extract_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(particles, n, dense_scratch);
-    return launch_chain(dense_scratch, 1, 0, n, mode, 0.f, 0.f, prefix, total, stream);
+    g_chain_extra += 1;
+    return launch_chain(dense_scratch, 1, 0, n, mode, 0.f, 0.f, prefix, total, chain_meta(dense_scratch, n), stream);
   }
-  return launch_chain(particles, 7, 6, n, mode, 0.f, 0.f, prefix, total, stream);
+  return launch_chain(particles, 7, 6, n, mode, 0.f, 0.f, prefix, total, nullptr, stream);
 }
 
-cudaError_t launch_chain_sum_array(const float* v, uint64_t n, float* total, cudaStream_t stream)
+cudaError_t launch_chain_sum_array(const float* v, uint64_t n, float* total, float* scratch, cudaStream_t stream)
 {
-  return launch_chain(v, 1, 0, n, kChainSum, 0.f, 0.f, nullptr, total, stream);
+  return launch_chain(v, 1, 0, n, kChainSum, 0.f, 0.f, nullptr, total, chain_meta(scratch, n), stream);
 }
 
-cudaError_t launch_chain_thresholds(int S, float* thr, cudaStream_t stream)
+cudaError_t launch_chain_thresholds(int S, float* thr, float* scratch, cudaStream_t stream)
 {
   if (S <= 0)
     return cudaSuccess;
   const float inteval = 1.0f / S;  // ParticleFilter.cpp:267 (IEEE f32 divide on the host)
   const float samp0 = 0.5f / S;    // ParticleFilter.cpp:268
-  return launch_chain(nullptr, 1, 0, (uint64_t)S, kChainThreshold, samp0, inteval, thr, nullptr, stream);
+  return launch_chain(nullptr, 1, 0, (uint64_t)S, kChainThreshold, samp0, inteval, thr, nullptr,
+                      chain_meta(scratch, (uint64_t)S), stream);
 }
 
 cudaError_t launch_normalize(const MapDev& map, float* particles, uint64_t n, const float* total, cudaStream_t stream)

@@ -97,8 +97,9 @@ int amcl3d_b200_set_l2_fetch_granularity(int device, int bytes);
 int amcl3d_b200_get_l2_fetch_granularity(int device, int* bytes);
 
 /* How the sequential f32 recurrences of particleNormalize / resample / uniformSample are evaluated
- * (process-wide): 0 (default) the exact parallel binade scan, 1 the plain serial chain kernel.  Both give
- * the reference's bits; the switch exists for A/B timing and cross-checking. */
+ * (process-wide): 0 (default) the exact binade scan spread over many CTAs, 1 the plain serial chain kernel,
+ * 2 the exact binade scan on one CTA.  All give the reference's bits; the switch exists for A/B timing and
+ * cross-checking. */
 int amcl3d_b200_set_chain_mode(int mode);
 
 /* ---- Grid3d (amcl3d/src/Grid3d.{h,cpp}, PointCloudTools.{h,cpp}) ---------------------------- */

@@ -386,11 +386,12 @@ def _weights_cases():
     return {k: v.astype(np.float32) for k, v in cases.items()}
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("name", sorted(_weights_cases()))
 def test_sequential_f32_chains_bit_exact(O, world_c1, pf, name, mode):
-    """The sequential f32 recurrences (weight sum, inclusive prefix) evaluated by the exact parallel binade scan
-    (mode 0) and by the serial chain kernel (mode 1) against the oracle's plain loops, on adversarial inputs."""
+    """The sequential f32 recurrences (weight sum, inclusive prefix) evaluated by the exact binade scan over many
+    CTAs (mode 0), by the serial chain kernel (mode 1) and by the one-CTA scan (mode 2) against the oracle's plain
+    loops, on adversarial inputs."""
     from amcl3d_test_b200 import api
 
     w = _weights_cases()[name]
@@ -407,6 +408,49 @@ def test_sequential_f32_chains_bit_exact(O, world_c1, pf, name, mode):
         assert np.array_equal(bits(pf.p_[:, 6]), bits(ref[:, 6])), name
     finally:
         api.set_chain_mode(0)
+
+
+def _big_weights(name):
+    rng = np.random.RandomState(7)
+    n = 1_000_000
+    if name == "gamma":
+        w = rng.gamma(2.0, 1.0, n)
+    elif name == "equal":
+        w = np.full(n, 1.0 / n)
+    elif name == "leading_zero_tiles":
+        w = np.concatenate([np.zeros(100_000), rng.rand(n - 100_000)])
+    elif name == "zero_gaps":
+        w = rng.rand(n)
+        w[200_000:300_000] = 0
+        w[rng.rand(n) < 0.5] = 0
+    elif name == "outliers":
+        w = np.where(rng.rand(n) < 1e-4, 1e7 * rng.rand(n), rng.rand(n) * 1e-4)
+    elif name == "round_up_bias":  # every add rounds the same way for a whole binade: f32 drifts from the true sum
+        w = np.full(n, 0.75)
+    elif name == "growing":
+        w = np.exp(np.linspace(-30, 8, n))
+    elif name == "stagnation":  # the f32 sum stops at 2^24 while the true sum doubles: every later guess is wrong
+        w = np.ones(2 ** 24 + 3_000_000)
+    else:
+        raise KeyError(name)
+    return w.astype(np.float32)
+
+
+@pytest.mark.parametrize("name", ["gamma", "equal", "leading_zero_tiles", "zero_gaps", "outliers", "round_up_bias",
+                                  "growing", "stagnation"])
+def test_many_tile_chains_bit_exact(O, world_c1, pf, name):
+    """Arrays of dozens to a thousand scan tiles: the per-tile step functions, the serial resolve with its
+    exact redo of missed tiles, and the per-tile prefix emission."""
+    w = _big_weights(name)
+    P = np.zeros((w.size, 7), np.float32)
+    P[:, :3] = np.array([10, 10, 1.0], np.float32)
+    P[:, 6] = w
+    pf.p_ = P
+    assert np.array_equal(bits(pf.prefix()), bits(O.prefix(P))), name
+    ref = P.copy()
+    wtp = O.normalize(world_c1["map"], ref)
+    assert bits(pf.particleNormalize()) == bits(wtp), name
+    assert np.array_equal(bits(pf.p_[:, 6]), bits(ref[:, 6])), name
 
 
 @pytest.mark.parametrize("S", [1, 2, 3, 600, 8191, 8192, 8193, 100_000, 1_000_003])

@@ -1255,15 +1255,21 @@ __global__ void __launch_bounds__(kRedThreads) mean_pass1(const float* __restric
     part[blockIdx.x * 7 + threadIdx.x] = v;
   }
 }
-__global__ void mean_pass2(const double* __restrict__ part, int nb, float* __restrict__ out7)
+// one warp per component: lane-strided partial sums in a fixed order, then a fixed shuffle tree (deterministic)
+__global__ void __launch_bounds__(7 * 32) mean_pass2(const double* __restrict__ part, int nb, float* __restrict__ out7)
 {
-  const int c = threadIdx.x;
-  if (c >= 7)
-    return;
+  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double v = 0;
-  for (int k = 0; k < nb; ++k)
+  for (int k = lane; k < nb; k += 32)
     v = (c == 6) ? fmax(v, part[k * 7 + c]) : v + part[k * 7 + c];
-  out7[c] = (float)v;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    const double t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = (c == 6) ? fmax(v, t) : v + t;
+  }
+  if (lane == 0)
+    out7[c] = (float)v;
 }
 
 // ParticleFilter.cpp:98-111 with the ranGaussian results supplied by the caller
@@ -1465,7 +1471,7 @@ cudaError_t launch_mean(const float* particles, uint64_t n, int exact, float* ou
   if (nb > kRedBlocks)
     nb = kRedBlocks;
   mean_pass1<<<nb, kRedThreads, 0, stream>>>(particles, n, part);
-  mean_pass2<<<1, 32, 0, stream>>>(part, nb, out7);
+  mean_pass2<<<1, 7 * 32, 0, stream>>>(part, nb, out7);
   return cudaGetLastError();
 }
 

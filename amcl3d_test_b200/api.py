@@ -221,6 +221,28 @@ class ParticleFilter:
         npts = cloud.shape[0]
         check(self._L.amcl3d_b200_pf_set_cloud(self._h, cloud.ctypes.data if npts else None, cloud.shape[1] if cloud.ndim == 2 else 3, npts))
 
+    def set_cloud_downsampled(self, cloud, leaf, intensity_offset=None, skip_nonfinite=False) -> int:
+        """ds_.filter() of amcl3d.cpp:51-52 (pcl::VoxelGrid centroid filter, leaf = voxel_size) on the device; the
+        result becomes the cloud of the next update().  Returns the number of points now set."""
+        cloud = _f32(cloud)
+        npts, stride = cloud.shape[0], cloud.shape[1]
+        if intensity_offset is None:
+            intensity_offset = 4 if stride >= 8 else (3 if stride >= 4 else -1)
+        out = C.c_uint32(0)
+        check(self._L.amcl3d_b200_pf_set_cloud_downsampled(self._h, cloud.ctypes.data if npts else None, stride,
+                                                           int(intensity_offset), npts, float(leaf), int(skip_nonfinite),
+                                                           C.byref(out)))
+        return int(out.value)
+
+    def get_cloud(self) -> np.ndarray:
+        """The cloud currently set, (npts, 4) = x y z intensity."""
+        n = C.c_uint32(0)
+        check(self._L.amcl3d_b200_pf_get_cloud(self._h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 4), np.float32)
+        if n.value:
+            check(self._L.amcl3d_b200_pf_get_cloud(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
     def set_cloud_device(self, ptr: int, stride: int, npts: int):
         check(self._L.amcl3d_b200_pf_set_cloud_device(self._h, C.c_void_p(ptr), stride, npts))
 

@@ -24,7 +24,8 @@ SYMBOLS = [
     "amcl3d_b200_pf_set_two_phase",
     "amcl3d_b200_pf_set_particles", "amcl3d_b200_pf_get_particles", "amcl3d_b200_pf_size",
     "amcl3d_b200_pf_bind_device", "amcl3d_b200_pf_device_ptr", "amcl3d_b200_pf_set_cloud",
-    "amcl3d_b200_pf_set_cloud_device", "amcl3d_b200_pf_update", "amcl3d_b200_pf_update_cloud",
+    "amcl3d_b200_pf_set_cloud_device", "amcl3d_b200_pf_set_cloud_downsampled", "amcl3d_b200_pf_get_cloud",
+    "amcl3d_b200_pf_update", "amcl3d_b200_pf_update_cloud",
     "amcl3d_b200_pf_update_split", "amcl3d_b200_pf_fuse_range",
     "amcl3d_b200_pf_normalize", "amcl3d_b200_pf_scale_by_max", "amcl3d_b200_pf_resample",
     "amcl3d_b200_pf_uniform_sample", "amcl3d_b200_pf_mean", "amcl3d_b200_pf_best", "amcl3d_b200_pf_predict",
@@ -105,6 +106,8 @@ def load():
         "amcl3d_b200_pf_device_ptr": (i, [vp, P(vp), P(u64)]),
         "amcl3d_b200_pf_set_cloud": (i, [vp, vp, u32, u32]),
         "amcl3d_b200_pf_set_cloud_device": (i, [vp, vp, u32, u32]),
+        "amcl3d_b200_pf_set_cloud_downsampled": (i, [vp, vp, u32, i, u32, f32, i, P(u32)]),
+        "amcl3d_b200_pf_get_cloud": (i, [vp, vp, u32, P(u32)]),
         "amcl3d_b200_pf_update": (i, [vp, P(Beacon), u32, f32, f32, P(u64)]),
         "amcl3d_b200_pf_update_cloud": (i, [vp, vp, u32, u32]),
         "amcl3d_b200_pf_update_split": (i, [vp, P(Beacon), u32, f32, vp, P(u64)]),

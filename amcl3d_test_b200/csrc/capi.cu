@@ -102,6 +102,12 @@ struct amcl3d_b200_pf_s
   uint32_t npts = 0, npad = 0;
   float* d_stage = nullptr;
   uint64_t stage_cap = 0;
+  // input downsample (voxelfilter.cu): centroids (x y z intensity) + workspace
+  float4* d_filtered = nullptr;
+  uint64_t filtered_cap = 0;
+  char* d_vf_scratch = nullptr;
+  uint64_t vf_scratch_cap = 0;
+  bool filtered_valid = false;
   // two-phase sweep: Morton-sorted cloud, sort scratch, staged codes
   float4* d_sorted = nullptr;
   uint64_t sorted_cap = 0;
@@ -717,6 +723,8 @@ int amcl3d_b200_pf_destroy(amcl3d_b200_pf_t pf)
   cudaFree(pf->d_thr);
   cudaFree(pf->d_wr);
   cudaFree(pf->d_dense);
+  cudaFree(pf->d_filtered);
+  cudaFree(pf->d_vf_scratch);
   cudaFree(pf->d_idx);
   cudaFree(pf->d_noise);
   cudaFree(pf->d_scalars);
@@ -846,6 +854,7 @@ static int set_cloud_common(amcl3d_b200_pf_t pf, const float* d_src, uint32_t st
   }
   pf->npts = npts;
   pf->npad = npad;
+  pf->filtered_valid = false;
   return AMCL3D_B200_OK;
 }
 
@@ -873,6 +882,65 @@ int amcl3d_b200_pf_set_cloud_device(amcl3d_b200_pf_t pf, const void* d_cloud, ui
   if (int rc = use_device(pf->grid->device))
     return rc;
   return set_cloud_common(pf, reinterpret_cast<const float*>(d_cloud), stride, npts);
+}
+
+int amcl3d_b200_pf_set_cloud_downsampled(amcl3d_b200_pf_t pf, const float* cloud, uint32_t stride, int intensity_offset,
+                                         uint32_t npts, float leaf, int skip_nonfinite, uint32_t* npts_out)
+{
+  if (!pf || (npts && !cloud) || stride < 3 || intensity_offset >= (int)stride || !(leaf > 0.f))
+    return fail(AMCL3D_B200_ERR_ARG, "bad cloud / leaf size");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  const uint64_t floats = (uint64_t)npts * stride;
+  CU(ensure(pf->d_stage, pf->stage_cap, floats));
+  CU(ensure(pf->d_filtered, pf->filtered_cap, (uint64_t)(npts ? npts : 1)));
+  const size_t need = voxel_filter_scratch_bytes(npts);
+  CU(ensure(pf->d_vf_scratch, pf->vf_scratch_cap, need));
+  if (floats)
+    CU(cudaMemcpyAsync(pf->d_stage, cloud, sizeof(float) * floats, cudaMemcpyHostToDevice, pf->stream));
+  int64_t cells = 0;
+  uint32_t launched = 0;
+  {
+    Timed t(pf);
+    CU(run_voxel_filter(pf->d_stage, stride, intensity_offset, npts, leaf, skip_nonfinite, pf->d_filtered,
+                        pf->d_vf_scratch, need, &cells, &launched, pf->stream));
+    pf->launches += launched;
+  }
+  int rc;
+  if (cells < 0)  // PCL: "Leaf size is too small for the input dataset" -> the input passes through
+    rc = set_cloud_common(pf, pf->d_stage, stride, npts);
+  else
+  {
+    rc = set_cloud_common(pf, reinterpret_cast<const float*>(pf->d_filtered), 4, (uint32_t)cells);
+    pf->filtered_valid = (rc == AMCL3D_B200_OK);
+  }
+  if (rc)
+    return rc;
+  CU(cudaStreamSynchronize(pf->stream));
+  if (npts_out)
+    *npts_out = pf->npts;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_get_cloud(amcl3d_b200_pf_t pf, float* xyzi, uint32_t cap, uint32_t* npts)
+{
+  if (!pf || (!xyzi && cap))
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  if (npts)
+    *npts = pf->npts;
+  if (!xyzi)
+    return AMCL3D_B200_OK;
+  if (cap < pf->npts)
+    return fail(AMCL3D_B200_ERR_ARG, "output too small");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  if (pf->npts)
+  {
+    const float4* src = pf->filtered_valid ? pf->d_filtered : pf->d_cloud;  // d_cloud: x y z 0
+    CU(cudaMemcpyAsync(xyzi, src, sizeof(float4) * pf->npts, cudaMemcpyDeviceToHost, pf->stream));
+    CU(cudaStreamSynchronize(pf->stream));
+  }
+  return AMCL3D_B200_OK;
 }
 
 static int fuse_range_async(amcl3d_b200_pf_t pf, const float* d_wr, float alpha)

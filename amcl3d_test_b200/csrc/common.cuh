@@ -127,6 +127,12 @@ cudaError_t launch_pack_cloud(const float* src, uint32_t stride, uint32_t npts, 
 cudaError_t launch_gather_bench(const float* cells, uint64_t window, uint32_t blocks, uint32_t iters, int coherent,
                                 float* sink, cudaStream_t stream);
 
+// ---- input downsample (voxelfilter.cu) ----------------------------------------------------------
+size_t voxel_filter_scratch_bytes(uint32_t n);
+cudaError_t run_voxel_filter(const float* d_pts, uint32_t stride, int ioff, uint32_t n, float leaf, int skip_nonfinite,
+                             float4* d_out, void* scratch, size_t scratch_bytes, int64_t* cells, uint32_t* launches,
+                             cudaStream_t stream);
+
 // ---- particle-set ops (pfops.cu) --------------------------------------------------------------
 // serial f32 chain over w (stride 7 floats): prefix[i] (nullable) = sequential inclusive prefix starting
 // from 0; positive_only: add only w > 0 (particleNormalize).  total[0] receives the final value.

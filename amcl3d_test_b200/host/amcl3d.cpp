@@ -1,6 +1,7 @@
 // amcl3d.cpp -- host shim of the localisation steps around the weighting path over the C-ABI.
 #include "amcl3d/amcl3d.h"
 
+#include <cstddef>
 #include <limits>
 #include <stdexcept>
 #include <string>
@@ -75,6 +76,43 @@ void MonteCarloLocalization::RelocPose(const int num_particles, const float x_in
                             localization_params_.init_pitch_dev_, localization_params_.init_yaw_dev_);
   setParticleNum(localization_params_.max_particle_num_global, localization_params_.min_particle_num_global);
   global_loc_done_ = false;
+}
+
+int MonteCarloLocalization::downsampleInput(const pcl::PointCloud<PointType>::Ptr& input_cloud, pcl::PointCloud<PointType>* cloud_ds)
+{
+  const uint32_t n = input_cloud ? static_cast<uint32_t>(input_cloud->size()) : 0u;
+  constexpr uint32_t stride = sizeof(PointType) / sizeof(float);
+  const int ioff = static_cast<int>(offsetof(PointType, intensity) / sizeof(float));
+  uint32_t kept = 0;
+  check(amcl3d_b200_pf_set_cloud_downsampled(handle(), n ? &input_cloud->points[0].x : nullptr, stride, ioff, n, voxel_size_,
+                                             (input_cloud && !input_cloud->is_dense) ? 1 : 0, &kept),
+        "downsampleInput");
+  if (cloud_ds)
+  {
+    std::vector<float> xyzi(static_cast<size_t>(kept) * 4);
+    check(amcl3d_b200_pf_get_cloud(handle(), xyzi.data(), kept, &kept), "download filtered cloud");
+    cloud_ds->points.resize(kept);
+    for (uint32_t i = 0; i < kept; ++i)
+    {
+      PointType& q = cloud_ds->points[i];
+      q.x = xyzi[4 * i];
+      q.y = xyzi[4 * i + 1];
+      q.z = xyzi[4 * i + 2];
+      q.intensity = xyzi[4 * i + 3];
+    }
+    cloud_ds->width = kept;
+    cloud_ds->height = 1;
+    cloud_ds->is_dense = true;
+  }
+  return static_cast<int>(kept);
+}
+
+void MonteCarloLocalization::updateDownsampled()
+{
+  check(amcl3d_b200_pf_set_particles(handle(), p_.empty() ? nullptr : &p_[0].x, p_.size()), "upload p_");
+  check(amcl3d_b200_pf_update(handle(), nullptr, 0, 1.f, 1.f, nullptr), "update");
+  uint64_t n = 0;
+  check(amcl3d_b200_pf_get_particles(handle(), p_.empty() ? nullptr : &p_[0].x, p_.size(), &n), "download p_");
 }
 
 void MonteCarloLocalization::PFMove(const Particle& d, const Particle& noise)

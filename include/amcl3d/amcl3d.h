@@ -29,6 +29,15 @@ public:
    *  One C-ABI call; the particle set stays on the device between the four steps. */
   void PFResample(const bool weight_multiply = false);
 
+  /*! Reference: ds_.setLeafSize(voxel_size x3) (amcl3d.cpp:37). */
+  void setVoxelSize(const double voxel_size) { voxel_size_ = static_cast<float>(voxel_size); }
+  /*! Reference: ds_.setInputCloud(input_cloud); ds_.filter(*cloud_ds) (amcl3d.cpp:51-52) -- pcl::VoxelGrid's
+   *  centroid filter on the device.  The filtered cloud stays resident as the input of updateDownsampled();
+   *  cloud_ds (optional) receives a host copy.  Returns the number of points kept. */
+  int downsampleInput(const pcl::PointCloud<PointType>::Ptr& input_cloud, pcl::PointCloud<PointType>* cloud_ds = nullptr);
+  /*! ParticleFilter::update on the cloud downsampleInput left on the device (no second upload). */
+  void updateDownsampled();
+
   std::vector<Particle> getParticle() { return p_; }
   const bool globalLocalizationDone() const { return global_loc_done_; }
 
@@ -41,6 +50,7 @@ public:
 
 private:
   std::vector<float> keyposeArray() const;
+  float voxel_size_{ 0.1f };
   bool global_loc_done_{ false };
   Particle set_pose_;
 };

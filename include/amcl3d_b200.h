@@ -171,6 +171,18 @@ int amcl3d_b200_pf_device_ptr(amcl3d_b200_pf_t pf, void** d_aos7, uint64_t* n);
 int amcl3d_b200_pf_set_cloud(amcl3d_b200_pf_t pf, const float* cloud, uint32_t stride, uint32_t npts);
 /* same from a DEVICE buffer (no host round trip) */
 int amcl3d_b200_pf_set_cloud_device(amcl3d_b200_pf_t pf, const void* d_cloud, uint32_t stride, uint32_t npts);
+/* The input downsample in front of update(): ds_.setLeafSize(voxel_size x3) + ds_.filter(), amcl3d.cpp:37,51-52
+ * (pcl::VoxelGrid<PointXYZI> centroid filter with default settings, PCL filters/impl/voxel_grid.hpp) -- the raw
+ * cloud goes H2D once, is reduced to one centroid per occupied leaf on the device and becomes the cloud of the
+ * following update() without a host round trip.  intensity_offset: float index of the intensity inside a point
+ * (4 for pcl::PointXYZI's 8-float layout, 3 for packed xyzi, < 0: none).  skip_nonfinite = !cloud.is_dense.
+ * Cell set, order and counts are exact; centroids are f32 sums in input order / (float)count (PCL's order inside
+ * a cell is that of an unstable sort, so a PCL run can differ in the last ulp).  If PCL's "leaf size too small"
+ * guard trips the input passes through unchanged, as in PCL.  npts_out: points now set. */
+int amcl3d_b200_pf_set_cloud_downsampled(amcl3d_b200_pf_t pf, const float* cloud, uint32_t stride, int intensity_offset,
+                                         uint32_t npts, float leaf, int skip_nonfinite, uint32_t* npts_out);
+/* the cloud currently set, 4 floats per point (x y z intensity; intensity 0 unless it came from the downsample) */
+int amcl3d_b200_pf_get_cloud(amcl3d_b200_pf_t pf, float* xyzi, uint32_t cap, uint32_t* npts);
 
 /* ParticleFilter::update(cloud) (ParticleFilter.cpp:114-139) on the cloud set above: w = 0 outside the
  * map, else computeCloudWeight.  With nb > 0 the range-only beacon weight (row R of SURVEY 8(a);

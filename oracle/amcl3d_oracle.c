@@ -449,6 +449,89 @@ int orc_pf_resample_step(const orc_map* m, orc_particle* p, uint64_t n, int weig
   return sample_num;
 }
 
+/* amcl3d/src/amcl3d.cpp:37,51-52 -> pcl::VoxelGrid<PointXYZI>::applyFilter (PCL filters/impl/voxel_grid.hpp) */
+static int cmp_u64(const void* a, const void* b)
+{
+  const uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;
+  return (x > y) - (x < y);
+}
+int64_t orc_voxel_filter(const float* pts, uint32_t stride, int ioff, uint64_t n, float leaf, int skip_nonfinite, float* out)
+{
+  const float inv = 1.0f / leaf; /* inverse_leaf_size_ = Array4f::Ones() / leaf_size_ */
+  float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+  uint64_t valid = 0;
+  for (uint64_t i = 0; i < n; ++i) /* getMinMax3D */
+  {
+    const float* p = pts + i * stride;
+    if (skip_nonfinite && (!isfinite(p[0]) || !isfinite(p[1]) || !isfinite(p[2])))
+      continue;
+    ++valid;
+    for (int a = 0; a < 3; ++a)
+    {
+      if (p[a] < lo[a])
+        lo[a] = p[a];
+      if (p[a] > hi[a])
+        hi[a] = p[a];
+    }
+  }
+  if (valid == 0)
+    return 0;
+  const int64_t dx = (int64_t)((hi[0] - lo[0]) * inv) + 1;
+  const int64_t dy = (int64_t)((hi[1] - lo[1]) * inv) + 1;
+  const int64_t dz = (int64_t)((hi[2] - lo[2]) * inv) + 1;
+  if (dx * dy * dz > (int64_t)INT_MAX)
+    return -1;
+  int min_b[3], div_b[3];
+  for (int a = 0; a < 3; ++a)
+  {
+    min_b[a] = (int)floorf(lo[a] * inv);
+    div_b[a] = (int)floorf(hi[a] * inv) - min_b[a] + 1;
+  }
+  const int mul1 = div_b[0], mul2 = div_b[0] * div_b[1];
+  uint64_t* keyed = (uint64_t*)malloc(sizeof(uint64_t) * (valid ? valid : 1));
+  uint64_t m = 0;
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    const float* p = pts + i * stride;
+    if (skip_nonfinite && (!isfinite(p[0]) || !isfinite(p[1]) || !isfinite(p[2])))
+      continue;
+    const int ijk0 = (int)(floorf(p[0] * inv) - (float)min_b[0]);
+    const int ijk1 = (int)(floorf(p[1] * inv) - (float)min_b[1]);
+    const int ijk2 = (int)(floorf(p[2] * inv) - (float)min_b[2]);
+    const int idx = ijk0 + ijk1 * mul1 + ijk2 * mul2;
+    keyed[m++] = ((uint64_t)(unsigned int)idx << 32) | (uint64_t)(uint32_t)i; /* input order inside a cell */
+  }
+  qsort(keyed, m, sizeof(uint64_t), cmp_u64);
+  int64_t cells = 0;
+  uint64_t index = 0;
+  while (index < m)
+  {
+    uint64_t i = index + 1;
+    while (i < m && (keyed[i] >> 32) == (keyed[index] >> 32))
+      ++i;
+    float s[4] = { 0.f, 0.f, 0.f, 0.f };
+    for (uint64_t li = index; li < i; ++li)
+    {
+      const float* p = pts + (keyed[li] & 0xFFFFFFFFu) * stride;
+      s[0] += p[0];
+      s[1] += p[1];
+      s[2] += p[2];
+      if (ioff >= 0)
+        s[3] += p[ioff];
+    }
+    const float cnt = (float)(i - index);
+    float* o = out + 4 * cells;
+    o[0] = s[0] / cnt;
+    o[1] = s[1] / cnt;
+    o[2] = s[2] / cnt;
+    o[3] = s[3] / cnt;
+    ++cells;
+    index = i;
+  }
+  free(keyed);
+  return cells;
+}
+
 /* amcl3d/src/ParticleFilter.cpp:198-216 */
 void orc_mean(const orc_particle* p, uint64_t n, orc_particle* mean)
 {

@@ -109,6 +109,18 @@ float orc_update_sample_height(orc_particle* p, uint64_t n, const float* keypose
 /* MonteCarloLocalization::PFResample, amcl3d.cpp:192-203; out must hold max_resamp particles; returns new size */
 int orc_pf_resample_step(const orc_map* m, orc_particle* p, uint64_t n, int weight_multiply, int min_resamp, int max_resamp,
                          const float* keyposes, uint64_t nk, orc_particle* out);
+/* The input downsample in front of update(): ds_.setLeafSize(voxel_size x3) / ds_.filter(), amcl3d.cpp:37,51-52.
+ * pcl::VoxelGrid is third-party and absent from /root/reference (PCL as shipped with ROS Kinetic, 1.7.2; same
+ * arithmetic in 1.8): this restates the published applyFilter of filters/impl/voxel_grid.hpp for PointXYZI with
+ * default settings -- f32 bounds, inverse leaf 1.0f/leaf, ijk = (int)(floorf(v*inv) - (float)min_b),
+ * idx = ijk.(1, div_x, div_x*div_y), cells in increasing idx, centroid = f32 running sums / (float)count.
+ * PCL orders the points of one cell by an unstable std::sort on idx alone; here they are taken in input order
+ * (the one deterministic choice), so centroids can differ from a PCL run in the last ulp.  PARITY UNPINNED for
+ * this row: no PCL here and no reference test covers it.
+ * pts: n points, `stride` floats apart, x y z first, intensity at float `ioff` (ioff < 0: none, output 0).
+ * skip_nonfinite = !is_dense.  out: 4 floats per cell (x y z intensity), capacity n.  Returns the cell count, or
+ * -1 when PCL's "leaf size too small" guard trips (PCL then passes the input through unchanged). */
+int64_t orc_voxel_filter(const float* pts, uint32_t stride, int ioff, uint64_t n, float leaf, int skip_nonfinite, float* out);
 /* sequential f32 inclusive prefix (ParticleFilter.cpp:259-264) -- exposed for the scan tests */
 void orc_prefix(const orc_particle* p, uint64_t n, float* out);
 

@@ -144,6 +144,7 @@ def lib():
         "orc_prefix": (None, [vp, C.c_uint64, f32p]),
         "orc_compute_sample_num": (C.c_int, [vp, C.c_uint64, C.c_int, C.c_int, C.c_int]),
         "orc_update_sample_height": (C.c_float, [vp, C.c_uint64, f32p, C.c_uint64]),
+        "orc_voxel_filter": (C.c_int64, [f32p, C.c_uint32, C.c_int, C.c_uint64, C.c_float, C.c_int, f32p]),
         "orc_pf_resample_step": (C.c_int, [mp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int, f32p, C.c_uint64, vp]),
         "orc_reloc_pose": (None, [vp, C.c_uint64, f32p, f32p, f32p, vp]),
         "orc_predict": (None, [vp, C.c_uint64, f64p, f32p]),
@@ -271,6 +272,15 @@ def pf_resample_step(m: Map, p, weight_multiply, min_resamp, max_resamp, keypose
     out = np.zeros((max(max_resamp, 1), 7), np.float32)
     n = lib().orc_pf_resample_step(C.byref(m.c), p.ctypes.data, p.shape[0], int(weight_multiply), min_resamp, max_resamp, _fp(kp), kp.shape[0], out.ctypes.data)
     return out[:n].copy()
+
+
+def voxel_filter(pts, leaf, ioff=3, skip_nonfinite=False):
+    """pcl::VoxelGrid centroid filter (amcl3d.cpp:37,51-52); pts (n, stride>=3) f32 -> (cells, 4) or None when
+    PCL's leaf-too-small guard passes the input through."""
+    pts = np.ascontiguousarray(pts, np.float32)
+    out = np.zeros((max(pts.shape[0], 1), 4), np.float32)
+    k = lib().orc_voxel_filter(_fp(pts), pts.shape[1], int(ioff), pts.shape[0], float(leaf), int(skip_nonfinite), _fp(out))
+    return None if k < 0 else out[:k].copy()
 
 
 def reloc_pose(n, init, dev, noise):
@@ -428,6 +438,7 @@ def ref():
         "ref_mcl_compute_sample_num": (C.c_int, [vp, C.c_int]),
         "ref_mcl_update_sample_height": (None, [vp]),
         "ref_mcl_pf_resample": (None, [vp, C.c_int]),
+        "ref_mcl_downsample": (C.c_uint64, [vp, f32p, C.c_uint64, C.c_double, C.c_int, f32p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -575,6 +586,12 @@ class RefMCL:
 
     def pf_resample(self, weight_multiply):
         ref().ref_mcl_pf_resample(self.h, int(weight_multiply))
+
+    def downsample(self, xyzi, voxel_size, is_dense=True):
+        xyzi = _as_f32(xyzi, 4)
+        out = np.zeros((max(xyzi.shape[0], 1), 4), np.float32)
+        k = ref().ref_mcl_downsample(self.h, _fp(xyzi), xyzi.shape[0], float(voxel_size), int(is_dense), _fp(out))
+        return out[:k].copy()
 
 
 def ref_compute_grid(xyz, resol, sensor_dev, which=0, bounds=None):

@@ -337,6 +337,37 @@ void ref_mcl_pf_resample(void* mv, int weight_multiply)
   static_cast<amcl3d::MonteCarloLocalization*>(mv)->PFResample(weight_multiply != 0);
 }
 
+// the input downsample exactly as amcl3d.cpp:37,51-52 drives it: the MonteCarloLocalization's own ds_ member
+// (private, reached like the other members), setLeafSize(voxel_size x3), setInputCloud, filter.  The filter
+// class itself is the stand-in of oracle/stubs (PCL is absent), so this pins the call pattern, not PCL.
+uint64_t ref_mcl_downsample(void* mv, const float* xyzi, uint64_t n, double voxel_size, int is_dense, float* out4)
+{
+  auto* m = static_cast<amcl3d::MonteCarloLocalization*>(mv);
+  pcl::PointCloud<PointType>::Ptr in(new pcl::PointCloud<PointType>());
+  in->points.resize(n);
+  for (uint64_t i = 0; i < n; ++i)
+  {
+    in->points[i].x = xyzi[4 * i];
+    in->points[i].y = xyzi[4 * i + 1];
+    in->points[i].z = xyzi[4 * i + 2];
+    in->points[i].intensity = xyzi[4 * i + 3];
+  }
+  in->width = (uint32_t)n;
+  in->is_dense = is_dense != 0;
+  m->ds_.setLeafSize(voxel_size, voxel_size, voxel_size);
+  m->ds_.setInputCloud(in);
+  pcl::PointCloud<PointType> out;
+  m->ds_.filter(out);
+  for (size_t i = 0; i < out.points.size(); ++i)
+  {
+    out4[4 * i] = out.points[i].x;
+    out4[4 * i + 1] = out.points[i].y;
+    out4[4 * i + 2] = out.points[i].z;
+    out4[4 * i + 3] = out.points[i].intensity;
+  }
+  return out.points.size();
+}
+
 // which trig overload did `const auto sr = sin(roll)` (Grid3d.cpp:240) bind to in THIS build?
 // Returns 8 for double, 4 for float.  Mirrors the same unqualified call with the same headers visible.
 int ref_trig_width()

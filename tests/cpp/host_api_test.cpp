@@ -244,6 +244,26 @@ int main(int argc, char** argv)
     PointType h = mcl.getMapHeight(P[0].x, P[0].y);
     const float hv[3] = { h.x, h.y, h.z };
     dump("mcl_map_height", hv, 1, 3);
+    // the input downsample (amcl3d.cpp:37,51-52) and the update on the resident filtered cloud
+    mcl.setVoxelSize(0.3);
+    pcl::PointCloud<PointType> cloud_ds;
+    const int kept = mcl.downsampleInput(cloud, &cloud_ds);
+    if (kept <= 0 || kept >= (int)cloud->size() || (int)cloud_ds.size() != kept)
+      return 6;
+    {
+      std::vector<float> xyzi(cloud_ds.size() * 4);
+      for (size_t i = 0; i < cloud_ds.size(); ++i)
+      {
+        xyzi[4 * i] = cloud_ds.points[i].x;
+        xyzi[4 * i + 1] = cloud_ds.points[i].y;
+        xyzi[4 * i + 2] = cloud_ds.points[i].z;
+        xyzi[4 * i + 3] = cloud_ds.points[i].intensity;
+      }
+      dump("mcl_cloud_ds", xyzi.data(), cloud_ds.size(), 4);
+    }
+    mcl.p_ = P;
+    mcl.updateDownsampled();
+    dump_particles("mcl_after_update_ds", mcl.p_);
   }
   g_out.close();
   std::printf("host_api_test ok\n");

@@ -615,3 +615,65 @@ def test_mcl_resample_step(O, world_c1, pf, kind, spread):
     # empty set: computeBoundary gives zeros -> widths 1 -> one cell, zero count -> min_resamp
     pf.p_ = np.zeros((0, 7), np.float32)
     assert pf.computeSampleNum(3, 150, 800) == O.compute_sample_num(np.zeros((0, 7), np.float32), 3, 150, 800) == 150
+
+
+def _raw_scan(sm, n, seed):
+    """A raw (un-downsampled) sensor frame: map points near the pose, jittered, PointXYZI layout (8 floats)."""
+    from amcl3d_test_b200 import synth
+
+    rng = np.random.RandomState(seed)
+    base = synth.make_cloud(sm, min(n, 4000), 9.0)
+    pts = base[rng.randint(0, base.shape[0], n)] + rng.normal(0, 0.03, (n, 3)).astype(np.float32)
+    raw = np.zeros((n, 8), np.float32)
+    raw[:, :3] = pts
+    raw[:, 4] = rng.rand(n).astype(np.float32) * 255
+    return raw
+
+
+@pytest.mark.parametrize("leaf", [0.05, 0.1, 0.3, 1.0])
+def test_input_downsample_matches_checker(O, world_c1, pf, leaf):
+    """ds_.filter() (amcl3d.cpp:51-52): cell set, order, counts and centroids of the device voxel filter against the
+    CPU restatement of pcl::VoxelGrid -- bit for bit -- and the filtered cloud feeds update() without a round trip."""
+    w = world_c1
+    raw = _raw_scan(w["synth"], 60_000, 11)
+    ref = O.voxel_filter(raw, leaf, ioff=4)
+    n = pf.set_cloud_downsampled(raw, leaf)
+    got = pf.get_cloud()
+    assert n == ref.shape[0] and 0 < n < raw.shape[0]
+    assert np.array_equal(bits(got), bits(ref))
+    # update() on the resident filtered cloud == update() on the checker's filtered cloud
+    pf.p_ = w["T"]
+    pf.update()
+    refw = O.update(w["map"], O.particles(w["T"]), ref[:, :3].copy())
+    assert np.array_equal(bits(pf.p_[:, 6]), bits(refw[:, 6]))
+
+
+def test_input_downsample_edge_cases(O, world_c1, pf):
+    rng = np.random.RandomState(3)
+    # non-finite points are skipped when the cloud is not dense
+    raw = _raw_scan(world_c1["synth"], 5000, 5)
+    raw[::7, 0] = np.nan
+    raw[3::11, 2] = np.inf
+    ref = O.voxel_filter(raw, 0.2, ioff=4, skip_nonfinite=True)
+    n = pf.set_cloud_downsampled(raw, 0.2, skip_nonfinite=True)
+    assert n == ref.shape[0] and np.array_equal(bits(pf.get_cloud()), bits(ref))
+    # packed xyzi (stride 4), xyz only (stride 3), a single point, an empty cloud
+    for arr, ioff in ((np.ascontiguousarray(raw[1:2000:3, [0, 1, 2, 4]]), 3), (np.ascontiguousarray(raw[1:2000:3, :3]), -1)):
+        arr = arr[np.isfinite(arr).all(1)]
+        ref = O.voxel_filter(arr, 0.15, ioff=ioff)
+        assert pf.set_cloud_downsampled(arr, 0.15, intensity_offset=ioff) == ref.shape[0]
+        assert np.array_equal(bits(pf.get_cloud()), bits(ref))
+    one = np.array([[1.5, -2.25, 0.75, 9.0]], np.float32)
+    assert pf.set_cloud_downsampled(one, 0.1, intensity_offset=3) == 1
+    assert np.array_equal(bits(pf.get_cloud()), bits(one))
+    assert pf.set_cloud_downsampled(np.zeros((0, 4), np.float32), 0.1) == 0 and pf.get_cloud().shape == (0, 4)
+    # PCL's guard: a leaf far too small for the extent passes the input through unchanged
+    wide = (rng.rand(1000, 4) * [4000, 4000, 400, 1]).astype(np.float32)
+    assert O.voxel_filter(wide, 0.01) is None
+    assert pf.set_cloud_downsampled(wide, 0.01, intensity_offset=3) == 1000
+    assert np.array_equal(bits(pf.get_cloud()[:, :3]), bits(wide[:, :3]))
+    # many points per cell, negative coordinates
+    dense = (rng.normal(0, 0.5, (200_000, 4))).astype(np.float32)
+    ref = O.voxel_filter(dense, 0.25, ioff=3)
+    assert pf.set_cloud_downsampled(dense, 0.25, intensity_offset=3) == ref.shape[0]
+    assert np.array_equal(bits(pf.get_cloud()), bits(ref))

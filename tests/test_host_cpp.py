@@ -27,6 +27,7 @@ def test_host_library_builds_and_exports_the_reference_surface():
         "amcl3d::MonteCarloLocalization::PFResample(bool)", "amcl3d::MonteCarloLocalization::computeSampleNum(int)",
         "amcl3d::MonteCarloLocalization::updateSampleHeight()", "amcl3d::MonteCarloLocalization::RelocPose(",
         "amcl3d::MonteCarloLocalization::PFMove(", "amcl3d::MonteCarloLocalization::getMapHeight(",
+        "amcl3d::MonteCarloLocalization::downsampleInput(", "amcl3d::MonteCarloLocalization::updateDownsampled()",
     ]:
         assert sym in out, sym
 
@@ -125,6 +126,11 @@ def test_cpp_classes_match_the_oracle(O, tmp_path):
     O.update_sample_height(Z, kp)
     assert np.array_equal(bits(d["mcl_after_height"]), bits(Z))
     assert np.array_equal(bits(d["mcl_after_pfresample"]), bits(O.pf_resample_step(m, W.copy(), 1, 150, 400, kp)))
+    # input downsample through the C++ class (to_cloud() of the driver sets intensity = i % 5)
+    raw = np.concatenate([cloud, (np.arange(cloud.shape[0]) % 5).astype(np.float32)[:, None]], 1)
+    ds = O.voxel_filter(raw, 0.3, ioff=3)
+    assert np.array_equal(bits(d["mcl_cloud_ds"]), bits(ds))
+    assert np.array_equal(bits(d["mcl_after_update_ds"][:, 6]), bits(O.update(m, O.particles(P), ds[:, :3].copy())[:, 6]))
     # free-function builders
     ref2 = O.compute_grid2(m, sm.points)
     assert np.allclose(d["free_compute_grid2"].reshape(-1), ref2, rtol=1e-6, atol=1e-30)

@@ -177,6 +177,14 @@ class ParticleFilter:
         check(self._L.amcl3d_b200_pf_get_particles(self._h, out.ctypes.data, n, C.byref(got)))
         return out
 
+    def read_particles(self, out: np.ndarray) -> int:
+        """p_ into a caller-owned (n, 7) float32 array -- e.g. a view of pinned memory, which makes the device->host
+        copy a single DMA instead of a staged pageable copy.  Returns the number of particles written."""
+        assert out.dtype == np.float32 and out.ndim == 2 and out.shape[1] == 7 and out.flags["C_CONTIGUOUS"]
+        got = C.c_uint64(0)
+        check(self._L.amcl3d_b200_pf_get_particles(self._h, out.ctypes.data, out.shape[0], C.byref(got)))
+        return int(got.value)
+
     @p_.setter
     def p_(self, aos7):
         aos7 = _f32(aos7)

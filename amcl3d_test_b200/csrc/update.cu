@@ -552,7 +552,8 @@ __global__ void __launch_bounds__(kSumThreads)
   const uint32_t tid = threadIdx.x;
   const uint32_t i = blockIdx.x * kSumThreads + tid;
   for (uint32_t k = tid; k < 256; k += kSumThreads)
-    lut_s[k] = k < map.lut_n ? map.lut[k] : 0.f;
+    lut_s[k] = k < map.lut_n ? map.lut[k] : (k == kStageSkip ? -0.f : 0.f);
+  const uint32_t lut_base = (uint32_t)__cvta_generic_to_shared(lut_s);
   if (tid == 0)
   {
     mbar_init(&full_bar[0], 1);
@@ -592,18 +593,18 @@ __global__ void __launch_bounds__(kSumThreads)
     const uint32_t rows = min((uint32_t)kSumRows, npts - c * kSumRows);
     if (inmap)
     {
+      uint32_t skipped = 0;
       const uint8_t* col = &ring[c & 1][tid];
 #pragma unroll 8
       for (uint32_t rr = 0; rr < rows; ++rr)
       {
         const uint32_t code = col[rr * kSumThreads];
-        const float v = lut_s[code];
-        if (code != kStageSkip)
-        {
-          weight = __fadd_rn(weight, v);  // Grid3d.cpp:292, cloud order
-          ++cnt;
-        }
+        float v;  // lut_s[code]; lut_s[kStageSkip] = -0.0f, and x + (-0) = x for every x this sum can hold
+        asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(lut_base + code * 4u));
+        weight = __fadd_rn(weight, v);  // Grid3d.cpp:292, cloud order
+        skipped += (code + 1u) >> 8;  // kStageSkip == 0xFF is the only code that carries into bit 8
       }
+      cnt += (int)(rows - skipped);
     }
     __syncthreads();
     if (tid == 0 && c + 2 < nchunks)

@@ -384,6 +384,8 @@ def run_b200(args):
     pf = ParticleFilter(grid)
     pf.set_stream(stream.cuda_stream)
 
+    out_view = pin_out.numpy()
+
     def e2e_step():
         pf.p_ = pin_p.numpy()               # H2D particles
         if args.workload in BEACONS:
@@ -392,8 +394,7 @@ def run_b200(args):
             pf.update(pin_c.numpy())        # H2D cloud + K3
         pf.particleNormalize()
         pf.resample(u01)
-        got = pf.p_                         # D2H resampled set
-        pin_out.numpy()[...] = got
+        pf.read_particles(out_view)         # D2H resampled set, straight into the pinned buffer
         return pf.getMean()                 # D2H 7 floats
 
     for _ in range(max(1, args.warmup)):

@@ -290,10 +290,21 @@ class ParticleFilter:
     def fuse_range(self, d_wr: int, alpha):
         check(self._L.amcl3d_b200_pf_fuse_range(self._h, C.c_void_p(d_wr), float(alpha)))
 
-    def particleNormalize(self) -> np.float32:
+    def particleNormalize(self, fetch=True):
+        """ParticleFilter::particleNormalize; returns wtp (fetch=False: nothing is read back, no host wait in async mode)."""
+        if not fetch:
+            check(self._L.amcl3d_b200_pf_normalize(self._h, None))
+            return None
         wtp = C.c_float(0)
         check(self._L.amcl3d_b200_pf_normalize(self._h, C.byref(wtp)))
         return np.float32(wtp.value)
+
+    def set_async(self, enable: bool):
+        """Stream order instead of call order for the calls that return nothing to the host (see the C header)."""
+        check(self._L.amcl3d_b200_pf_set_async(self._h, int(bool(enable))))
+
+    def sync(self):
+        check(self._L.amcl3d_b200_pf_sync(self._h))
 
     def addParticleWeight(self):
         check(self._L.amcl3d_b200_pf_scale_by_max(self._h))
@@ -318,6 +329,10 @@ class ParticleFilter:
         out = np.zeros(7, np.float32)
         check(self._L.amcl3d_b200_pf_mean(self._h, int(exact), out.ctypes.data))
         return out
+
+    def mean_device(self, d_out7: int, exact=False):
+        """getMean into 7 floats of caller-owned device memory (no host wait in async mode)."""
+        check(self._L.amcl3d_b200_pf_mean_device(self._h, int(exact), C.c_void_p(d_out7)))
 
     def getBestParticle(self) -> np.ndarray:
         out = np.zeros(7, np.float32)

@@ -22,13 +22,14 @@ SYMBOLS = [
     "amcl3d_b200_grid_cloud_weight", "amcl3d_b200_grid_device_ptr", "amcl3d_b200_grid_use_codes",
     "amcl3d_b200_pf_create", "amcl3d_b200_pf_destroy", "amcl3d_b200_pf_set_trig_mode", "amcl3d_b200_pf_set_stream",
     "amcl3d_b200_pf_set_two_phase",
+    "amcl3d_b200_pf_set_async", "amcl3d_b200_pf_sync",
     "amcl3d_b200_pf_set_particles", "amcl3d_b200_pf_get_particles", "amcl3d_b200_pf_size",
     "amcl3d_b200_pf_bind_device", "amcl3d_b200_pf_device_ptr", "amcl3d_b200_pf_set_cloud",
     "amcl3d_b200_pf_set_cloud_device", "amcl3d_b200_pf_set_cloud_downsampled", "amcl3d_b200_pf_get_cloud",
     "amcl3d_b200_pf_update", "amcl3d_b200_pf_update_cloud",
     "amcl3d_b200_pf_update_split", "amcl3d_b200_pf_fuse_range",
     "amcl3d_b200_pf_normalize", "amcl3d_b200_pf_scale_by_max", "amcl3d_b200_pf_resample",
-    "amcl3d_b200_pf_uniform_sample", "amcl3d_b200_pf_mean", "amcl3d_b200_pf_best", "amcl3d_b200_pf_predict",
+    "amcl3d_b200_pf_uniform_sample", "amcl3d_b200_pf_mean", "amcl3d_b200_pf_mean_device", "amcl3d_b200_pf_best", "amcl3d_b200_pf_predict",
     "amcl3d_b200_pf_prefix", "amcl3d_b200_pf_last_kernel_ms", "amcl3d_b200_pf_launch_count",
     "amcl3d_b200_pf_compute_sample_num", "amcl3d_b200_pf_update_sample_height", "amcl3d_b200_pf_resample_step",
     "amcl3d_b200_bench_gather",
@@ -104,6 +105,8 @@ def load():
         "amcl3d_b200_pf_size": (i, [vp, P(u64)]),
         "amcl3d_b200_pf_bind_device": (i, [vp, vp, u64, u64]),
         "amcl3d_b200_pf_device_ptr": (i, [vp, P(vp), P(u64)]),
+        "amcl3d_b200_pf_set_async": (i, [vp, i]),
+        "amcl3d_b200_pf_sync": (i, [vp]),
         "amcl3d_b200_pf_set_cloud": (i, [vp, vp, u32, u32]),
         "amcl3d_b200_pf_set_cloud_device": (i, [vp, vp, u32, u32]),
         "amcl3d_b200_pf_set_cloud_downsampled": (i, [vp, vp, u32, i, u32, f32, i, P(u32)]),
@@ -117,6 +120,7 @@ def load():
         "amcl3d_b200_pf_resample": (i, [vp, f32, u64, u64, vp, vp]),
         "amcl3d_b200_pf_uniform_sample": (i, [vp, i, u64, u64, vp, vp, P(i)]),
         "amcl3d_b200_pf_mean": (i, [vp, i, vp]),
+        "amcl3d_b200_pf_mean_device": (i, [vp, i, vp]),
         "amcl3d_b200_pf_best": (i, [vp, vp]),
         "amcl3d_b200_pf_predict": (i, [vp, f64p, vp]),
         "amcl3d_b200_pf_prefix": (i, [vp, P(vp), vp, u64]),

@@ -137,6 +137,7 @@ struct amcl3d_b200_pf_s
   void* d_scratch = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
+  bool async_mode = false;  // amcl3d_b200_pf_set_async: calls that hand nothing back to the host do not synchronise
   uint64_t launches = 0;
 };
 
@@ -193,6 +194,18 @@ int use_device(int device)
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess)
     return fail_cuda(e, "cudaSetDevice");
+  return AMCL3D_B200_OK;
+}
+
+// end of an entry point that returns nothing to the host: the reference API is synchronous, so is this one unless
+// the caller opted into stream order
+int finish_call(amcl3d_b200_pf_t pf)
+{
+  if (pf->async_mode)
+    return AMCL3D_B200_OK;
+  cudaError_t e = cudaStreamSynchronize(pf->stream);
+  if (e != cudaSuccess)
+    return fail_cuda(e, "cudaStreamSynchronize");
   return AMCL3D_B200_OK;
 }
 
@@ -751,6 +764,24 @@ int amcl3d_b200_pf_set_trig_mode(amcl3d_b200_pf_t pf, int trig_mode)
   return AMCL3D_B200_OK;
 }
 
+int amcl3d_b200_pf_set_async(amcl3d_b200_pf_t pf, int enable)
+{
+  if (!pf)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+  pf->async_mode = enable != 0;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_sync(amcl3d_b200_pf_t pf)
+{
+  if (!pf)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  CU(cudaStreamSynchronize(pf->stream));
+  return AMCL3D_B200_OK;
+}
+
 int amcl3d_b200_pf_set_two_phase(amcl3d_b200_pf_t pf, int enable)
 {
   if (!pf)
@@ -1026,10 +1057,9 @@ static int update_impl(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beacons,
     CU(cudaMemcpyAsync(&c, d_counter, sizeof(c), cudaMemcpyDeviceToHost, pf->stream));
     CU(cudaStreamSynchronize(pf->stream));
     *in_bounds = c;
+    return AMCL3D_B200_OK;
   }
-  else
-    CU(cudaStreamSynchronize(pf->stream));
-  return AMCL3D_B200_OK;
+  return finish_call(pf);
 }
 
 int amcl3d_b200_pf_update(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beacons, uint32_t nb, float alpha, float sigma,
@@ -1058,8 +1088,7 @@ int amcl3d_b200_pf_fuse_range(amcl3d_b200_pf_t pf, const void* d_wr, float alpha
     if (int rc = fuse_range_async(pf, reinterpret_cast<const float*>(d_wr), alpha))
       return rc;
   }
-  CU(cudaStreamSynchronize(pf->stream));
-  return AMCL3D_B200_OK;
+  return finish_call(pf);
 }
 
 int amcl3d_b200_pf_update_cloud(amcl3d_b200_pf_t pf, const float* cloud, uint32_t stride, uint32_t npts)
@@ -1091,11 +1120,12 @@ int amcl3d_b200_pf_normalize(amcl3d_b200_pf_t pf, float* wtp)
     if (int rc = normalize_async(pf))
       return rc;
   }
+  if (!wtp)
+    return finish_call(pf);
   float total = 0;
   CU(cudaMemcpyAsync(&total, pf->d_scalars, sizeof(float), cudaMemcpyDeviceToHost, pf->stream));
   CU(cudaStreamSynchronize(pf->stream));
-  if (wtp)
-    *wtp = total;
+  *wtp = total;
   return AMCL3D_B200_OK;
 }
 
@@ -1112,8 +1142,7 @@ int amcl3d_b200_pf_scale_by_max(amcl3d_b200_pf_t pf)
     pf->launches += 3;
     pf->launches += chain_extra_launches_take();
   }
-  CU(cudaStreamSynchronize(pf->stream));
-  return AMCL3D_B200_OK;
+  return finish_call(pf);
 }
 
 // replaces p_ by the first `count` particles of d_alt
@@ -1176,9 +1205,12 @@ int amcl3d_b200_pf_resample(amcl3d_b200_pf_t pf, float u01, uint64_t m0, uint64_
     if (int rc = adopt_alt(pf, n))
       return rc;
   if (idx && cnt)
+  {
     CU(cudaMemcpyAsync(idx, d_idx, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, pf->stream));
-  CU(cudaStreamSynchronize(pf->stream));
-  return AMCL3D_B200_OK;
+    CU(cudaStreamSynchronize(pf->stream));
+    return AMCL3D_B200_OK;
+  }
+  return finish_call(pf);
 }
 
 int amcl3d_b200_pf_uniform_sample(amcl3d_b200_pf_t pf, int sample_num, uint64_t k0, uint64_t k1, void* d_out,
@@ -1250,6 +1282,20 @@ int amcl3d_b200_pf_mean(amcl3d_b200_pf_t pf, int exact, float out7[7])
   CU(cudaMemcpyAsync(out7, pf->d_scalars + 8, 7 * sizeof(float), cudaMemcpyDeviceToHost, pf->stream));
   CU(cudaStreamSynchronize(pf->stream));
   return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_mean_device(amcl3d_b200_pf_t pf, int exact, void* d_out7)
+{
+  if (!pf || !d_out7)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  {
+    Timed t(pf);
+    CU(launch_mean(pf->d_p, pf->n, exact, reinterpret_cast<float*>(d_out7), pf->d_scratch, pf->stream));
+    pf->launches += exact ? 1 : 2;
+  }
+  return finish_call(pf);
 }
 
 int amcl3d_b200_pf_best(amcl3d_b200_pf_t pf, float out7[7])

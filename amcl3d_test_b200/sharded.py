@@ -84,6 +84,18 @@ class ShardedFilter:
         self.shard.resample_full(u01, self.lo, self.hi)
         return wtp
 
+    def mean_device(self):
+        """Global mean as a 7-float device tensor, nothing read back: local weighted sums on the device, one
+        all-gather of 7 floats per rank, combined on the device (sums in f64, w = max)."""
+        loc = self.shard.mean_local_device()
+        if self.world == 1:
+            return loc
+        if getattr(self, "_mean_all", None) is None:
+            self._mean_all = torch.empty((self.world, 7), dtype=torch.float32, device=loc.device)
+        dist.all_gather_into_tensor(self._mean_all, loc.view(1, 7), group=self.group)
+        sums = self._mean_all[:, :6].to(torch.float64).sum(0).to(torch.float32)
+        return torch.cat([sums, self._mean_all[:, 6].max().view(1)])
+
     def mean(self):
         part = torch.as_tensor(np.asarray(self.shard.mean_local(), np.float64))
         if self.world > 1:
@@ -135,14 +147,28 @@ class CudaShard:
     def fuse_full(self):
         self.pf_full.fuse_range(self.wr_full.data_ptr(), self.alpha)
 
+    def set_async(self, enable: bool):
+        """Stream order for the stages that return nothing to the host; mean() stays the one wait of a step."""
+        self.async_ = bool(enable)
+        self.pf_local.set_async(enable)
+        self.pf_full.set_async(enable)
+
+    async_ = False
+
     def normalize_full(self):
-        return self.pf_full.particleNormalize()
+        return self.pf_full.particleNormalize(fetch=not self.async_)
 
     def resample_full(self, u01, m0, m1):
         self.pf_full.resample(u01, m0=m0, m1=m1, d_out=self.local.data_ptr())
 
     def mean_local(self):
         return self.pf_local.getMean(exact=False)
+
+    def mean_local_device(self):
+        if getattr(self, "_mean_buf", None) is None:
+            self._mean_buf = torch.zeros(7, dtype=torch.float32, device=self.device)
+        self.pf_local.mean_device(self._mean_buf.data_ptr(), exact=False)
+        return self._mean_buf
 
     def launch_count(self):
         return self.pf_local.launch_count() + self.pf_full.launch_count()

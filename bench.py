@@ -354,16 +354,25 @@ def run_b200(args):
     sampler.start()
     l0 = shard.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the resident loop runs in stream order (amcl3d_b200_pf_set_async): no host wait between the stages of a step or
+    # between steps; the update's share is taken from event pairs recorded on the same stream, read after the loop
+    ev_u = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    shard.set_async(True)
     torch.cuda.synchronize()
     e0.record(stream)
-    for _ in range(args.steps):
+    for k in range(args.steps):
         shard.local.copy_(backup)
+        ev_u[k][0].record(stream)
         filt.update()
-        upd_ms.append(shard.pf_local.last_kernel_ms())
+        ev_u[k][1].record(stream)
         filt.resample(u01)
-        filt.mean()
+        mean_dev = filt.mean_device()
     e1.record(stream)
     torch.cuda.synchronize()
+    shard.set_async(False)
+    upd_ms = [a.elapsed_time(b) for a, b in ev_u]
+    mean_host = mean_dev.cpu().numpy()
+    assert np.all(np.isfinite(mean_host))
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()

@@ -149,6 +149,14 @@ int amcl3d_b200_grid_device_ptr(amcl3d_b200_grid_t g, void** d_prob);
 int amcl3d_b200_pf_create(amcl3d_b200_grid_t g, amcl3d_b200_pf_t* out);
 int amcl3d_b200_pf_destroy(amcl3d_b200_pf_t pf);
 int amcl3d_b200_pf_set_trig_mode(amcl3d_b200_pf_t pf, int trig_mode);
+/* Stream order instead of call order.  The reference API is synchronous and so is every entry point by default.
+ * With async enabled, the calls that hand nothing back to the host -- update (in_bounds == NULL), update_split,
+ * fuse_range, normalize (wtp == NULL), scale_by_max, resample (idx == NULL) -- only enqueue their kernels on the
+ * handle's stream and return; anything that returns a value (mean, best, get_particles, a non-NULL out pointer)
+ * still waits for it, which also orders everything enqueued before.  amcl3d_b200_pf_sync waits explicitly.
+ * Lets a caller that keeps the particle set resident run frames back to back without a host round trip per stage. */
+int amcl3d_b200_pf_set_async(amcl3d_b200_pf_t pf, int enable);
+int amcl3d_b200_pf_sync(amcl3d_b200_pf_t pf);
 /* enable (default) / disable the two-phase update: phase 1 sweeps the cloud in Morton order (so that all
  * particles work in the same neighbourhood of the map at the same time) and parks 1-byte codes, phase 2 adds
  * them in the original cloud order -- bit-identical weights, ~1.4x faster on large grids.  Takes effect at
@@ -223,6 +231,9 @@ int amcl3d_b200_pf_uniform_sample(amcl3d_b200_pf_t pf, int sample_num, uint64_t 
 /* ParticleFilter::getMean (ParticleFilter.cpp:198-216): exact != 0 replays the sequential f32 sums,
  * otherwise a deterministic f64 tree reduction of the f32 products.  out7 = x..yaw, w = max weight */
 int amcl3d_b200_pf_mean(amcl3d_b200_pf_t pf, int exact, float out7[7]);
+/* getMean with the 7 floats written to DEVICE memory of the caller (e.g. the send buffer of a collective);
+ * no host wait in async mode */
+int amcl3d_b200_pf_mean_device(amcl3d_b200_pf_t pf, int exact, void* d_out7);
 /* ParticleFilter::getBestParticle (ParticleFilter.cpp:218-228): first arg-max with w > 0 */
 int amcl3d_b200_pf_best(amcl3d_b200_pf_t pf, float out7[7]);
 

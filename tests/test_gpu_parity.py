@@ -677,3 +677,33 @@ def test_input_downsample_edge_cases(O, world_c1, pf):
     ref = O.voxel_filter(dense, 0.25, ioff=3)
     assert pf.set_cloud_downsampled(dense, 0.25, intensity_offset=3) == ref.shape[0]
     assert np.array_equal(bits(pf.get_cloud()), bits(ref))
+
+
+def test_stream_ordered_calls_give_the_same_bits(O, world_c1, gpu_c1):
+    """amcl3d_b200_pf_set_async: update / normalize / resample only enqueue; the values read afterwards are those
+    of the synchronous calls."""
+    from amcl3d_test_b200 import ParticleFilter
+
+    w = world_c1
+    u01 = 0.37
+    a, b = ParticleFilter(gpu_c1), ParticleFilter(gpu_c1)
+    for pf, asyn in ((a, False), (b, True)):
+        pf.set_async(asyn)
+        pf.p_ = w["T"]
+        pf.set_cloud(w["cloud"])
+        pf.update()
+        assert pf.particleNormalize(fetch=not asyn) is None or not asyn
+        pf.resample(u01)
+        if asyn:
+            pf.sync()
+    assert np.array_equal(bits(a.p_), bits(b.p_))
+    ref = O.update(w["map"], O.particles(w["T"]), w["cloud"])
+    O.normalize(w["map"], ref)
+    out, _ = O.resample(ref, np.float32(u01))
+    assert np.array_equal(bits(b.p_), bits(out))
+    import torch
+
+    buf = torch.zeros(7, dtype=torch.float32, device="cuda:0")
+    b.mean_device(buf.data_ptr())
+    b.sync()
+    assert np.allclose(buf.cpu().numpy(), O.mean(out), rtol=2e-5, atol=1e-6)

@@ -1,0 +1,136 @@
+"""Full BASELINE sizes (config 2 grid 2000x2000x400, config 3 = 100 k particles x 10 k points) through properties
+that do not need a CPU run of the whole problem:
+  * grid build: sampled voxels against a brute-force nearest neighbour over the map points around them
+    (the field is exactly 0 beyond the expf underflow radius, so a local search decides every sampled voxel);
+  * update: a sample of the particles evaluated again on their own by the small-problem path (one kernel, caller's
+    cloud order) and on the plain float grid must reproduce the bits they got inside the full two-phase run on the
+    page-blocked coded grid -- the small-problem path is the one pinned against the oracle in test_gpu_parity.py;
+  * normalise / resample / mean at full size: weights sum to 1, resampled set is made of input particles in
+    non-decreasing index order with weight 1/N, bit-identical on a second run (determinism).
+"""
+import numpy as np
+import pytest
+
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full(O):
+    from amcl3d_test_b200 import Grid3d, synth
+
+    cfg = synth.CONFIGS["C3"]
+    sm = synth.make_map(cfg["extent"], cfg["resol"])
+    g = Grid3d(0)
+    mn, mx = g.computePointCloud(sm.points, cfg["resol"])
+    g.computeGrid(sm.points, 0.05, sub=2)
+    cloud = synth.make_cloud(sm, cfg["points"], cfg["radius"])
+    return dict(sm=sm, g=g, mn=mn, mx=mx, cloud=cloud, cfg=cfg)
+
+
+class _DevArray:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def test_config2_grid_sampled_voxels_vs_local_brute_force(O, full):
+    import torch
+
+    sm, g = full["sm"], full["g"]
+    info = g.info()
+    sx, sy, sz = info["size"]
+    assert (sx, sy, sz) == (2000, 2000, 400) and info["n_cells"] == 1_600_000_000
+    resol, sigma = 0.05, 0.05
+    prob = torch.as_tensor(_DevArray(g.device_ptr(), (sz, sy, sx), "<f4"), device="cuda:0")
+    # occupancy of the synthetic map on the half-voxel lattice (points sit at voxel centres)
+    vox = np.floor(sm.points[2:].astype(np.float64) / resol).astype(np.int64)
+    occ = np.zeros((sz, sy, sx), np.bool_)
+    occ[vox[:, 2], vox[:, 1], vox[:, 0]] = True
+    rng = np.random.RandomState(21)
+    # sample: voxels around random occupied voxels (inside the band where the field is non-zero) + uniform ones
+    seeds = vox[rng.randint(0, vox.shape[0], 3000)]
+    near = seeds + rng.randint(-14, 15, seeds.shape)
+    uni = np.stack([rng.randint(0, sx, 1500), rng.randint(0, sy, 1500), rng.randint(0, sz, 1500)], 1)
+    q = np.concatenate([near, uni])
+    q = q[(q >= 0).all(1) & (q[:, 0] < sx) & (q[:, 1] < sy) & (q[:, 2] < sz)]
+    qi = torch.as_tensor(q, device="cuda:0")
+    got = prob[qi[:, 2], qi[:, 1], qi[:, 0]].cpu().numpy()
+    R = 24  # voxels; beyond 17 voxels c1*expf(-d^4 c2) is exactly 0 at sigma = 0.05
+    c1 = np.float32(1.0 / (sigma * np.sqrt(2 * np.pi)))
+    c2 = np.float32(1.0 / (2 * sigma * sigma))
+    want = np.zeros(q.shape[0], np.float32)
+    for k, (x, y, z) in enumerate(q):
+        x0, x1, y0, y1, z0, z1 = max(x - R, 0), min(x + R, sx), max(y - R, 0), min(y + R, sy), max(z - R, 0), min(z + R, sz)
+        zz, yy, xx = np.nonzero(occ[z0:z1, y0:y1, x0:x1])
+        if zz.size == 0:
+            continue
+        # squared distance corner (2x,2y,2z) -> centre (2i+1, ...) in half-voxel units (integers)
+        d2 = ((2 * (xx + x0) + 1 - 2 * x) ** 2 + (2 * (yy + y0) + 1 - 2 * y) ** 2 + (2 * (zz + z0) + 1 - 2 * z) ** 2).min()
+        dist = np.float32(np.float64(d2) * (resol / 2) ** 2)          # PointCloudTools.cpp:158 (squared metres)
+        want[k] = c1 * np.exp(np.float32(-(dist * dist) * c2), dtype=np.float32)  # :160-162 (the d^4 quirk)
+    nz = want > 0
+    assert nz.sum() > 1000  # (clutter makes voxels farther than the underflow radius from every site rare)
+    assert np.array_equal(got == 0, want == 0)
+    assert np.allclose(got[nz], want[nz], rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize("kind", ["T", "G"])
+def test_config3_update_sample_reproduced_by_the_small_problem_paths(O, full, kind):
+    from amcl3d_test_b200 import ParticleFilter, synth
+
+    g, cloud, cfg = full["g"], full["cloud"], full["cfg"]
+    P = synth.make_particles(full["sm"], cfg["particles"], kind)
+    pf = ParticleFilter(g)
+    pf.p_ = P
+    n_in = pf.update(cloud, count=True)
+    W = pf.p_
+    assert 0.3 < n_in / (P.shape[0] * cloud.shape[0]) < 0.95
+    assert (W[:, 6] > 0).mean() > 0.5
+    rng = np.random.RandomState(4)
+    pick = np.sort(rng.choice(P.shape[0], 384, replace=False))
+    # (a) same coded grid, single-kernel path in the caller's cloud order
+    small = ParticleFilter(g)
+    small.set_two_phase(False)
+    small.p_ = P[pick]
+    small.update(cloud)
+    assert np.array_equal(bits(small.p_[:, 6]), bits(W[pick, 6]))
+    # (b) plain linear float grid (what the reference indexes: ix + iy*size_x + iz*size_x*size_y)
+    g.useCodes(False)
+    try:
+        assert g.info()["rep"] == 0
+        lin = ParticleFilter(g)
+        lin.p_ = P[pick]
+        lin.update(cloud)
+        assert np.array_equal(bits(lin.p_[:, 6]), bits(W[pick, 6]))
+    finally:
+        g.useCodes(True)
+
+
+def test_config3_normalise_resample_mean_properties(O, full):
+    from amcl3d_test_b200 import ParticleFilter, synth
+
+    g, cloud, cfg = full["g"], full["cloud"], full["cfg"]
+    P = synth.make_particles(full["sm"], cfg["particles"], "T")
+    n = P.shape[0]
+    runs = []
+    for _ in range(2):
+        pf = ParticleFilter(g)
+        pf.p_ = P
+        pf.update(cloud)
+        wtp = pf.particleNormalize()
+        Wn = pf.p_
+        idx = pf.resample(0.4321, want_idx=True)
+        out = pf.p_
+        runs.append((wtp, Wn, idx, out, pf.getMean(exact=True)))
+    wtp, Wn, idx, out, mean = runs[0]
+    assert wtp > 0 and abs(float(Wn[:, 6].astype(np.float64).sum()) - 1.0) < 1e-4
+    assert np.all(np.diff(idx) >= 0) and idx.min() >= 0 and idx.max() < n
+    assert np.array_equal(bits(out[:, :6]), bits(P[idx, :6]))
+    assert np.all(out[:, 6] == np.float32(1.0) / np.float32(n))
+    # the sequential-chain oracle on the weights alone (cheap at any size): indices and mean, bit for bit
+    ref_out, ref_idx = O.resample(Wn, np.float32(0.4321))
+    assert np.array_equal(idx, ref_idx)
+    assert np.array_equal(bits(mean), bits(O.mean(ref_out)))
+    for a, b in zip(runs[0], runs[1]):
+        assert np.array_equal(bits(np.asarray(a)), bits(np.asarray(b)))

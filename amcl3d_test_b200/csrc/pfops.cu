@@ -670,80 +670,121 @@ __global__ void __launch_bounds__(kScanThreads)
   }
 }
 
-// which candidate of a run guessed at g covers state c (-1: none / the integer scheme does not apply); s = the
-// state's integer mantissa
-__device__ __forceinline__ int candidate_of(float c, int g, int& s)
+// Warp-cooperative application of up to 32 consecutive runs to the state c.  Lane v holds run v: the binade guess
+// g its three candidate functions d were evaluated around, and whether it is all +0 (identity for ANY state).
+// Runs [u, m) are live.  Returns the first live run that cannot be applied in O(1) -- the state would leave its
+// binade inside it, an operand needs the real add, or no candidate covers the state's binade -- or 32 if all
+// went through.  `before` (per lane) = state in front of run v, valid for u <= v <= min(returned, m - 1);
+// c_out (uniform) = state in front of the returned run, or behind the last live run.
+__device__ __forceinline__ int warp_walk(float c, int u, int m, int g, int d00, int d01, int d10, int d11, int d20, int d21,
+                                         bool identity, float& before, float& c_out)
 {
+  const int lane = threadIdx.x & 31;
   const uint32_t cb = __float_as_uint(c);
   const int ce = (int)((cb >> 23) & 0xFFu);
-  s = (int)((cb & 0x7FFFFFu) | 0x800000u);
-  if (g == kNoGuess || (cb & 0x80000000u) || ce <= 27 || ce == 0xFF)
-    return -1;
-  const int idx = (ce - 127) - (g - 1);
-  return (idx < 0 || idx >= kCand) ? -1 : idx;
-}
-// O(1) application of a run to the state; false if the state would leave the binade (or an operand needs the
-// real add)
-__device__ __forceinline__ bool fn_apply(int d0, int d1, int s, float& c)
-{
-  const int d = (s & 1) ? d1 : d0;
-  if (d >= kSat || s + d >= (1 << 24))
-    return false;
-  c = __uint_as_float((__float_as_uint(c) & 0x7F800000u) | ((uint32_t)(s + d) & 0x7FFFFFu));
-  return true;
+  const bool c_ok = !(cb & 0x80000000u) && ce > 27 && ce < 0xFF;  // positive, normal, e >= -99
+  const int s = (int)((cb & 0x7FFFFFu) | 0x800000u);
+  StepFn f{ 0, 0 };
+  if (lane >= u && lane < m && !identity)
+  {
+    const int idx = (ce - 127) - (g - 1);
+    if (c_ok && g != kNoGuess && idx >= 0 && idx < kCand)
+      f = StepFn{ idx == 0 ? d00 : (idx == 1 ? d10 : d20), idx == 0 ? d01 : (idx == 1 ? d11 : d21) };
+    else
+      f = StepFn{ kSat, kSat };
+  }
+  StepFn incl = f;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1)
+  {
+    StepFn p;
+    p.d0 = __shfl_up_sync(0xffffffffu, incl.d0, o);
+    p.d1 = __shfl_up_sync(0xffffffffu, incl.d1, o);
+    if (lane >= o)
+      incl = step_compose(p, incl);
+  }
+  StepFn excl;
+  excl.d0 = __shfl_up_sync(0xffffffffu, incl.d0, 1);
+  excl.d1 = __shfl_up_sync(0xffffffffu, incl.d1, 1);
+  if (lane == 0)
+    excl = StepFn{ 0, 0 };
+  const int d_in = (s & 1) ? incl.d1 : incl.d0;
+  const int d_ex = (s & 1) ? excl.d1 : excl.d0;
+  // d == 0 leaves the state as it is whatever it is (runs of +0 in front of a zero / denormal state included)
+  const bool ok_in = d_in == 0 || (d_in < kSat && s + d_in < (1 << 24));
+  const uint32_t hi = cb & 0x7F800000u;
+  before = d_ex == 0 ? c : __uint_as_float(hi | ((uint32_t)(s + d_ex) & 0x7FFFFFu));
+  const float after = d_in == 0 ? c : __uint_as_float(hi | ((uint32_t)(s + d_in) & 0x7FFFFFu));
+  const uint32_t fail = __ballot_sync(0xffffffffu, !ok_in);  // increments only grow: once a lane fails all later do
+  const int ff = fail ? __ffs(fail) - 1 : 32;
+  c_out = ff < 32 ? __shfl_sync(0xffffffffu, before, ff) : __shfl_sync(0xffffffffu, after, 31);
+  return ff;
 }
 
-// One thread walks the sub-tiles of a staged tile from state c.  A sub-tile whose function applies costs O(1);
-// otherwise its operands are added one by one (kept: the running values replace them in `stage`, and the
-// sub-tile is marked finished).  sub_state (nullable) receives every sub-tile's incoming state.  Stops early,
-// returning the sub-tile index, once more than kMaxSerialSubTiles needed the adds (the caller then switches to
-// the block-wide scan); returns kSubTiles when the tile is through.
-__device__ int walk_sub_tiles(const TileSubFn& sub, float* stage, int len, bool keep, float& c, float* sub_state,
-                              int* sub_done)
+// real f32 adds over operands [i0, i1) of a staged tile (i0 a multiple of 8); keep: the running values replace them
+__device__ __forceinline__ float serial_adds(float* stage, int i0, int i1, bool keep, float c)
 {
-  int serial_left = kMaxSerialSubTiles;
-  for (int u = 0; u < kSubTiles; ++u)
+  float cc = c;
+  for (int i = i0; i < i1; i += 8)  // a multiple of 8 operands share one pad-free run of slots
   {
-    if (sub_state)
+    float v[8];
+    const int slot = stage_slot(i);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      v[k] = (i + k < i1) ? stage[slot + k] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
     {
-      sub_state[u] = c;
-      sub_done[u] = 0;
-    }
-    if (u * kSubLen >= len)
-      continue;
-    int s;
-    const int idx = candidate_of(c, sub.g[u], s);
-    if (idx >= 0 && fn_apply(sub.f[idx][u].d0, sub.f[idx][u].d1, s, c))
-      continue;
-    if (serial_left-- == 0)
-      return u;
-    const int i1 = min((u + 1) * kSubLen, len);
-    float cc = c;
-    for (int i = u * kSubLen; i < i1; i += 8)  // sub-tiles start on a multiple of 8: one pad-free run of slots
-    {
-      float v[8];
-      const int slot = stage_slot(i);
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        v[k] = (i + k < i1) ? stage[slot + k] : 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-      {
-        if (i + k < i1)
-          cc = __fadd_rn(cc, v[k]);
-        v[k] = cc;
-      }
-      if (keep)
-      {
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (i + k < i1)
-            stage[slot + k] = v[k];
-      }
+      if (i + k < i1)
+        cc = __fadd_rn(cc, v[k]);
+      v[k] = cc;
     }
     if (keep)
-      sub_done[u] = 1;
-    c = cc;
+    {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (i + k < i1)
+          stage[slot + k] = v[k];
+    }
+  }
+  return cc;
+}
+
+// Warp 0 walks the sub-tiles of a staged tile from state c.  Sub-tiles whose function applies cost O(1) for the
+// whole run of them (one warp scan); a sub-tile where it does not is redone with real adds by lane 0 (keep: the
+// running values replace its operands in `stage` and it is marked finished).  sub_state / sub_done (nullable,
+// shared memory) receive every sub-tile's incoming state.  Returns the sub-tile where the walk gave up (more than
+// kMaxSerialSubTiles needed the adds: the caller switches to the block-wide scan from there), or kSubTiles.
+__device__ int walk_sub_tiles(const TileSubFn& sub, float* stage, int len, bool keep, float& c, float* sub_state, int* sub_done)
+{
+  const int lane = threadIdx.x & 31;
+  const int nsub = (len + kSubLen - 1) / kSubLen;
+  const int g = sub.g[lane];
+  const StepFn f0 = sub.f[0][lane], f1 = sub.f[1][lane], f2 = sub.f[2][lane];
+  if (sub_done)
+    sub_done[lane] = 0;
+  int serial_left = kMaxSerialSubTiles;
+  int su = 0;
+  while (su < nsub)
+  {
+    float before, c_out;
+    const int ff = warp_walk(c, su, nsub, g, f0.d0, f0.d1, f1.d0, f1.d1, f2.d0, f2.d1, false, before, c_out);
+    if (sub_state && lane >= su && lane <= min(ff, nsub - 1))
+      sub_state[lane] = before;
+    c = c_out;
+    if (ff >= nsub)
+      break;
+    if (serial_left-- == 0)
+      return ff;
+    float cc = c;
+    if (lane == 0)
+    {
+      cc = serial_adds(stage, ff * kSubLen, min((ff + 1) * kSubLen, len), keep, c);
+      if (sub_done)
+        sub_done[ff] = 1;
+    }
+    c = __shfl_sync(0xffffffffu, cc, 0);
+    su = ff + 1;
   }
   return kSubTiles;
 }
@@ -763,75 +804,74 @@ __device__ __forceinline__ void stage_tile(const ChainOps& ops, uint64_t tbeg, i
     reinterpret_cast<int*>(sh_sub)[tid] = reinterpret_cast<const int*>(src)[tid];
 }
 
-constexpr int kResolveBatch = 256;
 __global__ void __launch_bounds__(kScanThreads)
     resolve_kernel(ChainOps ops, uint64_t nadd, float start, const TileFn* __restrict__ fns,
                    const TileSubFn* __restrict__ subs, uint64_t ntiles, float* __restrict__ state_in,
                    float* __restrict__ total)
 {
-  __shared__ TileFn sh_tiles[kResolveBatch];
   __shared__ TileSubFn sh_sub;
   __shared__ float stage[kStageWords];
-  __shared__ unsigned long long sh_t;
   __shared__ float sh_state;
-  __shared__ int sh_u;
-  const int tid = threadIdx.x;
+  __shared__ int sh_ff, sh_u;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   ChainOps quiet = ops;  // the prefix is written by emit_kernel
   quiet.prefix = nullptr;
   float c = start;
   if (tid == 0 && ops.mode == kChainThreshold && ops.prefix != nullptr)
     ops.prefix[0] = start;
-  for (uint64_t b0 = 0; b0 < ntiles; b0 += kResolveBatch)
+  // 32 tiles at a time, one per lane of warp 0; the next group's functions are fetched while this one is walked
+  TileFn cur{}, nxt{};
+  if (warp == 0 && (uint64_t)lane < ntiles)
+    cur = fns[lane];
+  for (uint64_t tb = 0; tb < ntiles; tb += 32)
   {
-    const uint64_t bend = min(b0 + (uint64_t)kResolveBatch, ntiles);
-    __syncthreads();
-    for (uint64_t k = b0 + tid; k < bend; k += kScanThreads)
-      sh_tiles[k - b0] = fns[k];
-    __syncthreads();
-    uint64_t t = b0;
-    while (true)
+    const int m = (int)min((uint64_t)32, ntiles - tb);
+    if (warp == 0 && tb + 32 + lane < ntiles)
+      nxt = fns[tb + 32 + lane];
+    int u = 0;
+    while (true)  // block-uniform
     {
-      if (tid == 0)
+      if (warp == 0)
       {
-        while (t < bend)
+        float before, c_out;
+        const int ff = warp_walk(c, u, m, cur.g, cur.d[0][0], cur.d[0][1], cur.d[1][0], cur.d[1][1], cur.d[2][0],
+                                 cur.d[2][1], cur.identity != 0, before, c_out);
+        if (lane >= u && lane <= min(ff, m - 1))
+          state_in[tb + lane] = before;
+        if (lane == 0)
         {
-          state_in[t] = c;
-          const TileFn& f = sh_tiles[t - b0];
-          if (!f.identity)
-          {
-            int s;
-            const int idx = candidate_of(c, f.g, s);
-            if (idx < 0 || !fn_apply(f.d[idx][0], f.d[idx][1], s, c))
-              break;
-          }
-          ++t;
+          sh_ff = ff;
+          sh_state = c_out;
         }
-        sh_t = t;
-        sh_state = c;
       }
       __syncthreads();
-      t = sh_t;
+      const int ff = sh_ff;
       c = sh_state;
-      if (t >= bend)
+      if (ff >= m)
         break;
-      // ---- tile t needs a closer look: stage it and walk its sub-tiles --------------------------------
-      const uint64_t tbeg = t * kTile;
+      // ---- tile tb + ff needs a closer look: stage it and walk its sub-tiles ----------------------------
+      const uint64_t tbeg = (tb + ff) * kTile;
       const int len = (int)min(kTile, nadd - tbeg);
-      stage_tile(ops, tbeg, len, subs + t, stage, &sh_sub);
+      stage_tile(ops, tbeg, len, subs + tb + ff, stage, &sh_sub);
       __syncthreads();
-      if (tid == 0)
+      if (warp == 0)
       {
-        sh_u = walk_sub_tiles(sh_sub, stage, len, false, c, nullptr, nullptr);
-        sh_state = c;
+        const int stop = walk_sub_tiles(sh_sub, stage, len, false, c, nullptr, nullptr);
+        if (lane == 0)
+        {
+          sh_u = stop;
+          sh_state = c;
+        }
       }
       __syncthreads();
       c = sh_state;
-      const int u = sh_u;
-      if (u < kSubTiles)
-        c = scan_range(quiet, tbeg + (uint64_t)u * kSubLen, tbeg + len, c, stage);  // the guess is of no use here
-      ++t;
+      const int stop = sh_u;
+      if (stop < kSubTiles)
+        c = scan_range(quiet, tbeg + (uint64_t)stop * kSubLen, tbeg + len, c, stage);  // the guess is of no use here
+      u = ff + 1;
       __syncthreads();
     }
+    cur = nxt;
   }
   if (tid == 0 && total != nullptr)
     total[0] = c;
@@ -865,10 +905,14 @@ __global__ void __launch_bounds__(kScanThreads)
   }
   stage_tile(ops, tbeg, len, subs + t, stage, &sh_sub);
   __syncthreads();
-  if (tid == 0)
+  if (warp == 0)
   {
-    sh_u = walk_sub_tiles(sh_sub, stage, len, true, c, sub_state, sub_done);
-    sh_state = c;
+    const int stop = walk_sub_tiles(sh_sub, stage, len, true, c, sub_state, sub_done);
+    if (lane == 0)
+    {
+      sh_u = stop;
+      sh_state = c;
+    }
   }
   __syncthreads();
   const int u_stop = sh_u;

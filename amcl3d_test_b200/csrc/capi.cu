@@ -1027,26 +1027,43 @@ static int update_impl(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beacons,
     CU(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), pf->stream));
   }
   // two-phase sweep when it pays: enough particles to fill the machine, a u8-coded grid, staging that fits
+  // The staging buffer holds one byte per particle x point; a particle set too large for the budget is swept in
+  // slices of whole particle tiles, one after the other through the same buffer (particles are independent).
   TwoPhase tp{};
   const TwoPhase* tpp = nullptr;
+  uint64_t slice_n = pf->n;
   if (pf->two_phase && pf->n >= 4096 && pf->npts >= 64 && pf->d_sorted != nullptr && map.rep == kRepCode8 && map.lut_n < 255)
   {
     const uint64_t pitch = stage_tile_width();  // bytes per staged row of one particle tile (= particles per block)
-    const uint64_t bytes = ((pf->n + pitch - 1) / pitch) * pitch * pf->npad;
-    if (bytes <= (16ull << 30))
+    const uint64_t tile_bytes = pitch * pf->npad;
+    const uint64_t tiles = (pf->n + pitch - 1) / pitch;
+    uint64_t budget = 4ull << 30;
+    if (const char* env = getenv("AMCL3D_B200_STAGE_MB"))
+      budget = (uint64_t)atoll(env) << 20;
+    uint64_t slice_tiles = budget / tile_bytes;
+    if (slice_tiles > tiles)
+      slice_tiles = tiles;
+    if (slice_tiles >= 16)  // below that a slice does not fill the machine: single-kernel path
     {
-      CU(ensure(pf->d_codes_staged, pf->codes_staged_cap, bytes));
+      CU(ensure(pf->d_codes_staged, pf->codes_staged_cap, slice_tiles * tile_bytes));
       tp.sorted = pf->d_sorted;
       tp.stage = pf->d_codes_staged;
       tp.pitch = pitch;
       tpp = &tp;
+      slice_n = slice_tiles * pitch;
     }
   }
   {
     Timed t(pf);
-    CU(launch_update(map, pf->d_p, (uint32_t)pf->n, pf->d_cloud, pf->npts, pf->npad, pf->d_beacons, d_wr, pf->trig_mode,
-                     d_counter, tpp, pf->stream));
-    pf->launches += pf->n ? (tpp ? 2 : 1) : 0;
+    for (uint64_t off = 0; off < pf->n || off == 0; off += slice_n)
+    {
+      const uint64_t n_s = pf->n - off < slice_n ? pf->n - off : slice_n;
+      CU(launch_update(map, pf->d_p + 7 * off, (uint32_t)n_s, pf->d_cloud, pf->npts, pf->npad, pf->d_beacons,
+                       d_wr ? d_wr + off : nullptr, pf->trig_mode, d_counter, tpp, pf->stream));
+      pf->launches += n_s ? (tpp ? 2 : 1) : 0;
+      if (pf->n == 0)
+        break;
+    }
     if (nb && pf->n && d_wr_ext == nullptr)
       if (int rc = fuse_range_async(pf, pf->d_wr, alpha))
         return rc;

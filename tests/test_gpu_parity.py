@@ -516,6 +516,28 @@ def test_two_phase_update_is_bit_identical(O, world_c1, kind):
         pf.p_ = P[:n]
         pf.update(cloud[:npts])
         assert np.array_equal(bits(pf.p_[:, 6]), bits(ref[:, 6])), (n, npts)
+    # a particle set whose staged codes exceed the budget is swept in slices through the same buffer
+    import os
+
+    P2 = synth.make_particles(w["synth"], 12_345, kind)
+    ref = O.update(m, O.particles(P2), cloud)
+    beacons = synth.make_beacons(w["synth"], 4)
+    pf.p_ = P2
+    pf.update(cloud, beacons=beacons, alpha=0.5, sigma=0.53)
+    fused_whole = pf.p_
+    os.environ["AMCL3D_B200_STAGE_MB"] = "8"  # 256 x 1504 B per tile -> 21 tiles per slice, 3 slices
+    try:
+        pf.p_ = P2
+        before = pf.launch_count()
+        n3 = pf.update(cloud, count=True)
+        assert pf.launch_count() - before >= 6 + 4  # three slices of two launches each (+ cloud preparation)
+        assert np.array_equal(bits(pf.p_[:, 6]), bits(ref[:, 6]))
+        assert n3 == O.count_in_bounds(m, O.particles(P2), cloud)
+        pf.p_ = P2
+        pf.update(cloud, beacons=beacons, alpha=0.5, sigma=0.53)
+        assert np.array_equal(bits(pf.p_), bits(fused_whole))
+    finally:
+        del os.environ["AMCL3D_B200_STAGE_MB"]
 
 
 def test_range_split_then_fuse_equals_fused_update(world_c1, pf):

@@ -134,3 +134,80 @@ def test_config3_normalise_resample_mean_properties(O, full):
     assert np.array_equal(bits(mean), bits(O.mean(ref_out)))
     for a, b in zip(runs[0], runs[1]):
         assert np.array_equal(bits(np.asarray(a)), bits(np.asarray(b)))
+
+
+def test_config5_extent_voxel_addresses_beyond_2_to_the_32(O):
+    """Config 5's extent (400 x 400 x 40 m at 0.1 m = 6.4e9 voxels, 25.6 GB of f32): linear and coded voxel addresses
+    exceed 32 bits, where the reference's uint32_t index wraps (Grid3d.cpp:263-264,288) and no CPU run can be the
+    checker.  Properties instead: (1) voxels sampled in the part of the grid above 2^32 cells equal the local brute
+    force; (2) weights of particles living there are the same bits on the page-blocked coded grid (two-phase and
+    single-kernel) and on the linear float grid -- three independent address computations over two arrays."""
+    import torch
+
+    from amcl3d_test_b200 import Grid3d, ParticleFilter
+
+    free, total = torch.cuda.mem_get_info(0)
+    if free < 100 * 2**30:
+        pytest.skip("needs ~90 GB of free device memory")
+    resol, sigma = 0.1, 0.05
+    ext = (400.0, 400.0, 40.0)
+    rng = np.random.RandomState(55)
+    # a furnished corner of the map: random occupied voxels (centres) in a 20 x 20 x 8 m block at the far end
+    lo = np.array([3750, 3750, 300])
+    vox = lo + np.stack([rng.randint(0, 200, 150_000), rng.randint(0, 200, 150_000), rng.randint(0, 80, 150_000)], 1)
+    vox = np.unique(vox, axis=0)
+    pts = np.concatenate([[[0, 0, 0], list(ext)], (vox + 0.5) * resol]).astype(np.float32)
+    g = Grid3d(0)
+    g.computePointCloud(pts, resol)
+    g.computeGrid(pts, sigma, sub=2)
+    info = g.info()
+    sx, sy, sz = info["size"]
+    assert (sx, sy, sz) == (4000, 4000, 400) and info["n_cells"] == 6_400_000_000 and info["rep"] == 1
+    assert (int(lo[2]) * sy + int(lo[1])) * sx + int(lo[0]) > 2**32
+    # (1) sampled voxels around the block vs brute force (half-voxel lattice, d^4 quirk)
+    prob = torch.as_tensor(_DevArray(g.device_ptr(), (sz, sy, sx), "<f4"), device="cuda:0")
+    q = lo + np.stack([rng.randint(-20, 220, 3000), rng.randint(-20, 220, 3000), rng.randint(-20, 100, 3000)], 1)
+    q = q[(q[:, 0] < sx) & (q[:, 1] < sy) & (q[:, 2] < sz)]
+    qi = torch.as_tensor(q, device="cuda:0")
+    got = prob[qi[:, 2], qi[:, 1], qi[:, 0]].cpu().numpy()
+    occ = np.zeros((80, 200, 200), np.bool_)
+    occ[vox[:, 2] - lo[2], vox[:, 1] - lo[1], vox[:, 0] - lo[0]] = True
+    zz, yy, xx = np.nonzero(occ)
+    sites = 2 * (np.stack([xx, yy, zz], 1) + lo) + 1
+    c1 = np.float32(1.0 / (sigma * np.sqrt(2 * np.pi)))
+    c2 = np.float32(1.0 / (2 * sigma * sigma))
+    want = np.zeros(q.shape[0], np.float32)
+    for k in range(q.shape[0]):
+        d = sites - 2 * q[k]
+        near = np.abs(d).max(1) <= 40
+        if not near.any():
+            continue
+        d2 = (d[near].astype(np.int64) ** 2).sum(1).min()
+        dist = np.float32(np.float64(d2) * (resol / 2) ** 2)
+        want[k] = c1 * np.exp(np.float32(-(dist * dist) * c2), dtype=np.float32)
+    assert (want > 0).sum() > 500 and (want == 0).sum() > 100
+    assert np.array_equal(got == 0, want == 0)
+    assert np.allclose(got[want > 0], want[want > 0], rtol=2e-6, atol=0)
+    # (2) particles in that corner, cloud = the block's own points seen from the pose
+    pose = np.array([385.0, 385.0, 33.0, 0.0, 0.0, 0.3], np.float32)
+    n = 8192
+    P = np.zeros((n, 7), np.float32)
+    P[:, :6] = pose + rng.normal(0, 1, (n, 6)).astype(np.float32) * np.array([0.5, 0.5, 0.4, 0.2, 0.2, 0.4], np.float32)
+    world = (vox[rng.choice(vox.shape[0], 3000, replace=False)] + 0.5) * resol
+    cy, sy_ = np.cos(0.3), np.sin(0.3)
+    R = np.array([[cy, -sy_, 0], [sy_, cy, 0], [0, 0, 1]])
+    cloud = ((world - pose[:3].astype(np.float64)) @ R).astype(np.float32)
+    pf = ParticleFilter(g)
+    pf.p_ = P
+    n_in = pf.update(cloud, count=True)
+    two = pf.p_[:, 6].copy()
+    assert n_in > 0.3 * n * cloud.shape[0] and (two > 0).mean() > 0.9
+    pf.set_two_phase(False)
+    pf.p_ = P
+    assert pf.update(cloud, count=True) == n_in
+    assert np.array_equal(bits(pf.p_[:, 6]), bits(two))
+    g.useCodes(False)
+    lin = ParticleFilter(g)
+    lin.p_ = P
+    assert lin.update(cloud, count=True) == n_in
+    assert np.array_equal(bits(lin.p_[:, 6]), bits(two))

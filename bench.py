@@ -41,9 +41,12 @@ WORKLOADS = {
     # config 5 with the grid size BASELINE.json quotes (~2.6 GB replica = 4000 x 4000 x 40 voxels, i.e. 4 m tall):
     # cloud + 8 UWB range beacons fused, 1 M particles in total (strong).  The literal 400 x 400 x 40 m box is 25.6 GB.
     "C5s": ((400.0, 400.0, 4.0), 0.1, 1_000_000, 20_000, 30.0),
+    # the literal config-5 box: 4000 x 4000 x 400 voxels = 6.4e9 cells (25.6 GB f32, 8.6 GB coded), addresses beyond 2^32.
+    # Building the synthetic map takes minutes and ~40 GB of host memory per rank: meant for 1 GPU.
+    "C5": ((400.0, 400.0, 40.0), 0.1, 1_000_000, 20_000, 30.0),
 }
-STRONG = {"C4", "C5s"}
-BEACONS = {"C5s"}
+STRONG = {"C4", "C5s", "C5"}
+BEACONS = {"C5s", "C5"}
 
 
 def parse():

@@ -307,6 +307,8 @@ int amcl3d_b200_grid_create(int device, amcl3d_b200_grid_t* out)
   if (!g)
     return fail(AMCL3D_B200_ERR_ARG, "out of host memory");
   g->device = device;
+  if (const char* env = getenv("AMCL3D_B200_EDT_FAST"))
+    set_edt_fast_passes(atoi(env) != 0);
   if (const char* env = getenv("AMCL3D_B200_CODES"))
     g->use_codes = atoi(env) != 0;
   {

@@ -189,6 +189,7 @@ struct CodedGrid
 };
 // full build: EDT (+ optional kept distances) and fused Gaussian into prob (device, n_cells floats);
 // coded (nullable) additionally receives the dictionary-coded bricked copy (caller frees codes / lut)
+void set_edt_fast_passes(int enable);  // 1 (default): capped window passes when the exact EDT is not kept
 cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t stride, uint64_t n, double sensor_dev,
                            int mode, int sub, float* prob, int32_t** keep_d2, CodedGrid* coded, cudaStream_t stream,
                            char* err, size_t errlen);

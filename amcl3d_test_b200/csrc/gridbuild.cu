@@ -400,6 +400,111 @@ __global__ void __launch_bounds__(256) envelope_kernel(const TIn* __restrict__ i
   }
 }
 
+// ---- capped lower envelope by direct search -------------------------------------------------------------
+// The field only needs min(d2, cap): cap = the smallest squared distance whose probability is exactly 0.0f, a few
+// dozen lattice steps (34 half-voxels at sigma = 0.05 m).  Below cap the minimising site is within R = floor(sqrt(cap-1))
+// lattice steps along every axis, so  out[i] = min(cap, min_{|sub*(i-j)-par| <= R} in[j] + (sub*i-(sub*j+par))^2)  equals
+// min(exact, cap) -- no stacks, no divisions, every access coalesced, inputs staged once per tile in shared memory.
+// Layout as envelope_kernel: in [plane][j][col], out [plane][i][col].  Used when the caller does not keep the EDT.
+constexpr int kWinTX = 64;    // columns per block
+constexpr int kWinTI = 32;    // outputs per column per block
+constexpr int kWinPer = 8;    // outputs per thread (256 threads = 64 columns x 4 groups of 8)
+constexpr int kWinMaxW = 44;  // widest window (sites on each side) the tile is sized for (31 KB of shared memory)
+constexpr int32_t kBig = 1 << 28;
+
+__device__ __forceinline__ int32_t win_load(const uint16_t* in, uint64_t idx, int32_t cap, bool squared)
+{
+  const int32_t v = (int32_t)in[idx];
+  if (squared)
+    return v == (int32_t)kInf16 ? kBig : v * v;  // x pass output: |dx|
+  return v >= cap ? kBig : v;                    // y pass output: already min(., cap)
+}
+
+template <bool kFinal>
+__global__ void __launch_bounds__(256)
+    window_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out16, const __grid_constant__ PassArgs A,
+                  int32_t cap, int W, const __grid_constant__ FinalArgs F)
+{
+  __shared__ int32_t tile[kWinTI + 2 * kWinMaxW + 2][kWinTX];
+  const uint64_t col_tiles = (A.ncol + kWinTX - 1) / kWinTX;
+  const uint64_t i_tiles = ((uint64_t)A.len_out + kWinTI - 1) / kWinTI;
+  uint64_t b = blockIdx.x;
+  const uint64_t ct = b % col_tiles;
+  b /= col_tiles;
+  const uint64_t it = b % i_tiles;
+  const uint64_t plane = b / i_tiles;
+  const int tx = threadIdx.x & (kWinTX - 1), ty = threadIdx.x / kWinTX;
+  const uint64_t col = ct * kWinTX + tx;
+  const int i0 = (int)it * kWinTI;
+  const int j_lo = max(0, i0 - W - 1);
+  const int j_hi = min(A.len_in - 1, i0 + kWinTI - 1 + W + 1);
+  const int rows = j_hi - j_lo + 1;
+  const uint16_t* src = in + plane * (uint64_t)A.len_in * A.ncol;
+  for (int r = ty; r < rows; r += 256 / kWinTX)
+    tile[r][tx] = col < A.ncol ? win_load(src, (uint64_t)(j_lo + r) * A.ncol + col, cap, !kFinal) : kBig;
+  __syncthreads();
+  if (col >= A.ncol)
+    return;
+  const int ib = i0 + ty * kWinPer;  // first output of this thread
+  int32_t best[kWinPer];
+#pragma unroll
+  for (int k = 0; k < kWinPer; ++k)
+    best[k] = cap;
+  // rows that can matter for outputs ib .. ib+kWinPer-1
+  const int r0 = max(ib - W - 1, j_lo) - j_lo, r1 = min(ib + kWinPer - 1 + W + 1, j_hi) - j_lo;
+  for (int r = r0; r <= r1; ++r)
+  {
+    const int32_t v = tile[r][tx];
+    if (v >= cap)
+      continue;
+    const int d = A.sub * (ib - (j_lo + r)) - A.par;  // offset of output ib from site j
+#pragma unroll
+    for (int k = 0; k < kWinPer; ++k)
+    {
+      const int off = d + A.sub * k;
+      best[k] = min(best[k], v + off * off);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kWinPer; ++k)
+  {
+    const int i = ib + k;
+    if (i >= A.len_out)
+      break;
+    int32_t d2 = best[k];  // = min(exact, cap)
+    const uint64_t o = plane * (uint64_t)A.len_out * A.ncol + (uint64_t)i * A.ncol + col;
+    if (!kFinal)
+    {
+      out16[o] = (uint16_t)d2;
+      continue;
+    }
+    if (F.prev != nullptr)
+      d2 = min(d2, F.prev[o]);
+    if (F.enabled)
+    {
+      if (F.nsparse > 0)
+      {
+        const long long qx = (long long)A.sub * (long long)(col % (uint64_t)F.sx);
+        const long long qy = (long long)A.sub * (long long)(col / (uint64_t)F.sx);
+        const long long qz = (long long)A.sub * i;
+        for (int sidx = 0; sidx < F.nsparse; ++sidx)
+        {
+          const int4 h = F.sparse[sidx];
+          const long long dx = qx - h.x, dy = qy - h.y, dz = qz - h.z;
+          const long long dd = dx * dx + dy * dy + dz * dz;
+          if (dd < (long long)d2)
+            d2 = (int32_t)dd;
+        }
+      }
+      F.prob[o] = prob_of(F.g, d2);  // prob_of(cap) is exactly 0 by the definition of cap
+      if (F.d2_out != nullptr)
+        F.d2_out[o] = d2;
+    }
+    else
+      F.d2_out[o] = d2;
+  }
+}
+
 // no dense class at all: brute force over the sparse sites only
 __global__ void sparse_only_kernel(uint64_t cells, int sx, int sy, int sub, const int4* __restrict__ sparse, int nsparse,
                                    const __grid_constant__ Gauss g, float* __restrict__ prob, int32_t* __restrict__ d2_out)
@@ -570,6 +675,29 @@ cudaError_t build_grid_splat(const MapDev& map, const float* d_xyz, uint32_t str
   return cudaGetLastError();
 }
 
+// smallest squared lattice distance whose probability is exactly 0.0f; 0xFFFFFFFF if there is none below the limit
+static cudaError_t find_cap(const Gauss& G, unsigned int* h_cap, cudaStream_t stream)
+{
+  const uint32_t kLimit = 1u << 22;
+  unsigned int* d_cap = nullptr;
+  *h_cap = 0xFFFFFFFFu;
+  cudaError_t rc = cudaMalloc(&d_cap, sizeof(unsigned int));
+  if (rc != cudaSuccess)
+    return rc;
+  rc = cudaMemcpyAsync(d_cap, h_cap, sizeof(unsigned int), cudaMemcpyHostToDevice, stream);
+  if (rc == cudaSuccess)
+  {
+    find_cap_kernel<<<kLimit / 256, 256, 0, stream>>>(G, kLimit, d_cap);
+    rc = cudaGetLastError();
+  }
+  if (rc == cudaSuccess)
+    rc = cudaMemcpyAsync(h_cap, d_cap, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream);
+  if (rc == cudaSuccess)
+    rc = cudaStreamSynchronize(stream);
+  cudaFree(d_cap);
+  return rc;
+}
+
 // Builds the dictionary-coded, bricked copy of the field from the linear int32 distance transform.
 // On success out->rep is kRepCode8 / kRepCode16; kRepFloat (no allocation) if the field has too many
 // distinct values for 16-bit codes or never underflows to zero inside the probed range.
@@ -583,8 +711,6 @@ static cudaError_t build_codes(const MapDev& map, const int32_t* d_d2, const Gau
   out->lut_n = 0;
   const uint32_t sx = map.size[0], sy = map.size[1], sz = map.size[2];
   const uint64_t cells = (uint64_t)sx * sy * sz;
-  const uint32_t kLimit = 1u << 22;
-  unsigned int* d_cap = nullptr;
   uint8_t* d_present = nullptr;
   uint16_t* d_rank = nullptr;
   int32_t* d_values = nullptr;
@@ -595,12 +721,7 @@ static cudaError_t build_codes(const MapDev& map, const int32_t* d_d2, const Gau
   std::vector<uint16_t> rank;
   std::vector<int32_t> values;
 
-  CK(cudaMalloc(&d_cap, sizeof(unsigned int)));
-  CK(cudaMemcpyAsync(d_cap, &h_cap, sizeof(h_cap), cudaMemcpyHostToDevice, stream));
-  find_cap_kernel<<<kLimit / 256, 256, 0, stream>>>(G, kLimit, d_cap);
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(&h_cap, d_cap, sizeof(h_cap), cudaMemcpyDeviceToHost, stream));
-  CK(cudaStreamSynchronize(stream));
+  CK(find_cap(G, &h_cap, stream));
   if (h_cap == 0xFFFFFFFFu)
     goto done;  // the Gaussian never reaches 0.0f: keep the float grid
   {
@@ -658,13 +779,18 @@ static cudaError_t build_codes(const MapDev& map, const int32_t* d_d2, const Gau
     d_lut = nullptr;
   }
 done:
-  cudaFree(d_cap);
   cudaFree(d_present);
   cudaFree(d_rank);
   cudaFree(d_values);
   cudaFree(d_codes);
   cudaFree(d_lut);
   return rc;
+}
+
+static int g_fast_passes = 1;  // AMCL3D_B200_EDT_FAST=0 (read by the C-ABI) forces the exact envelope passes
+void set_edt_fast_passes(int enable)
+{
+  g_fast_passes = enable;
 }
 
 cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t stride, uint64_t n, double sensor_dev,
@@ -698,6 +824,7 @@ cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t strid
   unsigned int* d_sparse_count = nullptr;
   uint16_t* d_d1 = nullptr;
   int32_t* d_dxy = nullptr;
+  uint16_t* d_dxy16 = nullptr;
   int32_t* d_d2 = nullptr;
   int2* d_stack = nullptr;
   unsigned long long h_counts[8] = { 0 };
@@ -760,10 +887,31 @@ cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t strid
       const uint64_t bits_words = rows * L.words_per_row;
       CK(cudaMalloc(&d_bits, sizeof(uint32_t) * bits_words));
       CK(cudaMalloc(&d_d1, sizeof(uint16_t) * rows * (uint64_t)sx));
-      CK(cudaMalloc(&d_dxy, sizeof(int32_t) * (uint64_t)sx * sy * L.w[2]));
+      // Fast passes when only the field is wanted (the exact transform is not kept): min(d2, cap) by direct search
+      // inside the window the cap allows.  Falls back to the exact envelopes when the caller keeps the EDT, when the
+      // probability never reaches 0.0f, or when the window would be wide (large sigma / fine lattice).
+      unsigned int h_cap = 0xFFFFFFFFu;
+      int win = 0;
+      if (keep_d2 == nullptr && g_fast_passes)
+      {
+        CK(find_cap(G, &h_cap, stream));
+        if (h_cap != 0xFFFFFFFFu && h_cap >= 1 && h_cap < 65535u)
+        {
+          const int R = (int)floor(sqrt((double)(h_cap - 1)));
+          win = R / sub + 1;
+          if (win > kWinMaxW)
+            win = 0;
+        }
+      }
       const uint64_t nthreads = 148ull * 1024ull;
       const int maxlen = (L.w[1] > L.w[2] ? L.w[1] : L.w[2]);
-      CK(cudaMalloc(&d_stack, sizeof(int2) * nthreads * (uint64_t)maxlen));
+      if (win > 0)
+        CK(cudaMalloc(&d_dxy16, sizeof(uint16_t) * (uint64_t)sx * sy * L.w[2]));
+      else
+      {
+        CK(cudaMalloc(&d_dxy, sizeof(int32_t) * (uint64_t)sx * sy * L.w[2]));
+        CK(cudaMalloc(&d_stack, sizeof(int2) * nthreads * (uint64_t)maxlen));
+      }
 
       for (int k = 0; k < ndense; ++k)
       {
@@ -780,38 +928,50 @@ cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t strid
           CK(cudaGetLastError());
         }
         FinalArgs F0{};
+        PassArgs Ay, Az;
+        Ay.ncol = (uint64_t)sx;
+        Ay.nplane = (uint32_t)L.w[2];
+        Ay.len_in = L.w[1];
+        Ay.len_out = sy;
+        Ay.sub = sub;
+        Ay.par = py;
+        Ay.nthreads = nthreads;
+        Az.ncol = (uint64_t)sx * sy;
+        Az.nplane = 1;
+        Az.len_in = L.w[2];
+        Az.len_out = sz;
+        Az.sub = sub;
+        Az.par = pz;
+        Az.nthreads = nthreads;
+        FinalArgs F{};
+        F.enabled = last ? 1 : 0;
+        F.prev = (k > 0) ? d_d2 : nullptr;
+        F.d2_out = d_d2;  // null only when single class and !keep
+        F.prob = prob;
+        F.sparse = d_sparse;
+        F.nsparse = last ? (int)h_nsparse : 0;
+        F.sx = sx;
+        F.sy = sy;
+        F.g = G;
+        if (win > 0)
         {
-          PassArgs A;
-          A.ncol = (uint64_t)sx;
-          A.nplane = (uint32_t)L.w[2];
-          A.len_in = L.w[1];
-          A.len_out = sy;
-          A.sub = sub;
-          A.par = py;
-          A.nthreads = nthreads;
-          envelope_kernel<uint16_t, false><<<(unsigned)(nthreads / 256), 256, 0, stream>>>(d_d1, d_dxy, A, d_stack, F0);
+          const uint64_t by = (uint64_t)Ay.nplane * ((Ay.len_out + kWinTI - 1) / kWinTI) * ((Ay.ncol + kWinTX - 1) / kWinTX);
+          const uint64_t bz = (uint64_t)Az.nplane * ((Az.len_out + kWinTI - 1) / kWinTI) * ((Az.ncol + kWinTX - 1) / kWinTX);
+          if (by > 0x7FFFFFFFull || bz > 0x7FFFFFFFull)
+          {
+            rc = cudaErrorInvalidValue;
+            goto done;
+          }
+          window_kernel<false><<<(unsigned)by, 256, 0, stream>>>(d_d1, d_dxy16, Ay, (int32_t)h_cap, win, F0);
+          CK(cudaGetLastError());
+          window_kernel<true><<<(unsigned)bz, 256, 0, stream>>>(d_dxy16, nullptr, Az, (int32_t)h_cap, win, F);
           CK(cudaGetLastError());
         }
+        else
         {
-          PassArgs A;
-          A.ncol = (uint64_t)sx * sy;
-          A.nplane = 1;
-          A.len_in = L.w[2];
-          A.len_out = sz;
-          A.sub = sub;
-          A.par = pz;
-          A.nthreads = nthreads;
-          FinalArgs F{};
-          F.enabled = last ? 1 : 0;
-          F.prev = (k > 0) ? d_d2 : nullptr;
-          F.d2_out = d_d2;  // null only when single class and !keep
-          F.prob = prob;
-          F.sparse = d_sparse;
-          F.nsparse = last ? (int)h_nsparse : 0;
-          F.sx = sx;
-          F.sy = sy;
-          F.g = G;
-          envelope_kernel<int32_t, true><<<(unsigned)(nthreads / 256), 256, 0, stream>>>(d_dxy, nullptr, A, d_stack, F);
+          envelope_kernel<uint16_t, false><<<(unsigned)(nthreads / 256), 256, 0, stream>>>(d_d1, d_dxy, Ay, d_stack, F0);
+          CK(cudaGetLastError());
+          envelope_kernel<int32_t, true><<<(unsigned)(nthreads / 256), 256, 0, stream>>>(d_dxy, nullptr, Az, d_stack, F);
           CK(cudaGetLastError());
         }
       }
@@ -824,6 +984,8 @@ cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t strid
     d_d1 = nullptr;
     cudaFree(d_dxy);
     d_dxy = nullptr;
+    cudaFree(d_dxy16);
+    d_dxy16 = nullptr;
     cudaFree(d_stack);
     d_stack = nullptr;
     if (coded != nullptr)
@@ -844,6 +1006,7 @@ done:
   cudaFree(d_sparse_count);
   cudaFree(d_d1);
   cudaFree(d_dxy);
+  cudaFree(d_dxy16);
   cudaFree(d_d2);
   cudaFree(d_stack);
   return rc;

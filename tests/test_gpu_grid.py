@@ -111,3 +111,43 @@ def test_grid_file_roundtrip(O, world_c1, gpu_c1, tmp_path):
     assert not g.loadGrid(tmp_path / "missing.grid", 0.05)
     with pytest.raises(RuntimeError):
         g.computePointCloud(np.zeros((1, 3), np.float32), 0.1)  # PointCloudTools.cpp:89-91
+
+
+@pytest.mark.parametrize("lattice,sub", [("centre", 2), ("corner", 1), ("corner", 2), ("mixed", 2)])
+@pytest.mark.parametrize("sigma,mode", [(0.05, 0), (0.12, 0), (0.05, 1), (0.2, 1), (0.6, 0)])
+def test_capped_window_passes_give_the_same_field(O, lattice, sub, sigma, mode):
+    """When the exact transform is not kept the y/z passes search only the window the expf underflow allows
+    (min(d2, cap)); the float grid must be the same bits as the one the exact envelope passes write -- for small and
+    wide windows, both Gaussians, and the fallback when the window is too wide (sigma 0.6)."""
+    from amcl3d_test_b200 import Grid3d
+
+    pts, m = _small_map(O, lattice=lattice)
+    mode = O.GRID_QUIRK if mode == 0 else O.GRID_GAUSSIAN
+    g = Grid3d(0)
+    g.computePointCloud(pts, m.resol)
+    g.computeGrid(pts, sigma, mode=mode, sub=sub, keep_edt=True)   # exact envelopes
+    exact = g.downloadGrid()
+    rep_exact = g.info()["rep"]
+    g.computeGrid(pts, sigma, mode=mode, sub=sub)                  # capped windows (or the fallback)
+    fast = g.downloadGrid()
+    assert np.array_equal(bits(fast), bits(exact))
+    assert g.info()["rep"] == rep_exact
+    assert (exact > 0).any()
+
+
+def test_capped_window_passes_c1_update_bits(O, world_c1):
+    """C1 map through the fast passes: the coded grid drives update() to the oracle's bits."""
+    from amcl3d_test_b200 import Grid3d, ParticleFilter
+
+    w = world_c1
+    g = Grid3d(0)
+    g.computePointCloud(w["synth"].points, 0.1)
+    g.computeGrid(w["synth"].points, 0.05, sub=2)
+    prob = g.downloadGrid()
+    assert np.allclose(prob, w["prob"], rtol=1e-6, atol=1e-30) and np.array_equal(prob == 0, w["prob"] == 0)
+    m = O.Map(w["map"].mn, w["map"].mx, 0.1, 0.05, prob=prob)
+    pf = ParticleFilter(g)
+    pf.p_ = w["T"]
+    pf.update(w["cloud"])
+    ref = O.update(m, O.particles(w["T"]), w["cloud"])
+    assert np.array_equal(bits(pf.p_[:, 6]), bits(ref[:, 6]))

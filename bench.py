@@ -360,15 +360,13 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local_rank)
-    if os.environ.get("AMCL3D_BENCH_NO_SAMPLER") != "1":
-        sampler.start()
+    sampler.start()
     l0 = shard.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # the resident loop runs in stream order (amcl3d_b200_pf_set_async): no host wait between the stages of a step or
     # between steps; the update's share is taken from event pairs recorded on the same stream, read after the loop
     ev_u = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     shard.set_async(True)
-    sync_every = int(os.environ.get("AMCL3D_BENCH_SYNC_EVERY", "0"))
     dbg = os.environ.get("AMCL3D_BENCH_DEBUG") == "1"
     ev_d = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)] if dbg else []
     torch.cuda.synchronize()
@@ -384,8 +382,6 @@ def run_b200(args):
         mean_dev = filt.mean_device()
         if dbg:
             ev_d[k][1].record(stream)
-        if sync_every and (k + 1) % sync_every == 0:
-            stream.synchronize()
     e1.record(stream)
     torch.cuda.synchronize()
     shard.set_async(False)

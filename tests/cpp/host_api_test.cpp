@@ -244,6 +244,45 @@ int main(int argc, char** argv)
     PointType h = mcl.getMapHeight(P[0].x, P[0].y);
     const float hv[3] = { h.x, h.y, h.z };
     dump("mcl_map_height", hv, 1, 3);
+    // RelocPose (amcl3d.cpp:165-181: z from the nearest keypose, init deviations, global particle window) and PFMove
+    {
+      auto& lp = mcl.localization_params_;
+      lp.init_x_dev_ = 0.5;
+      lp.init_y_dev_ = 0.5;
+      lp.init_z_dev_ = 0.4;
+      lp.init_roll_dev_ = 0.2;
+      lp.init_pitch_dev_ = 0.2;
+      lp.init_yaw_dev_ = 0.4;
+      lp.max_particle_num_global = 3000;
+      lp.min_particle_num_global = 900;
+      const int n_rel = 300;
+      const float dev[6] = { 0.5f, 0.5f, 0.4f, 0.2f, 0.2f, 0.4f };
+      std::mt19937 peek(seed + 7);
+      std::vector<float> noise(6ull * (n_rel - 1));
+      for (int i = 0; i + 1 < n_rel; ++i)
+        for (int k = 0; k < 6; ++k)
+        {
+          std::normal_distribution<float> d(0, (double)dev[k]);
+          noise[6 * i + k] = d(peek);
+        }
+      dump("mcl_reloc_noise", noise.data(), n_rel - 1, 6);
+      mcl.setSeed(seed + 7);
+      mcl.RelocPose(n_rel, P[0].x, P[0].y, /*ignored*/ 123.f, 0.f, 0.f, 0.3f);
+      dump_particles("mcl_after_reloc", mcl.p_);
+      if (mcl.globalLocalizationDone())
+        return 7;
+      const float nd[6] = { 0.1f, 0.1f, 0.05f, 0.05f, 0.05f, 0.05f };
+      std::vector<float> pnoise(6ull * n_rel);
+      for (int i = 0; i < n_rel; ++i)
+        for (int k = 0; k < 6; ++k)
+        {
+          std::normal_distribution<float> d(0, (double)nd[k]);
+          pnoise[6 * i + k] = d(peek);
+        }
+      dump("mcl_move_noise", pnoise.data(), n_rel, 6);
+      mcl.PFMove(Particle(0.31f, -0.12f, 0.02f, 0.001f, -0.002f, 0.05f), Particle(nd[0], nd[1], nd[2], nd[3], nd[4], nd[5]));
+      dump_particles("mcl_after_move", mcl.p_);
+    }
     // the input downsample (amcl3d.cpp:37,51-52) and the update on the resident filtered cloud
     mcl.setVoxelSize(0.3);
     pcl::PointCloud<PointType> cloud_ds;

@@ -126,6 +126,14 @@ def test_cpp_classes_match_the_oracle(O, tmp_path):
     O.update_sample_height(Z, kp)
     assert np.array_equal(bits(d["mcl_after_height"]), bits(Z))
     assert np.array_equal(bits(d["mcl_after_pfresample"]), bits(O.pf_resample_step(m, W.copy(), 1, 150, 400, kp)))
+    # RelocPose: z of the nearest keypose replaces the given z (amcl3d.cpp:169-174), then ParticleFilter::relocPose
+    q = np.array([P[0, 0], P[0, 1], 0.0], np.float32)
+    nearest = kp[np.argmin(((kp - q) ** 2).astype(np.float32).sum(1))]
+    init = np.array([P[0, 0], P[0, 1], nearest[2], 0.0, 0.0, 0.3], np.float32)
+    R2, _ = O.reloc_pose(300, init, np.array([0.5, 0.5, 0.4, 0.2, 0.2, 0.4], np.float32), d["mcl_reloc_noise"].reshape(-1))
+    assert np.array_equal(bits(d["mcl_after_reloc"]), bits(R2))
+    Q2 = O.predict(R2.copy(), np.array([0.31, -0.12, 0.02, 0.001, -0.002, 0.05], np.float32).astype(np.float64), d["mcl_move_noise"].reshape(-1))
+    assert np.array_equal(bits(d["mcl_after_move"]), bits(Q2))
     # input downsample through the C++ class (to_cloud() of the driver sets intensity = i % 5)
     raw = np.concatenate([cloud, (np.arange(cloud.shape[0]) % 5).astype(np.float32)[:, None]], 1)
     ds = O.voxel_filter(raw, 0.3, ioff=3)

@@ -446,10 +446,12 @@ __global__ void __launch_bounds__(256)
   if (col >= A.ncol)
     return;
   const int ib = i0 + ty * kWinPer;  // first output of this thread
+  // candidate of site j for output ib + k:  v + (d + sub*k)^2 = (v + d^2) + k*(2*sub*d) + sub^2*k^2  with d the offset
+  // of output ib; the last term does not depend on the site, so it is added after the search (2 ops per pair)
   int32_t best[kWinPer];
 #pragma unroll
   for (int k = 0; k < kWinPer; ++k)
-    best[k] = cap;
+    best[k] = cap - A.sub * A.sub * k * k;
   // rows that can matter for outputs ib .. ib+kWinPer-1
   const int r0 = max(ib - W - 1, j_lo) - j_lo, r1 = min(ib + kWinPer - 1 + W + 1, j_hi) - j_lo;
   for (int r = r0; r <= r1; ++r)
@@ -457,14 +459,15 @@ __global__ void __launch_bounds__(256)
     const int32_t v = tile[r][tx];
     if (v >= cap)
       continue;
-    const int d = A.sub * (ib - (j_lo + r)) - A.par;  // offset of output ib from site j
+    const int d = A.sub * (ib - (j_lo + r)) - A.par;
+    const int32_t a = v + d * d, bb = 2 * A.sub * d;
 #pragma unroll
     for (int k = 0; k < kWinPer; ++k)
-    {
-      const int off = d + A.sub * k;
-      best[k] = min(best[k], v + off * off);
-    }
+      best[k] = min(best[k], a + k * bb);
   }
+#pragma unroll
+  for (int k = 0; k < kWinPer; ++k)
+    best[k] += A.sub * A.sub * k * k;
 #pragma unroll
   for (int k = 0; k < kWinPer; ++k)
   {
@@ -484,16 +487,15 @@ __global__ void __launch_bounds__(256)
     {
       if (F.nsparse > 0)
       {
-        const long long qx = (long long)A.sub * (long long)(col % (uint64_t)F.sx);
-        const long long qy = (long long)A.sub * (long long)(col / (uint64_t)F.sx);
-        const long long qz = (long long)A.sub * i;
+        // lattice coordinates stay below 26000 (checked by the host), so three squared differences fit an int32
+        const int qx = A.sub * (int)(col % (uint64_t)F.sx);
+        const int qy = A.sub * (int)(col / (uint64_t)F.sx);
+        const int qz = A.sub * i;
         for (int sidx = 0; sidx < F.nsparse; ++sidx)
         {
           const int4 h = F.sparse[sidx];
-          const long long dx = qx - h.x, dy = qy - h.y, dz = qz - h.z;
-          const long long dd = dx * dx + dy * dy + dz * dz;
-          if (dd < (long long)d2)
-            d2 = (int32_t)dd;
+          const int dx = qx - h.x, dy = qy - h.y, dz = qz - h.z;
+          d2 = min(d2, dx * dx + dy * dy + dz * dz);
         }
       }
       F.prob[o] = prob_of(F.g, d2);  // prob_of(cap) is exactly 0 by the definition of cap
@@ -597,23 +599,48 @@ __global__ void lut_kernel(const __grid_constant__ Gauss g, const int32_t* __res
   if (c < n)
     lut[c] = prob_of(g, values[c]);
 }
-// one thread per code slot, in coded (output) order
+// one thread per four consecutive code slots (four x-neighbours of one brick row), in coded (output) order
 template <typename TCode, int kRep>
 __global__ void encode_kernel(const int32_t* __restrict__ d2, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t nbx, uint32_t nby,
                               uint64_t slots, uint32_t cap, const uint16_t* __restrict__ rank, TCode* __restrict__ codes)
 {
-  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t t = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (t >= slots)
     return;
   uint32_t ix, iy, iz;
-  coded_voxel<kRep>(t, nbx, nby, ix, iy, iz);
-  uint32_t k = cap;  // padding voxels: the zero class (never addressed by the kernel)
-  if (ix < sx && iy < sy && iz < sz)
+  coded_voxel<kRep>(t, nbx, nby, ix, iy, iz);  // ix is a multiple of 4; slots t+1..t+3 are ix+1..ix+3
+  uint32_t k[4] = { cap, cap, cap, cap };      // padding voxels: the zero class (never addressed by the kernel)
+  if (iy < sy && iz < sz && ix < sx)
   {
-    const int32_t v = d2[(uint64_t)ix + (uint64_t)iy * sx + (uint64_t)iz * sx * sy];
-    k = (v < 0 || (uint32_t)v > cap) ? cap : (uint32_t)v;
+    const uint64_t base = (uint64_t)ix + (uint64_t)iy * sx + (uint64_t)iz * sx * sy;
+    int32_t v[4] = { -1, -1, -1, -1 };
+    if (ix + 3 < sx && (base & 3) == 0)
+    {
+      const int4 q = *reinterpret_cast<const int4*>(d2 + base);
+      v[0] = q.x;
+      v[1] = q.y;
+      v[2] = q.z;
+      v[3] = q.w;
+    }
+    else
+    {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (ix + e < sx)
+          v[e] = d2[base + e];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      k[e] = (v[e] < 0 || (uint32_t)v[e] > cap) ? cap : (uint32_t)v[e];
   }
-  codes[t] = (TCode)rank[k];
+  TCode out[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    out[e] = (TCode)rank[k[e]];
+  if constexpr (sizeof(TCode) == 1)
+    *reinterpret_cast<uchar4*>(codes + t) = make_uchar4(out[0], out[1], out[2], out[3]);
+  else
+    *reinterpret_cast<ushort4*>(codes + t) = make_ushort4(out[0], out[1], out[2], out[3]);
 }
 
 void gauss_consts(double sensor_dev, float* c1, float* c2)
@@ -760,10 +787,10 @@ static cudaError_t build_codes(const MapDev& map, const int32_t* d_d2, const Gau
     lut_kernel<<<(nvals + 255) / 256, 256, 0, stream>>>(G, d_values, nvals, d_lut);
     CK(cudaGetLastError());
     if (small)
-      encode_kernel<uint8_t, kRepCode8><<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(d_d2, sx, sy, sz, nbx, nby, slots, cap,
+      encode_kernel<uint8_t, kRepCode8><<<(unsigned)((slots / 4 + 255) / 256), 256, 0, stream>>>(d_d2, sx, sy, sz, nbx, nby, slots, cap,
                                                                                            d_rank, (uint8_t*)codes_aligned);
     else
-      encode_kernel<uint16_t, kRepCode16><<<(unsigned)((slots + 255) / 256), 256, 0, stream>>>(d_d2, sx, sy, sz, nbx, nby, slots,
+      encode_kernel<uint16_t, kRepCode16><<<(unsigned)((slots / 4 + 255) / 256), 256, 0, stream>>>(d_d2, sx, sy, sz, nbx, nby, slots,
                                                                                              cap, d_rank, (uint16_t*)codes_aligned);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(stream));

@@ -157,6 +157,7 @@ __global__ void voxelize_kernel(const __grid_constant__ Lattice L, const float* 
 // nearest site j in the row, kInf16 if the row is empty.
 __global__ void __launch_bounds__(256)
     xpass_kernel(const uint32_t* __restrict__ bits, uint32_t words_per_row, uint64_t rows, int sx, int wx, int sub, int par,
+                 int max_scan_words /* how many further words to look at on each side (capped passes: the window) */,
                  uint16_t* __restrict__ d1)
 {
   const uint32_t chunks = (uint32_t)((sx + 31) / 32);
@@ -177,7 +178,8 @@ __global__ void __launch_bounds__(256)
       left = (int)(wq * 32u) + 31 - __clz(m);
     else
     {
-      for (int w = (int)wq - 1; w >= 0; --w)
+      const int w_stop = max(0, (int)wq - max_scan_words);
+      for (int w = (int)wq - 1; w >= w_stop; --w)
       {
         const uint32_t v = r[w];
         if (v)
@@ -195,7 +197,8 @@ __global__ void __launch_bounds__(256)
       right = (int)(wq * 32u) + __ffs(m) - 1;
     else
     {
-      for (uint32_t w = wq + 1; w < words_per_row; ++w)
+      const uint32_t w_stop = (uint32_t)min((long long)words_per_row, (long long)wq + 1 + max_scan_words);
+      for (uint32_t w = wq + 1; w < w_stop; ++w)
       {
         const uint32_t v = r[w];
         if (v)
@@ -951,7 +954,9 @@ cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t strid
         {
           const uint64_t warps = rows * (uint64_t)((sx + 31) / 32);
           const uint64_t blocks = (warps * 32 + 255) / 256;
-          xpass_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_bits, L.words_per_row, rows, sx, L.w[0], sub, px, d_d1);
+          // capped passes: a site farther than the window along x cannot matter, so the bit scan stops there
+          const int scan_words = win > 0 ? (win + 31) / 32 + 1 : 0x7FFFFFF;
+          xpass_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_bits, L.words_per_row, rows, sx, L.w[0], sub, px, scan_words, d_d1);
           CK(cudaGetLastError());
         }
         FinalArgs F0{};

@@ -119,7 +119,9 @@ int amcl3d_b200_grid_set_map(amcl3d_b200_grid_t g, const double min[3], const do
  * exact Euclidean distance transform on the lattice of pitch resol/sub (sub = 1 or 2; map points are
  * snapped to it, bit-exact with the kd-tree build when they already lie on it) followed by the fused
  * Gaussian writer.  SPLAT takes arbitrary points.  keep_edt != 0 keeps the int32 squared distances
- * (units (resol/sub)^2) for amcl3d_b200_grid_download_edt. */
+ * (units (resol/sub)^2) for amcl3d_b200_grid_download_edt and runs the exact lower-envelope passes; without it
+ * the y / z passes only search the window beyond which the probability is exactly 0.0f (min(d2, cap)) -- the
+ * float grid is the same, bit for bit (environment AMCL3D_B200_EDT_FAST=0 forces the exact passes). */
 int amcl3d_b200_grid_build(amcl3d_b200_grid_t g, const float* xyz, uint32_t stride, uint64_t n,
                            double sensor_dev, int mode, int sub, int keep_edt);
 int amcl3d_b200_grid_download_edt(amcl3d_b200_grid_t g, int32_t* d2, uint64_t cap);

@@ -39,7 +39,7 @@ public:
   void updateDownsampled();
 
   std::vector<Particle> getParticle() { return p_; }
-  const bool globalLocalizationDone() const { return global_loc_done_; }
+  bool globalLocalizationDone() const { return global_loc_done_; }
 
   /*! Reference: amcl3d.cpp:242-288 (default cnt_per_grid = 3 as declared in amcl3d.h). */
   int computeSampleNum(const int cnt_per_grid = 3);

@@ -24,11 +24,6 @@ def device_info(device: int = 0) -> dict:
     return dict(device_count=cnt.value, sm_count=sm.value, cc=(maj.value, mnr.value), l2_bytes=l2.value, mem_bytes=mem.value)
 
 
-def set_chain_mode(mode: int) -> None:
-    """0: exact parallel binade scan (default), 1: serial chain kernel.  Same bits either way."""
-    check(capi.load().amcl3d_b200_set_chain_mode(int(mode)))
-
-
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
@@ -60,6 +55,10 @@ class Grid3d:
                     size=tuple(int(v) for v in gi.size), n_cells=int(gi.n_cells), has_map=bool(gi.has_map),
                     has_grid=bool(gi.has_grid), device=gi.device, rep=gi.rep, lut_n=int(gi.lut_n),
                     coded_bytes=int(gi.coded_bytes))
+
+    def set_edt_fast(self, enable: bool):
+        """A/B switch of the capped build passes (same float grid bit for bit either way)."""
+        check(self._L.amcl3d_b200_grid_set_edt_fast(self._h, int(bool(enable))))
 
     def useCodes(self, enable: bool):
         """A/B switch for the lossless dictionary-coded copy (bit-identical results either way)."""
@@ -222,6 +221,10 @@ class ParticleFilter:
 
     def set_trig_mode(self, mode):
         check(self._L.amcl3d_b200_pf_set_trig_mode(self._h, mode))
+
+    def set_chain_mode(self, mode: int):
+        """0: exact parallel binade scan (default), 1: serial chain kernel, 2: one-CTA scan.  Same bits either way."""
+        check(self._L.amcl3d_b200_pf_set_chain_mode(self._h, int(mode)))
 
     # ---- the path -----------------------------------------------------------------------------
     def set_cloud(self, cloud):

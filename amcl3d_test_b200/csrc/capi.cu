@@ -81,6 +81,7 @@ struct amcl3d_b200_grid_s
   uint64_t edt_cells = 0;
   CodedGrid coded{};       // lossless dictionary-coded copy (rep == kRepFloat: absent)
   int use_codes = 1;       // AMCL3D_B200_CODES=0 or grid_set_option disables it
+  int edt_fast = 1;        // AMCL3D_B200_EDT_FAST=0 or amcl3d_b200_grid_set_edt_fast: exact envelope passes always
   cudaStream_t stream = nullptr;
   amcl3d_b200_pf_t scratch_pf = nullptr;  // for the single-pose computeCloudWeight
 };
@@ -115,7 +116,11 @@ struct amcl3d_b200_pf_s
   uint64_t sort_scratch_cap = 0;
   uint8_t* d_codes_staged = nullptr;
   uint64_t codes_staged_cap = 0;
+  float* d_pose = nullptr;  // per-particle rotation + offsets of the current slice (pose_kernel)
+  uint64_t pose_cap = 0;
   int two_phase = 1;  // AMCL3D_B200_TWO_PHASE=0 / amcl3d_b200_pf_set_two_phase disables
+  bool sorted_valid = false;  // d_sorted holds the Morton order of the cloud currently in d_cloud
+  int chain_mode = 0;         // amcl3d_b200_pf_set_chain_mode
   // scratch
   float* d_prefix = nullptr;
   uint64_t prefix_cap = 0;
@@ -260,11 +265,19 @@ int amcl3d_b200_device_info(int device, int* device_count, int* sm_count, int* c
   return AMCL3D_B200_OK;
 }
 
-int amcl3d_b200_set_chain_mode(int mode)
+int amcl3d_b200_pf_set_chain_mode(amcl3d_b200_pf_t pf, int mode)
 {
-  if (mode < 0 || mode > 2)
+  if (!pf || mode < 0 || mode > 2)
     return fail(AMCL3D_B200_ERR_ARG, "chain mode must be 0, 1 or 2");
-  set_chain_mode(mode);
+  pf->chain_mode = mode;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_grid_set_edt_fast(amcl3d_b200_grid_t g, int enable)
+{
+  if (!g)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+  g->edt_fast = enable != 0;
   return AMCL3D_B200_OK;
 }
 
@@ -308,14 +321,15 @@ int amcl3d_b200_grid_create(int device, amcl3d_b200_grid_t* out)
     return fail(AMCL3D_B200_ERR_ARG, "out of host memory");
   g->device = device;
   if (const char* env = getenv("AMCL3D_B200_EDT_FAST"))
-    set_edt_fast_passes(atoi(env) != 0);
+    g->edt_fast = atoi(env) != 0;
   if (const char* env = getenv("AMCL3D_B200_CODES"))
     g->use_codes = atoi(env) != 0;
+  // The L2 fetch granularity is a per-device limit of the HOST application: it is only touched when asked for
+  // (AMCL3D_B200_L2_FETCH=32|64|128 or amcl3d_b200_set_l2_fetch_granularity).  Measured on B200: no effect on the
+  // DRAM bytes a scattered 1-byte gather costs (profiles/r2_gather_microbench.json).
+  if (const char* env = getenv("AMCL3D_B200_L2_FETCH"))
   {
-    // the weighting kernel uses 1-4 bytes of every line it touches: ask L2 for the smallest DRAM fetch
-    int gran = 32;
-    if (const char* env = getenv("AMCL3D_B200_L2_FETCH"))
-      gran = atoi(env);
+    const int gran = atoi(env);
     if (gran == 32 || gran == 64 || gran == 128)
       (void)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)gran);
     (void)cudaGetLastError();
@@ -524,7 +538,7 @@ int amcl3d_b200_grid_build(amcl3d_b200_grid_t g, const float* xyz, uint32_t stri
       e = build_grid_splat(g->map, d_xyz, stride, n, sensor_dev, g->d_prob, g->stream);
     else
       e = build_grid_edt(g->map, d_xyz, stride, n, sensor_dev, mode, sub, g->d_prob, keep_edt ? &g->d_edt : nullptr,
-                         g->use_codes ? &g->coded : nullptr, g->stream, msg, sizeof(msg));
+                         g->use_codes ? &g->coded : nullptr, g->edt_fast, g->stream, msg, sizeof(msg));
   }
   if (e == cudaSuccess)
     e = cudaStreamSynchronize(g->stream);
@@ -734,6 +748,7 @@ int amcl3d_b200_pf_destroy(amcl3d_b200_pf_t pf)
   cudaFree(pf->d_sorted);
   cudaFree(pf->d_sort_scratch);
   cudaFree(pf->d_codes_staged);
+  cudaFree(pf->d_pose);
   cudaFree(pf->d_prefix);
   cudaFree(pf->d_thr);
   cudaFree(pf->d_wr);
@@ -869,25 +884,33 @@ int amcl3d_b200_pf_device_ptr(amcl3d_b200_pf_t pf, void** d_aos7, uint64_t* n)
   return AMCL3D_B200_OK;
 }
 
+// Morton order of the cloud in d_cloud for the two-phase sweep (keys + radix sort + pack: a few microseconds).
+// Runs at set_cloud when the two-phase path is on, else lazily in update() the first time it is needed.
+static int sort_cloud(amcl3d_b200_pf_t pf)
+{
+  CU(ensure(pf->d_sorted, pf->sorted_cap, pf->npad));
+  const size_t need = sort_cloud_scratch_bytes(pf->npts);
+  CU(ensure(pf->d_sort_scratch, pf->sort_scratch_cap, need));
+  CU(launch_sort_cloud(reinterpret_cast<const float*>(pf->d_cloud), 4, pf->npts, pf->npad, pf->d_sorted, pf->d_sort_scratch,
+                       need, pf->stream));
+  pf->launches += 3;
+  pf->launches += chain_extra_launches_take();
+  pf->sorted_valid = true;
+  return AMCL3D_B200_OK;
+}
+
 static int set_cloud_common(amcl3d_b200_pf_t pf, const float* d_src, uint32_t stride, uint32_t npts)
 {
   const uint32_t npad = (npts + 31u) & ~31u;
   CU(ensure(pf->d_cloud, pf->cloud_cap, npad));
   CU(launch_pack_cloud(d_src, stride, npts, pf->d_cloud, npad, pf->stream));
   pf->launches += npad ? 1 : 0;
-  if (pf->two_phase && npts > 0)
-  {
-    // Morton order of this cloud for the two-phase sweep (keys + radix sort + pack: a few microseconds)
-    CU(ensure(pf->d_sorted, pf->sorted_cap, npad));
-    const size_t need = sort_cloud_scratch_bytes(npts);
-    CU(ensure(pf->d_sort_scratch, pf->sort_scratch_cap, need));
-    CU(launch_sort_cloud(d_src, stride, npts, npad, pf->d_sorted, pf->d_sort_scratch, need, pf->stream));
-    pf->launches += 3;
-    pf->launches += chain_extra_launches_take();
-  }
   pf->npts = npts;
   pf->npad = npad;
   pf->filtered_valid = false;
+  pf->sorted_valid = false;  // d_sorted (if any) belongs to the previous cloud
+  if (pf->two_phase && npts > 0)
+    return sort_cloud(pf);
   return AMCL3D_B200_OK;
 }
 
@@ -980,8 +1003,8 @@ static int fuse_range_async(amcl3d_b200_pf_t pf, const float* d_wr, float alpha)
 {
   // w = alpha*wp/sum(wp) + (1-alpha)*wr/sum(wr): both sums as sequential f32 chains
   CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(pf->n)));
-  CU(launch_chain_prefix(pf->d_p, pf->n, 0, nullptr, pf->d_scalars + 0, pf->d_dense, pf->stream));
-  CU(launch_chain_sum_array(d_wr, pf->n, pf->d_scalars + 1, pf->d_dense, pf->stream));
+  CU(launch_chain_prefix(pf->d_p, pf->n, 0, nullptr, pf->d_scalars + 0, pf->d_dense, pf->chain_mode, pf->stream));
+  CU(launch_chain_sum_array(d_wr, pf->n, pf->d_scalars + 1, pf->d_dense, pf->chain_mode, pf->stream));
   CU(launch_fuse_range(pf->d_p, d_wr, pf->n, pf->d_scalars + 0, pf->d_scalars + 1, alpha, pf->stream));
   pf->launches += 4;
   pf->launches += chain_extra_launches_take();
@@ -1034,8 +1057,11 @@ static int update_impl(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beacons,
   TwoPhase tp{};
   const TwoPhase* tpp = nullptr;
   uint64_t slice_n = pf->n;
-  if (pf->two_phase && pf->n >= 4096 && pf->npts >= 64 && pf->d_sorted != nullptr && map.rep == kRepCode8 && map.lut_n < 255)
+  if (pf->two_phase && pf->n >= 4096 && pf->npts >= 64 && two_phase_supported(map))
   {
+    if (!pf->sorted_valid)  // the cloud was set while the two-phase path was off: sort it now
+      if (int rc = sort_cloud(pf))
+        return rc;
     const uint64_t pitch = stage_tile_width();  // bytes per staged row of one particle tile (= particles per block)
     const uint64_t tile_bytes = pitch * pf->npad;
     const uint64_t tiles = (pf->n + pitch - 1) / pitch;
@@ -1048,21 +1074,29 @@ static int update_impl(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beacons,
     if (slice_tiles >= 16)  // below that a slice does not fill the machine: single-kernel path
     {
       CU(ensure(pf->d_codes_staged, pf->codes_staged_cap, slice_tiles * tile_bytes));
+      CU(ensure(pf->d_pose, pf->pose_cap, (uint64_t)pose_floats((uint32_t)(slice_tiles * pitch))));
       tp.sorted = pf->d_sorted;
       tp.stage = pf->d_codes_staged;
-      tp.pitch = pitch;
+      tp.pose = pf->d_pose;
       tpp = &tp;
       slice_n = slice_tiles * pitch;
     }
   }
   {
     Timed t(pf);
+    const uint64_t pitch_w = stage_tile_width();
     for (uint64_t off = 0; off < pf->n || off == 0; off += slice_n)
     {
       const uint64_t n_s = pf->n - off < slice_n ? pf->n - off : slice_n;
+      if (tpp && n_s)
+      {
+        // phase 0: rotation + offsets once per particle of this slice
+        CU(launch_pose(map, pf->d_p + 7 * off, (uint32_t)n_s, pf->trig_mode, pf->d_pose, pf->stream));
+        tp.pose_pitch = (uint32_t)((n_s + pitch_w - 1) / pitch_w * pitch_w);
+      }
       CU(launch_update(map, pf->d_p + 7 * off, (uint32_t)n_s, pf->d_cloud, pf->npts, pf->npad, pf->d_beacons,
                        d_wr ? d_wr + off : nullptr, pf->trig_mode, d_counter, tpp, pf->stream));
-      pf->launches += n_s ? (tpp ? 2 : 1) : 0;
+      pf->launches += n_s ? (tpp ? 3 : 1) : 0;
       if (pf->n == 0)
         break;
     }
@@ -1121,7 +1155,7 @@ int amcl3d_b200_pf_update_cloud(amcl3d_b200_pf_t pf, const float* cloud, uint32_
 static int normalize_async(amcl3d_b200_pf_t pf)
 {
   CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(pf->n)));
-  CU(launch_chain_prefix(pf->d_p, pf->n, 1, nullptr, pf->d_scalars + 0, pf->d_dense, pf->stream));
+  CU(launch_chain_prefix(pf->d_p, pf->n, 1, nullptr, pf->d_scalars + 0, pf->d_dense, pf->chain_mode, pf->stream));
   CU(launch_normalize(pf->grid->map, pf->d_p, pf->n, pf->d_scalars + 0, pf->stream));
   pf->launches += pf->n ? 2 : 1;
   pf->launches += chain_extra_launches_take();
@@ -1215,7 +1249,7 @@ int amcl3d_b200_pf_resample(amcl3d_b200_pf_t pf, float u01, uint64_t m0, uint64_
   }
   {
     Timed t(pf);
-    CU(launch_chain_prefix(pf->d_p, n, 0, pf->d_prefix, nullptr, pf->d_dense, pf->stream));
+    CU(launch_chain_prefix(pf->d_p, n, 0, pf->d_prefix, nullptr, pf->d_dense, pf->chain_mode, pf->stream));
     CU(launch_resample_search(pf->d_p, pf->d_prefix, n, u01, m0, m1, out, d_idx, pf->stream));
     pf->launches += 2;
     pf->launches += chain_extra_launches_take();
@@ -1267,8 +1301,8 @@ int amcl3d_b200_pf_uniform_sample(amcl3d_b200_pf_t pf, int sample_num, uint64_t 
     Timed t(pf);
     if (int rc = normalize_async(pf))  // ParticleFilter.cpp:258
       return rc;
-    CU(launch_chain_prefix(pf->d_p, n, 0, pf->d_prefix, nullptr, pf->d_dense, pf->stream));
-    CU(launch_chain_thresholds(sample_num, pf->d_thr, pf->d_dense, pf->stream));
+    CU(launch_chain_prefix(pf->d_p, n, 0, pf->d_prefix, nullptr, pf->d_dense, pf->chain_mode, pf->stream));
+    CU(launch_chain_thresholds(sample_num, pf->d_thr, pf->d_dense, pf->chain_mode, pf->stream));
     CU(launch_uniform_search(pf->d_p, pf->d_prefix, n, pf->d_thr, sample_num, k0, k1, out, d_idx, pf->stream));
     CU(launch_count_emitted(pf->d_thr, sample_num, pf->d_prefix, n, pf->d_int, pf->stream));
     pf->launches += 4;
@@ -1370,7 +1404,7 @@ int amcl3d_b200_pf_prefix(amcl3d_b200_pf_t pf, void** d_prefix, float* host_out,
   CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(pf->n)));
   {
     Timed t(pf);
-    CU(launch_chain_prefix(pf->d_p, pf->n, 0, pf->d_prefix, nullptr, pf->d_dense, pf->stream));
+    CU(launch_chain_prefix(pf->d_p, pf->n, 0, pf->d_prefix, nullptr, pf->d_dense, pf->chain_mode, pf->stream));
     pf->launches += 1;
     pf->launches += chain_extra_launches_take();
   }

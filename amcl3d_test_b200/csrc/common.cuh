@@ -104,15 +104,20 @@ struct BeaconSet
 // particles: AoS 7 floats; cloud4: (x,y,z,0) per point padded with NaN points to a multiple of 32.
 // wr_out (nullable) receives the raw range-beacon weight per particle; counter (nullable) the number
 // of evaluations that loaded a voxel.
-// Two-phase sweep state (nullptr / stage == nullptr: single-kernel path): the Morton-sorted cloud (w = index of
-// the point in the caller's order) and the staging buffer stage[(tile * npad + row) * pitch + lane] of 1-byte
-// codes, rows in the caller's order, pitch = stage_tile_width() particles per tile.
+// Large-set path state (nullptr / stage == nullptr: single-kernel path): the Morton-sorted cloud (w = index of the
+// point in the caller's order), the per-particle poses of THIS call's particles (pose_floats(n) floats, SoA with
+// pitch pose_pitch = n rounded up to the tile width, filled by launch_pose) and the staging buffer
+// stage[(tile * npad + row) * stage_tile_width() + lane] of 1-byte codes, rows in the caller's order.
 struct TwoPhase
 {
   const float4* sorted;
   uint8_t* stage;
-  size_t pitch;
+  const float* pose;
+  uint32_t pose_pitch;
 };
+size_t pose_floats(uint32_t n);
+bool two_phase_supported(const MapDev& map);  // u8 codes and a map the branch-free sweep arithmetic is valid for
+cudaError_t launch_pose(const MapDev& map, const float* particles, uint32_t n, int trig_mode, float* pose, cudaStream_t stream);
 cudaError_t launch_update(const MapDev& map, float* particles, uint32_t n, const float4* cloud4, uint32_t npts,
                           uint32_t npts_padded, const BeaconSet* beacons, float* wr_out, int trig_mode,
                           unsigned long long* counter, const TwoPhase* tp, cudaStream_t stream);
@@ -136,19 +141,22 @@ cudaError_t run_voxel_filter(const float* d_pts, uint32_t stride, int ioff, uint
 // ---- particle-set ops (pfops.cu) --------------------------------------------------------------
 // serial f32 chain over w (stride 7 floats): prefix[i] (nullable) = sequential inclusive prefix starting
 // from 0; positive_only: add only w > 0 (particleNormalize).  total[0] receives the final value.
+// chain_mode: 0 exact scan over many CTAs, 1 serial chain, 2 exact scan on one CTA (same bits; per filter handle)
 cudaError_t launch_chain_prefix(const float* particles, uint64_t n, int positive_only, float* prefix, float* total,
-                                float* dense_scratch /* chain_scratch_floats(n), nullable */, cudaStream_t stream);
+                                float* dense_scratch /* chain_scratch_floats(n), nullable */, int chain_mode,
+                                cudaStream_t stream);
 // thresholds samp_0 = 0.5f/S, samp_{k+1} = samp_k + 1.0f/S (sequential f32 chain)
-cudaError_t launch_chain_thresholds(int S, float* thr, float* scratch /* chain_scratch_floats(S), nullable */, cudaStream_t stream);
+cudaError_t launch_chain_thresholds(int S, float* thr, float* scratch /* chain_scratch_floats(S), nullable */, int chain_mode,
+                                    cudaStream_t stream);
 // w = total>0 ? w/total : 0 ; w = 0 outside the map
 cudaError_t launch_normalize(const MapDev& map, float* particles, uint64_t n, const float* total, cudaStream_t stream);
 // range fusion: w = alpha*wp/sum_p + (1-alpha)*wr/sum_r (sums: sequential f32 chains)
 cudaError_t launch_fuse_range(float* particles, const float* wr, uint64_t n, const float* sum_p, const float* sum_r,
                               float alpha, cudaStream_t stream);
-void set_chain_mode(int mode);  // 0 exact scan over many CTAs, 1 serial chain, 2 exact scan on one CTA
 uint64_t chain_scratch_floats(uint64_t n);  // dense operands + per-tile bookkeeping of the many-CTA scan
 uint32_t chain_extra_launches_take();       // kernels launched by the chain calls beyond one each, since the last take
-cudaError_t launch_chain_sum_array(const float* v, uint64_t n, float* total, float* scratch, cudaStream_t stream);
+cudaError_t launch_chain_sum_array(const float* v, uint64_t n, float* total, float* scratch, int chain_mode,
+                                   cudaStream_t stream);
 // max weight (and first arg-max with w > 0) -> out_max[0], out_arg[0] (UINT64_MAX if none)
 cudaError_t launch_max_weight(const float* particles, uint64_t n, float* out_max, unsigned long long* out_arg,
                               void* scratch, cudaStream_t stream);
@@ -189,10 +197,10 @@ struct CodedGrid
 };
 // full build: EDT (+ optional kept distances) and fused Gaussian into prob (device, n_cells floats);
 // coded (nullable) additionally receives the dictionary-coded bricked copy (caller frees codes / lut)
-void set_edt_fast_passes(int enable);  // 1 (default): capped window passes when the exact EDT is not kept
+// fast_passes != 0: capped window passes when the exact EDT is not kept (same float grid bit for bit)
 cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t stride, uint64_t n, double sensor_dev,
-                           int mode, int sub, float* prob, int32_t** keep_d2, CodedGrid* coded, cudaStream_t stream,
-                           char* err, size_t errlen);
+                           int mode, int sub, float* prob, int32_t** keep_d2, CodedGrid* coded, int fast_passes,
+                           cudaStream_t stream, char* err, size_t errlen);
 cudaError_t build_grid_splat(const MapDev& map, const float* d_xyz, uint32_t stride, uint64_t n, double sensor_dev,
                              float* prob, cudaStream_t stream);
 

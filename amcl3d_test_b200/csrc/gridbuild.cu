@@ -817,15 +817,9 @@ done:
   return rc;
 }
 
-static int g_fast_passes = 1;  // AMCL3D_B200_EDT_FAST=0 (read by the C-ABI) forces the exact envelope passes
-void set_edt_fast_passes(int enable)
-{
-  g_fast_passes = enable;
-}
-
 cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t stride, uint64_t n, double sensor_dev,
-                           int mode, int sub, float* prob, int32_t** keep_d2, CodedGrid* coded, cudaStream_t stream,
-                           char* err, size_t errlen)
+                           int mode, int sub, float* prob, int32_t** keep_d2, CodedGrid* coded, int fast_passes,
+                           cudaStream_t stream, char* err, size_t errlen)
 {
   cudaError_t rc = cudaSuccess;
   const int sx = (int)map.size[0], sy = (int)map.size[1], sz = (int)map.size[2];
@@ -922,7 +916,7 @@ cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t strid
       // probability never reaches 0.0f, or when the window would be wide (large sigma / fine lattice).
       unsigned int h_cap = 0xFFFFFFFFu;
       int win = 0;
-      if (keep_d2 == nullptr && g_fast_passes)
+      if (keep_d2 == nullptr && fast_passes)
       {
         CK(find_cap(G, &h_cap, stream));
         if (h_cap != 0xFFFFFFFFu && h_cap >= 1 && h_cap < 65535u)

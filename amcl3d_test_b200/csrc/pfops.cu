@@ -1358,13 +1358,8 @@ __global__ void extract_weights_kernel(const float* __restrict__ particles, uint
     dense[i] = particles[7 * i + 6];
 }
 
-// 0: exact scan over many CTAs (default), 1: the serial chain kernel, 2: the exact scan on one CTA.
-// All three give the reference's bits; 1 and 2 are kept for A/B timing and cross-checking.
-static int g_chain_mode = 0;
-void set_chain_mode(int mode)
-{
-  g_chain_mode = mode;
-}
+// chain_mode (per filter handle) -- 0: exact scan over many CTAs (default), 1: the serial chain kernel, 2: the exact
+// scan on one CTA.  All three give the reference's bits; 1 and 2 are kept for A/B timing and cross-checking.
 static thread_local uint32_t g_chain_extra = 0;
 uint32_t chain_extra_launches_take()
 {
@@ -1379,12 +1374,12 @@ uint64_t chain_scratch_floats(uint64_t n)
   return ((n + 63) / 64) * 64 + meta / sizeof(float);
 }
 static cudaError_t launch_chain(const float* src, uint32_t stride, uint32_t offset, uint64_t n, int mode, float start,
-                                float inc, float* prefix, float* total, void* meta, cudaStream_t stream)
+                                float inc, float* prefix, float* total, void* meta, int chain_mode, cudaStream_t stream)
 {
   const uint64_t nadd = (mode == kChainThreshold) ? (n > 0 ? n - 1 : 0) : n;
-  if (g_chain_mode == 1)
+  if (chain_mode == 1)
     chain_kernel<<<1, kChainThreads, 0, stream>>>(src, stride, offset, n, mode, start, inc, prefix, total);
-  else if (g_chain_mode == 2 || meta == nullptr || nadd <= 2 * kTile)
+  else if (chain_mode == 2 || meta == nullptr || nadd <= 2 * kTile)
     exact_scan_kernel<<<1, kScanThreads, 0, stream>>>(src, stride, offset, n, mode, start, inc, prefix, total);
   else
   {
@@ -1414,31 +1409,33 @@ static void* chain_meta(float* dense_scratch, uint64_t n)
 }
 
 cudaError_t launch_chain_prefix(const float* particles, uint64_t n, int positive_only, float* prefix, float* total,
-                                float* dense_scratch, cudaStream_t stream)
+                                float* dense_scratch, int chain_mode, cudaStream_t stream)
 {
   const int mode = positive_only ? kChainSumPositive : kChainSum;
-  if (dense_scratch != nullptr && n > 0 && g_chain_mode != 1)
+  if (dense_scratch != nullptr && n > 0 && chain_mode != 1)
   {
     extract_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(particles, n, dense_scratch);
     g_chain_extra += 1;
-    return launch_chain(dense_scratch, 1, 0, n, mode, 0.f, 0.f, prefix, total, chain_meta(dense_scratch, n), stream);
+    return launch_chain(dense_scratch, 1, 0, n, mode, 0.f, 0.f, prefix, total, chain_meta(dense_scratch, n), chain_mode,
+                        stream);
   }
-  return launch_chain(particles, 7, 6, n, mode, 0.f, 0.f, prefix, total, nullptr, stream);
+  return launch_chain(particles, 7, 6, n, mode, 0.f, 0.f, prefix, total, nullptr, chain_mode, stream);
 }
 
-cudaError_t launch_chain_sum_array(const float* v, uint64_t n, float* total, float* scratch, cudaStream_t stream)
+cudaError_t launch_chain_sum_array(const float* v, uint64_t n, float* total, float* scratch, int chain_mode,
+                                   cudaStream_t stream)
 {
-  return launch_chain(v, 1, 0, n, kChainSum, 0.f, 0.f, nullptr, total, chain_meta(scratch, n), stream);
+  return launch_chain(v, 1, 0, n, kChainSum, 0.f, 0.f, nullptr, total, chain_meta(scratch, n), chain_mode, stream);
 }
 
-cudaError_t launch_chain_thresholds(int S, float* thr, float* scratch, cudaStream_t stream)
+cudaError_t launch_chain_thresholds(int S, float* thr, float* scratch, int chain_mode, cudaStream_t stream)
 {
   if (S <= 0)
     return cudaSuccess;
   const float inteval = 1.0f / S;  // ParticleFilter.cpp:267 (IEEE f32 divide on the host)
   const float samp0 = 0.5f / S;    // ParticleFilter.cpp:268
   return launch_chain(nullptr, 1, 0, (uint64_t)S, kChainThreshold, samp0, inteval, thr, nullptr,
-                      chain_meta(scratch, (uint64_t)S), stream);
+                      chain_meta(scratch, (uint64_t)S), chain_mode, stream);
 }
 
 cudaError_t launch_normalize(const MapDev& map, float* particles, uint64_t n, const float* total, cudaStream_t stream)

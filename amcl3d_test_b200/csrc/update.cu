@@ -21,6 +21,13 @@
 //  * bounds: f32 value against f64 size is done against size_up = smallest f32 >= size (equivalent).
 //  * voxel index floor(fl64(v / resol)): f32 quotient v*rinv with an error band; inside the band an
 //    f64 product with a 1e-9 band; inside that the real f64 division.  Result identical to the DDIV.
+//
+// Two code paths (bit-identical weights):
+//  * update_kernel<rep>  -- one launch, cloud swept in the caller's order, weight accumulated in registers.
+//  * pose_kernel + sweep_kernel + ordered_sum_kernel -- the large-set path on u8-coded grids: the rotation and
+//    offsets are computed once per particle (pose_kernel), the Morton-sorted cloud is swept chunk-major so that
+//    all particles gather from the same neighbourhood of the map at the same time, 1-byte codes are parked at
+//    the point's original row (sweep_kernel), and the ordered sum adds them in the caller's cloud order.
 #include "common.cuh"
 
 #include <math_constants.h>
@@ -293,14 +300,7 @@ __device__ __forceinline__ void batch_consume(const typename Raw<kRep>::type raw
   cnt += __popc(mask);
 }
 
-// Where the gathered values of a batch go.
-//  * AccumSink: the reference's in-order f32 accumulation (Grid3d.cpp:292) -- the single-kernel path, the
-//    cloud is swept in its own order.
-//  * StageSink: two-phase path.  The cloud is swept in a spatially coherent (Morton) order so that all
-//    particles work in the same neighbourhood of the map at the same time (L2 / TLB locality), and the
-//    1-byte codes are parked at the point's ORIGINAL row of a staging buffer stage[tile][row][lane];
-//    ordered_sum_kernel then streams the rows front to back, i.e. adds in the original cloud order, so the
-//    rounding sequence -- and every bit of the weight -- is unchanged.
+// The single-kernel path accumulates in registers, in cloud order: the reference's f32 rounding chain (Grid3d.cpp:292).
 template <int kRep>
 struct AccumSink
 {
@@ -312,18 +312,7 @@ struct AccumSink
     batch_consume<kRep>(raw, mask, lut_s, weight, cnt);
   }
 };
-constexpr uint32_t kStageSkip = 0xFFu;  // staged code of an evaluation that loaded nothing
-struct StageSink
-{
-  uint8_t* __restrict__ column;  // &stage[tile][0][lane]
-  size_t pitch;                  // bytes from one row (cloud point, ORIGINAL order) to the next
-  __device__ __forceinline__ void put(const uint32_t raw[kUnroll], uint32_t mask, const uint32_t orow[kUnroll])
-  {
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
-      column[(size_t)orow[u] * pitch] = (uint8_t)(((mask >> u) & 1u) ? raw[u] : kStageSkip);
-  }
-};
+constexpr uint32_t kStageSkip = 0xFFu;  // staged code of an evaluation that loaded nothing (large-set path)
 
 // one tile of `count` points (a multiple of 2*kUnroll) for one particle; row0 = index of tile[0] in the sweep
 template <bool kF32Offset, int kRep, typename Sink>
@@ -397,33 +386,20 @@ __device__ __forceinline__ bool particle_gate(const MapDev& map, float px, float
 #ifndef AMCL3D_MINBLOCKS
 #define AMCL3D_MINBLOCKS 3
 #endif
-#ifndef AMCL3D_STAGE_TILES
-#define AMCL3D_STAGE_TILES 1  // cloud tiles per block of the staging sweep (lock-step granularity)
-#endif
-// kStage == false: the whole update in one kernel (sweep in cloud order, accumulate in registers).
-// kStage == true : phase 1 of the two-phase path (sweep the Morton-sorted cloud, park codes in `stage`).
-template <int kRep, bool kStage>
+// The whole update in one kernel: one block sweeps the whole cloud, in the caller's order, for its 256 particles.
+template <int kRep>
 __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
     update_kernel(const __grid_constant__ MapDev map, float* __restrict__ particles, uint32_t n,
                   const float4* __restrict__ cloud, uint32_t npts, uint32_t npad, const BeaconSet* __restrict__ beacons,
-                  float* __restrict__ wr_out, int trig_mode, unsigned long long* __restrict__ counter,
-                  uint8_t* __restrict__ stage, size_t stage_pitch, uint32_t tiles_per_block)
+                  float* __restrict__ wr_out, int trig_mode, unsigned long long* __restrict__ counter)
 {
-  constexpr int kT = kStage ? kStageTile : kTile;
+  constexpr int kT = kTile;
   __shared__ __align__(128) float4 tile[kStages][kT];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   extern __shared__ float lut_s[];  // kRep != kRepFloat: the code -> f32 dictionary
 
   const uint32_t tid = threadIdx.x;
-  // Block order.  Single-kernel path: one block sweeps the whole cloud for its 128 particles.  Staging path:
-  // the grid is (chunk of tiles_per_block tiles) x (particle tile) in CHUNK-MAJOR order, so the hardware block
-  // scheduler keeps every resident block inside the same one or two chunks of the Morton-sorted cloud: all
-  // particles gather from the same neighbourhood of the map at the same time (no flags, nothing to chain --
-  // the codes are only parked).
-  const uint32_t n_ptiles = (n + kThreads - 1) / kThreads;
-  const uint32_t ptile = kStage ? blockIdx.x % n_ptiles : blockIdx.x;
-  const uint32_t chunk = kStage ? blockIdx.x / n_ptiles : 0u;
-  const uint32_t i = ptile * kThreads + tid;
+  const uint32_t i = blockIdx.x * kThreads + tid;
   const bool live = i < n;
 
   float px = 0, py = 0, pz = 0, roll = 0, pitch = 0, yaw = 0;
@@ -457,9 +433,8 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
   // warp-uniform choice of the loop flavour; lanes that are not in the map do not vote it down
   const bool warp_f32 = __all_sync(0xffffffffu, f32_exact || !inmap);
 
-  const uint32_t ntiles_all = (npad + kT - 1) / kT;
-  const uint32_t tile0 = chunk * tiles_per_block;                       // first tile of this block
-  const uint32_t ntiles = min(tiles_per_block, ntiles_all - tile0);     // tiles this block sweeps
+  const uint32_t ntiles = (npad + kT - 1) / kT;
+  constexpr uint32_t tile0 = 0;
   if (tid == 0)
   {
 #pragma unroll
@@ -467,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
       mbar_init(&full_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (kRep != kRepFloat && !kStage)
+  if (kRep != kRepFloat)
     for (uint32_t k = tid; k < map.lut_n; k += kThreads)
       lut_s[k] = map.lut[k];
   __syncthreads();
@@ -482,9 +457,6 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
   }
 
   AccumSink<kRep> acc{ lut_s, 0.f, 0 };
-  // staging layout: [particle tile][row][lane] -- each particle tile owns one contiguous npad x kThreads block,
-  // so phase 2 (rows visited in original-cloud order, i.e. at random) stays inside a couple of 2 MB pages
-  StageSink park{ stage + (size_t)ptile * stage_pitch * npad + tid, stage_pitch };
   for (uint32_t t = 0; t < ntiles; ++t)
   {
     const uint32_t s = t % kStages;
@@ -494,20 +466,10 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
     const uint32_t count = min((uint32_t)kT, npad - row0);
     if (inmap)
     {
-      if constexpr (kStage)
-      {
-        if (warp_f32)
-          tile_loop<true, kRep>(map, &tile[s][0], count, row0, r, off_f, off_d, park);
-        else
-          tile_loop<false, kRep>(map, &tile[s][0], count, row0, r, off_f, off_d, park);
-      }
+      if (warp_f32)
+        tile_loop<true, kRep>(map, &tile[s][0], count, row0, r, off_f, off_d, acc);
       else
-      {
-        if (warp_f32)
-          tile_loop<true, kRep>(map, &tile[s][0], count, row0, r, off_f, off_d, acc);
-        else
-          tile_loop<false, kRep>(map, &tile[s][0], count, row0, r, off_f, off_d, acc);
-      }
+        tile_loop<false, kRep>(map, &tile[s][0], count, row0, r, off_f, off_d, acc);
     }
     __syncthreads();  // every lane is done with stage s before TMA overwrites it
     if (tid == 0 && t + kStages < ntiles)
@@ -519,8 +481,6 @@ __global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
     }
   }
 
-  if (kStage)
-    return;  // ordered_sum_kernel finishes the particle
   if (live)
     finish_particle(particles, i, inmap, acc.weight, acc.cnt, npts, px, py, pz, beacons, wr_out);
   if (counter != nullptr)
@@ -759,6 +719,326 @@ __global__ void __launch_bounds__(256)
 }
 }  // namespace
 
+// ---- large-set path: pose -> sweep -> ordered sum ---------------------------------------------------------
+namespace
+{
+constexpr int kPoseFloats = 13;  // r[9], off_f[3], flags
+constexpr uint32_t kPoseInMap = 1u, kPoseF32 = 2u;
+
+// pose[k * pitch + i]: rotation (Grid3d.cpp:240-250), f32-rounded offsets t - min (Grid3d.cpp:256-258) and the
+// flags "passes isIntoMap" / "all three offsets are exactly representable in f32".  Once per particle per update
+// instead of once per (particle, cloud chunk).
+__global__ void __launch_bounds__(256)
+    pose_kernel(const __grid_constant__ MapDev map, const float* __restrict__ particles, uint32_t n, int trig_mode,
+                float* __restrict__ pose, uint32_t pitch)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pitch)
+    return;
+  float px = 0, py = 0, pz = 0, roll = 0, pitch_a = 0, yaw = 0;
+  const bool live = i < n;
+  if (live)
+  {
+    const float* p = particles + (size_t)7 * i;
+    px = p[0];
+    py = p[1];
+    pz = p[2];
+    roll = p[3];
+    pitch_a = p[4];
+    yaw = p[5];
+  }
+  const bool inmap = live && particle_gate(map, px, py, pz);
+  float r[9];
+  rotation(roll, pitch_a, yaw, trig_mode, r);
+  const double off_d[3] = { __dsub_rn((double)px, map.min[0]), __dsub_rn((double)py, map.min[1]),
+                            __dsub_rn((double)pz, map.min[2]) };
+  bool f32_exact = true;
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+    pose[(size_t)k * pitch + i] = r[k];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+  {
+    // +0.0f turns an offset of -0 into +0: the sum s + off is then never -0 (x + (-x) = +0 in RN), which lets the
+    // sweep test 0 <= v < size with one unsigned compare of the bit patterns; -0 and +0 index the same voxel.
+    const float f = __fadd_rn(__double2float_rn(off_d[a]), 0.f);
+    f32_exact = f32_exact && ((double)f == off_d[a]);
+    pose[(size_t)(9 + a) * pitch + i] = f;
+  }
+  pose[(size_t)12 * pitch + i] = __uint_as_float((inmap ? kPoseInMap : 0u) | (f32_exact ? kPoseF32 : 0u));
+}
+
+// what the sweep needs of the map, with the constants of its index arithmetic
+struct SweepMap
+{
+  double min[3];
+  double rinv, resol;
+  uint32_t su_bits[3];  // bit patterns of size_up: for a float v that is never -0, 0 <= v < size_up  <=>  bits(v) < su_bits
+  uint32_t size[3];
+  float rinv_f, band;
+  uint32_t mul_z, mul_y;  // 128^3-voxel blocks: block = bz * mul_z + by * mul_y + bx
+  uint32_t bias;          // the three block coordinates are taken from magic-number floats and each carry the constant
+                          // kMagicHi; bias = kMagicHi * (mul_z + mul_y + 1) mod 2^32 removes it
+  const uint8_t* codes;
+};
+constexpr float kMagic = 12582912.f;               // 1.5 * 2^23: u + kMagic rounds u to the nearest integer
+constexpr uint32_t kMagicHi = 0x4B400000u >> 7;    // bits(kMagic) >> 7
+constexpr uint32_t kQueueCap = 1024;               // deferred exact-tier evaluations per block (mean ~50 at C3)
+
+// Branch-free voxel address of one point for one particle.  The quotient v / resol is formed as
+// u = fma(v, rinv_f, -0.5); t = u + 1.5*2^23 rounds it to the nearest integer, which is floor(v / resol) whenever the
+// quotient is farther than eps from an integer; the low 22 mantissa bits of t ARE that integer, so the brick / block
+// fields are cut straight out of bits(t).  |u - round(u)| >= band flags the rare evaluation that needs the exact tier.
+template <bool kF32Offset>
+__device__ __forceinline__ void point_address(const SweepMap& sm, const float4 pt, const float r[9], const float off_f[3],
+                                              const double off_d[3], uint32_t& off_lo, uint32_t& blk, bool& in, bool& rare)
+{
+  // Grid3d.cpp:275-277
+  const float sx = __fadd_rn(__fadd_rn(__fmul_rn(pt.x, r[0]), __fmul_rn(pt.y, r[1])), __fmul_rn(pt.z, r[2]));
+  const float sy = __fadd_rn(__fadd_rn(__fmul_rn(pt.x, r[3]), __fmul_rn(pt.y, r[4])), __fmul_rn(pt.z, r[5]));
+  const float sz = __fadd_rn(__fadd_rn(__fmul_rn(pt.x, r[6]), __fmul_rn(pt.y, r[7])), __fmul_rn(pt.z, r[8]));
+  const float nx = add_offset<kF32Offset>(sx, off_f[0], off_d[0]);
+  const float ny = add_offset<kF32Offset>(sy, off_f[1], off_d[1]);
+  const float nz = add_offset<kF32Offset>(sz, off_f[2], off_d[2]);
+  // Grid3d.cpp:279-280 (a NaN has a bit pattern above every finite size: fails like in the reference)
+  in = (__float_as_uint(nx) < sm.su_bits[0]) & (__float_as_uint(ny) < sm.su_bits[1]) & (__float_as_uint(nz) < sm.su_bits[2]);
+  // Grid3d.cpp:282-284, fast tier
+  const float ux = __fmaf_rn(nx, sm.rinv_f, -0.5f), uy = __fmaf_rn(ny, sm.rinv_f, -0.5f), uz = __fmaf_rn(nz, sm.rinv_f, -0.5f);
+  const float tx = __fadd_rn(ux, kMagic), ty = __fadd_rn(uy, kMagic), tz = __fadd_rn(uz, kMagic);
+  const float dev = fmaxf(fmaxf(fabsf(__fsub_rn(ux, __fsub_rn(tx, kMagic))), fabsf(__fsub_rn(uy, __fsub_rn(ty, kMagic)))),
+                          fabsf(__fsub_rn(uz, __fsub_rn(tz, kMagic))));
+  rare = in & !(dev < sm.band);
+  const uint32_t bx = __float_as_uint(tx), by = __float_as_uint(ty), bz = __float_as_uint(tz);
+  // within the 2 MB block: brick (z6..2 | y6..2 | x6..3) << 7 | voxel (z1..0 | y1..0 | x2..0), see coded_index()
+  const uint32_t wx = (bx | (bx << 4)) & 0x787u;
+  const uint32_t wy = ((by << 3) | (by << 9)) & 0xF818u;
+  const uint32_t wz = ((bz << 5) | (bz << 14)) & 0x1F0060u;
+  off_lo = wx | wy | wz;
+  blk = (bz >> 7) * sm.mul_z + ((by >> 7) * sm.mul_y + ((bx >> 7) - sm.bias));
+}
+
+// exact evaluation of one (particle, point) pair: every tier of the index, all bounds tests -- the deferred path
+__device__ __noinline__ uint32_t exact_code(const SweepMap& sm, const float4 pt, const float* __restrict__ pose, uint32_t pitch,
+                                            uint32_t i, const float* __restrict__ particles)
+{
+  float r[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+    r[k] = pose[(size_t)k * pitch + i];
+  const float sx = __fadd_rn(__fadd_rn(__fmul_rn(pt.x, r[0]), __fmul_rn(pt.y, r[1])), __fmul_rn(pt.z, r[2]));
+  const float sy = __fadd_rn(__fadd_rn(__fmul_rn(pt.x, r[3]), __fmul_rn(pt.y, r[4])), __fmul_rn(pt.z, r[5]));
+  const float sz = __fadd_rn(__fadd_rn(__fmul_rn(pt.x, r[6]), __fmul_rn(pt.y, r[7])), __fmul_rn(pt.z, r[8]));
+  // the f64 offset add of the reference itself (Grid3d.cpp:256-258, 275-277); equals the f32 add when that is exact
+  const float* p = particles + (size_t)7 * i;
+  const float nx = __double2float_rn(__dadd_rn((double)sx, __dsub_rn((double)p[0], sm.min[0])));
+  const float ny = __double2float_rn(__dadd_rn((double)sy, __dsub_rn((double)p[1], sm.min[1])));
+  const float nz = __double2float_rn(__dadd_rn((double)sz, __dsub_rn((double)p[2], sm.min[2])));
+  const bool in = (nx >= 0.f) & (__float_as_uint(__fadd_rn(nx, 0.f)) < sm.su_bits[0]) & (ny >= 0.f) &
+                  (__float_as_uint(__fadd_rn(ny, 0.f)) < sm.su_bits[1]) & (nz >= 0.f) &
+                  (__float_as_uint(__fadd_rn(nz, 0.f)) < sm.su_bits[2]);
+  if (!in)
+    return kStageSkip;
+  const uint32_t ix = voxel_exact(nx, sm.rinv, sm.resol), iy = voxel_exact(ny, sm.rinv, sm.resol),
+                 iz = voxel_exact(nz, sm.rinv, sm.resol);
+  if (!((ix < sm.size[0]) & (iy < sm.size[1]) & (iz < sm.size[2])))  // Grid3d.cpp:286 (and :290)
+    return kStageSkip;
+  return gather_u8(sm.codes + coded_index<kRepCode8>(ix, iy, iz, sm.mul_y, sm.mul_z / sm.mul_y));
+}
+
+template <bool kF32Offset, bool kIdx32>
+__device__ __forceinline__ void sweep_tile(const SweepMap& sm, const float4* __restrict__ tile, uint32_t count, const float r[9],
+                                           const float off_f[3], const double off_d[3], uint8_t* __restrict__ column,
+                                           uint32_t tid, uint32_t* __restrict__ q_count, uint32_t* __restrict__ queue)
+{
+  // software pipeline as in tile_loop: the gathers of batch k+1 are in flight while batch k is parked
+  uint32_t raw_a[kUnroll], raw_b[kUnroll], row_a[kUnroll], row_b[kUnroll];
+  auto issue = [&](uint32_t base, uint32_t raw[kUnroll], uint32_t row[kUnroll]) {
+    float4 pt[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      pt[u] = tile[base + u];  // broadcast LDS.128
+    uint32_t rare_mask = 0;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+    {
+      uint32_t off_lo, blk;
+      bool in, rare;
+      point_address<kF32Offset>(sm, pt[u], r, off_f, off_d, off_lo, blk, in, rare);
+      row[u] = __float_as_uint(pt[u].w);
+      raw[u] = kStageSkip;
+      rare_mask |= rare ? (1u << u) : 0u;
+      if (in & !rare)
+      {
+        if (kIdx32)
+          raw[u] = gather_u8(sm.codes + ((blk << 21) | off_lo));
+        else
+          raw[u] = gather_u8(sm.codes + (((uint64_t)blk << 21) | off_lo));
+      }
+    }
+    if (rare_mask)  // a handful per block: parked as "skip" now, redone exactly after the sweep (one branch per batch)
+    {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if ((rare_mask >> u) & 1u)
+        {
+          const uint32_t slot = atomicAdd(q_count, 1u);
+          if (slot < kQueueCap)
+            queue[slot] = (tid << 16) | (base + u);
+        }
+    }
+  };
+  auto park = [&](const uint32_t raw[kUnroll], const uint32_t row[kUnroll]) {
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      column[(size_t)row[u] * kThreads] = (uint8_t)raw[u];
+  };
+  issue(0, raw_a, row_a);
+#pragma unroll 1
+  for (uint32_t base = kUnroll; base < count; base += 2 * kUnroll)
+  {
+    issue(base, raw_b, row_b);
+    park(raw_a, row_a);
+    if (base + kUnroll < count)
+      issue(base + kUnroll, raw_a, row_a);
+    park(raw_b, row_b);
+  }
+}
+
+// Phase 1 of the large-set path.  Thread = particle, block = 256 particles x one 128-point chunk of the Morton-sorted
+// cloud, grid in CHUNK-MAJOR order: the hardware block scheduler keeps every resident block inside the same one or two
+// chunks, i.e. all particles look up the same neighbourhood of the map at the same time (no flags, nothing to chain --
+// the codes are only parked at the point's original row of stage[particle tile][row][lane]).
+template <bool kIdx32>
+__global__ void __launch_bounds__(kThreads, AMCL3D_MINBLOCKS)
+    sweep_kernel(const __grid_constant__ SweepMap sm, const float* __restrict__ pose, uint32_t pitch,
+                 const float* __restrict__ particles, const float4* __restrict__ sorted, uint32_t npad,
+                 uint8_t* __restrict__ stage)
+{
+  __shared__ __align__(128) float4 tile[kStageTile];
+  __shared__ __align__(8) uint64_t full_bar;
+  __shared__ uint32_t q_count;
+  __shared__ uint32_t queue[kQueueCap];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t n_ptiles = pitch / kThreads;
+  const uint32_t ptile = blockIdx.x % n_ptiles, chunk = blockIdx.x / n_ptiles;
+  const uint32_t i = ptile * kThreads + tid;
+  const uint32_t row0 = chunk * kStageTile;
+  const uint32_t count = min((uint32_t)kStageTile, npad - row0);  // npad is a multiple of 32
+  if (tid == 0)
+  {
+    mbar_init(&full_bar, 1);
+    q_count = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0)
+  {
+    mbar_expect_tx(&full_bar, count * 16u);
+    tma_bulk_g2s(&tile[0], sorted + row0, count * 16u, &full_bar);
+  }
+  // the particle's pose while the cloud chunk is in flight
+  float r[9], off_f[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+    r[k] = pose[(size_t)k * pitch + i];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    off_f[a] = pose[(size_t)(9 + a) * pitch + i];
+  const uint32_t flags = __float_as_uint(pose[(size_t)12 * pitch + i]);
+  const bool inmap = flags & kPoseInMap;
+  // warp-uniform choice of the loop flavour; lanes that are not in the map do not vote it down
+  const bool warp_f32 = __all_sync(0xffffffffu, (flags & kPoseF32) || !inmap);
+  uint8_t* const column = stage + (size_t)ptile * kThreads * npad + tid;
+  mbar_wait(&full_bar, 0);
+  if (inmap)
+  {
+    double off_d[3] = { 0, 0, 0 };
+    if (warp_f32)
+      sweep_tile<true, kIdx32>(sm, tile, count, r, off_f, off_d, column, tid, &q_count, queue);
+    else
+    {
+      const float* p = particles + (size_t)7 * i;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+        off_d[a] = __dadd_rn(__dsub_rn((double)p[a], sm.min[a]), 0.0);  // Grid3d.cpp:256-258 (never -0, see pose_kernel)
+      sweep_tile<false, kIdx32>(sm, tile, count, r, off_f, off_d, column, tid, &q_count, queue);
+    }
+  }
+  __syncthreads();
+  // deferred exact tier: evaluations within eps of a voxel face.  Kept out of the sweep so that its loop holds no call
+  // (a call site makes the compiler reload every uniform register after it, ~7 % of the sweep's instructions).
+  const uint32_t pending = q_count;
+  if (pending <= kQueueCap)
+  {
+    for (uint32_t e = tid; e < pending; e += kThreads)
+    {
+      const uint32_t q = queue[e], owner = q >> 16, j = q & 0xFFFFu;
+      const float4 pt = tile[j];
+      const uint32_t code = exact_code(sm, pt, pose, pitch, ptile * kThreads + owner, particles);
+      stage[(size_t)ptile * kThreads * npad + (size_t)__float_as_uint(pt.w) * kThreads + owner] = (uint8_t)code;
+    }
+  }
+  else if (inmap)
+  {
+    // queue overflow (e.g. a cloud and poses that sit on the voxel lattice): this thread redoes its whole column exactly
+    for (uint32_t j = 0; j < count; ++j)
+    {
+      const float4 pt = tile[j];
+      column[(size_t)__float_as_uint(pt.w) * kThreads] = (uint8_t)exact_code(sm, pt, pose, pitch, i, particles);
+    }
+  }
+}
+}  // namespace
+
+size_t pose_floats(uint32_t n)
+{
+  return (size_t)kPoseFloats * (((size_t)n + kThreads - 1) / kThreads * kThreads);
+}
+
+// true when the branch-free sweep index arithmetic is valid for this map: sizes below 2^21 per axis, and for the largest
+// coordinate that passes the bounds test the reference's floor(v / resol) already stays below the size on every axis
+// (so Grid3d.cpp:286 never rejects anything the bounds test accepted and the sweep can leave it out)
+static bool sweep_map(const MapDev& map, SweepMap* sm)
+{
+  if (map.rep != kRepCode8 || map.codes == nullptr || map.lut_n >= kStageSkip)
+    return false;
+  for (int a = 0; a < 3; ++a)
+  {
+    if (map.size[a] == 0 || map.size[a] >= (1u << 21) || !(map.size_up[a] > 0.f) || !isfinite(map.size_up[a]))
+      return false;
+    const float vmax = nextafterf(map.size_up[a], 0.f);
+    if (!(floor((double)vmax / map.resol) < (double)map.size[a]))
+      return false;
+    sm->min[a] = map.min[a];
+    memcpy(&sm->su_bits[a], &map.size_up[a], 4);
+    sm->size[a] = map.size[a];
+  }
+  sm->rinv = map.rinv;
+  sm->resol = map.resol;
+  sm->rinv_f = map.rinv_f;
+  sm->band = map.band;
+  sm->mul_y = map.nbx;
+  sm->mul_z = map.nbx * map.nby;
+  sm->bias = kMagicHi * (sm->mul_z + sm->mul_y + 1u);
+  sm->codes = reinterpret_cast<const uint8_t*>(map.codes);
+  return true;
+}
+
+bool two_phase_supported(const MapDev& map)
+{
+  SweepMap sm;
+  return sweep_map(map, &sm);
+}
+
+cudaError_t launch_pose(const MapDev& map, const float* particles, uint32_t n, int trig_mode, float* pose, cudaStream_t stream)
+{
+  if (n == 0)
+    return cudaSuccess;
+  const uint32_t pitch = (n + kThreads - 1) / kThreads * kThreads;
+  pose_kernel<<<pitch / 256, 256, 0, stream>>>(map, particles, n, trig_mode, pose, pitch);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_update(const MapDev& map, float* particles, uint32_t n, const float4* cloud4, uint32_t npts,
                           uint32_t npts_padded, const BeaconSet* beacons, float* wr_out, int trig_mode,
                           unsigned long long* counter, const TwoPhase* tp, cudaStream_t stream)
@@ -768,19 +1048,28 @@ cudaError_t launch_update(const MapDev& map, float* particles, uint32_t n, const
   const uint32_t blocks = (n + kThreads - 1) / kThreads;
   if (map.rep == kRepFloat || map.codes == nullptr || map.lut_n > kMaxLutSmem)
   {
-    update_kernel<kRepFloat, false><<<blocks, kThreads, 0, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
-                                                                     wr_out, trig_mode, counter, nullptr, 0, 0xFFFFFFFFu);
+    update_kernel<kRepFloat><<<blocks, kThreads, 0, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
+                                                                     wr_out, trig_mode, counter);
     return cudaGetLastError();
   }
-  if (tp != nullptr && tp->stage != nullptr && map.rep == kRepCode8 && map.lut_n < kStageSkip)
+  SweepMap sm;
+  if (tp != nullptr && tp->stage != nullptr && tp->pose != nullptr && sweep_map(map, &sm))
   {
-    // phase 1: sweep the Morton-sorted cloud, park the codes; phase 2: ordered sum
-    const uint32_t ntiles = (npts_padded + kStageTile - 1) / kStageTile;
-    const uint32_t tpb = AMCL3D_STAGE_TILES;
-    const uint32_t chunks = (ntiles + tpb - 1) / tpb;
-    update_kernel<kRepCode8, true><<<blocks * chunks, kThreads, 0, stream>>>(map, particles, n, tp->sorted, npts, npts_padded,
-                                                                             beacons, nullptr, trig_mode, nullptr, tp->stage,
-                                                                             tp->pitch, tpb);
+    // phase 1: sweep the Morton-sorted cloud, park the codes; phase 2: ordered sum.  tp->pose holds this slice's poses
+    // (pitch = tp->pose_pitch of the whole set, the slice starts at a multiple of the tile width).
+    const uint32_t chunks = (npts_padded + kStageTile - 1) / kStageTile;
+    // n_ptiles of THIS slice: the kernel derives it from the pitch it is given, so hand it the slice's own pitch and
+    // address the SoA rows of the full array through a per-row stride
+    const uint32_t slice_pitch = blocks * kThreads;
+    if (tp->pose_pitch != slice_pitch)
+      return cudaErrorInvalidValue;  // slices carry their own pose block (see update_impl)
+    const uint64_t coded_bytes = ((uint64_t)map.nbx * map.nby * ((map.size[2] + 127) / 128)) << 21;
+    if (coded_bytes <= (1ull << 32))
+      sweep_kernel<true><<<blocks * chunks, kThreads, 0, stream>>>(sm, tp->pose, slice_pitch, particles, tp->sorted,
+                                                                    npts_padded, tp->stage);
+    else
+      sweep_kernel<false><<<blocks * chunks, kThreads, 0, stream>>>(sm, tp->pose, slice_pitch, particles, tp->sorted,
+                                                                     npts_padded, tp->stage);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
       return e;
@@ -789,21 +1078,19 @@ cudaError_t launch_update(const MapDev& map, float* particles, uint32_t n, const
     return cudaGetLastError();
   }
   const size_t dyn = sizeof(float) * map.lut_n;
-  static bool attr_set = false;
-  if (!attr_set)
+  if (map.rep == kRepCode8)
+    update_kernel<kRepCode8><<<blocks, kThreads, dyn, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
+                                                                       wr_out, trig_mode, counter);
+  else
   {
-    cudaError_t e = cudaFuncSetAttribute(update_kernel<kRepCode16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    // the opt-in is a per-device attribute of the function: set it on every launch (cheap) rather than once per process
+    cudaError_t e = cudaFuncSetAttribute(update_kernel<kRepCode16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(sizeof(float) * kMaxLutSmem));
     if (e != cudaSuccess)
       return e;
-    attr_set = true;
+    update_kernel<kRepCode16><<<blocks, kThreads, dyn, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
+                                                                        wr_out, trig_mode, counter);
   }
-  if (map.rep == kRepCode8)
-    update_kernel<kRepCode8, false><<<blocks, kThreads, dyn, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
-                                                                       wr_out, trig_mode, counter, nullptr, 0, 0xFFFFFFFFu);
-  else
-    update_kernel<kRepCode16, false><<<blocks, kThreads, dyn, stream>>>(map, particles, n, cloud4, npts, npts_padded, beacons,
-                                                                        wr_out, trig_mode, counter, nullptr, 0, 0xFFFFFFFFu);
   return cudaGetLastError();
 }
 

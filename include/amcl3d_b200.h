@@ -30,7 +30,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define AMCL3D_B200_ABI_VERSION 1
+#define AMCL3D_B200_ABI_VERSION 2
 
 enum
 {
@@ -90,17 +90,12 @@ const char* amcl3d_b200_last_error(void);
 int amcl3d_b200_device_info(int device, int* device_count, int* sm_count, int* cc_major, int* cc_minor,
                             uint64_t* l2_bytes, uint64_t* mem_bytes);
 
-/* cudaLimitMaxL2FetchGranularity of the current context (32, 64 or 128 bytes).  The weighting kernel
- * consumes 4 bytes per 32-byte sector at scattered addresses, so anything above 32 only multiplies
- * DRAM traffic; grid_create sets 32 unless AMCL3D_B200_L2_FETCH is set in the environment. */
+/* cudaLimitMaxL2FetchGranularity of the device (32, 64 or 128 bytes) -- a measurement knob.  The library never
+ * changes this limit of the host application on its own (only when AMCL3D_B200_L2_FETCH is set in the
+ * environment or through this call).  Measured on B200 (profiles/r2_gather_microbench.json): a scattered 1-byte
+ * gather that misses L2 costs a full 128-byte line of DRAM traffic at every setting, 32, 64 and 128 alike. */
 int amcl3d_b200_set_l2_fetch_granularity(int device, int bytes);
 int amcl3d_b200_get_l2_fetch_granularity(int device, int* bytes);
-
-/* How the sequential f32 recurrences of particleNormalize / resample / uniformSample are evaluated
- * (process-wide): 0 (default) the exact binade scan spread over many CTAs, 1 the plain serial chain kernel,
- * 2 the exact binade scan on one CTA.  All give the reference's bits; the switch exists for A/B timing and
- * cross-checking. */
-int amcl3d_b200_set_chain_mode(int mode);
 
 /* ---- Grid3d (amcl3d/src/Grid3d.{h,cpp}, PointCloudTools.{h,cpp}) ---------------------------- */
 int amcl3d_b200_grid_create(int device, amcl3d_b200_grid_t* out);
@@ -125,6 +120,9 @@ int amcl3d_b200_grid_set_map(amcl3d_b200_grid_t g, const double min[3], const do
 int amcl3d_b200_grid_build(amcl3d_b200_grid_t g, const float* xyz, uint32_t stride, uint64_t n,
                            double sensor_dev, int mode, int sub, int keep_edt);
 int amcl3d_b200_grid_download_edt(amcl3d_b200_grid_t g, int32_t* d2, uint64_t cap);
+/* per grid handle: 1 (default) capped passes when the EDT is not kept, 0 the exact envelope passes always (the float
+ * grid is the same bit for bit; A/B switch).  Environment AMCL3D_B200_EDT_FAST=0 sets the default for new handles. */
+int amcl3d_b200_grid_set_edt_fast(amcl3d_b200_grid_t g, int enable);
 
 /* loadGrid's payload (Grid3d.cpp:404-442): cells + sizes + sensor_dev from host memory */
 int amcl3d_b200_grid_upload(amcl3d_b200_grid_t g, const float* prob, const uint32_t size[3], double sensor_dev);
@@ -151,6 +149,10 @@ int amcl3d_b200_grid_device_ptr(amcl3d_b200_grid_t g, void** d_prob);
 int amcl3d_b200_pf_create(amcl3d_b200_grid_t g, amcl3d_b200_pf_t* out);
 int amcl3d_b200_pf_destroy(amcl3d_b200_pf_t pf);
 int amcl3d_b200_pf_set_trig_mode(amcl3d_b200_pf_t pf, int trig_mode);
+/* How this handle evaluates the sequential f32 recurrences of particleNormalize / resample / uniformSample:
+ * 0 (default) the exact binade scan spread over many CTAs, 1 the plain serial chain kernel, 2 the exact binade scan
+ * on one CTA.  All give the reference's bits; the switch exists for A/B timing and cross-checking. */
+int amcl3d_b200_pf_set_chain_mode(amcl3d_b200_pf_t pf, int mode);
 /* Stream order instead of call order.  The reference API is synchronous and so is every entry point by default.
  * With async enabled, the calls that hand nothing back to the host -- update (in_bounds == NULL), update_split,
  * fuse_range, normalize (wtp == NULL), scale_by_max, resample (idx == NULL) -- only enqueue their kernels on the

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", str(capi.lib_path())], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (amcl3d_b200_\w+)", out))
     assert set(header_symbols()) <= exported
-    assert L.amcl3d_b200_abi_version() == 1
+    assert L.amcl3d_b200_abi_version() == 2
     # nothing but the C-ABI leaks out of the library
     leaked = [l for l in out.splitlines() if " T " in l and "amcl3d_b200_" not in l]
     assert not leaked, leaked[:5]

@@ -211,3 +211,141 @@ def test_config5_extent_voxel_addresses_beyond_2_to_the_32(O):
     lin.p_ = P
     assert lin.update(cloud, count=True) == n_in
     assert np.array_equal(bits(lin.p_[:, 6]), bits(two))
+
+
+# ---- the benchmarked configurations pinned to the oracle AND the compiled reference -------------
+# The grid the GPU built (EDT + Gaussian, 2000 x 2000 x 400) is downloaded once; the oracle (oracle/amcl3d_oracle.c) and the
+# reference's own ParticleFilter::update / Grid3d::computeCloudWeight compiled from /root/reference (oracle/_ref, when it
+# travelled with the snapshot) index that very float array on the host, and the weights of a sample of the particles
+# must equal -- bit for bit -- what the same particles got inside the full-size run on the page-blocked coded grid
+# through pose_kernel + sweep_kernel + ordered_sum_kernel.  Reference loop: ParticleFilter.cpp:114-139 -> Grid3d.cpp:234-301.
+@pytest.fixture(scope="module")
+def full_host(O, full):
+    g = full["g"]
+    prob = g.downloadGrid()
+    m = O.Map(full["mn"], full["mx"], full["cfg"]["resol"], 0.05)
+    assert m.size == g.info()["size"]
+    m.set_prob(prob)
+    ref_grid = None
+    if O.ref_available():
+        ref_grid = O.RefGrid(m)
+    return dict(m=m, ref_grid=ref_grid)
+
+
+def _sample_vs_host(O, full_host, P, W, cloud, pick, beacons=None):
+    ref = O.update(full_host["m"], O.particles(P[pick]), cloud, threads=O.num_threads())
+    assert np.array_equal(bits(ref[:, 6]), bits(W[pick, 6])), "GPU weights differ from the oracle"
+    if full_host["ref_grid"] is not None:
+        rp = O.RefPF(full_host["ref_grid"])
+        rp.set(P[pick])
+        rp.update(cloud)
+        assert np.array_equal(bits(rp.get()[:, 6]), bits(W[pick, 6])), "GPU weights differ from the compiled reference"
+    return ref
+
+
+@pytest.mark.parametrize("kind", ["T", "G"])
+def test_config3_full_run_equals_oracle_and_compiled_reference(O, full, full_host, kind):
+    """C3 as benchmarked: 100 k particles x 10 k points, coded two-phase path; 640 sampled particles against the
+    oracle and the compiled reference on the downloaded 6.4 GB grid."""
+    from amcl3d_test_b200 import ParticleFilter, synth
+
+    g, cloud, cfg = full["g"], full["cloud"], full["cfg"]
+    assert g.info()["rep"] == 1
+    P = synth.make_particles(full["sm"], cfg["particles"], kind)
+    pf = ParticleFilter(g)
+    pf.p_ = P
+    pf.update(cloud)
+    assert pf.launch_count() >= 3 + 3  # cloud pack + sort, then pose + sweep + ordered sum: the large-set path ran
+    W = pf.p_
+    rng = np.random.RandomState(11)
+    pick = np.sort(rng.choice(P.shape[0], 640, replace=False))
+    ref = _sample_vs_host(O, full_host, P, W, cloud, pick)
+    assert (ref[:, 6] > 0).mean() > 0.5
+
+
+def test_config4_shape_sliced_staging_equals_oracle(O, full, full_host, monkeypatch):
+    """C4's shape on one GPU: a 20 k-point cloud and a particle set whose staged codes exceed the staging budget, so
+    the set is swept in >= 3 slices through the same buffer (capi.cu update_impl).  T and G particles mixed."""
+    from amcl3d_test_b200 import ParticleFilter, synth
+
+    g, sm = full["g"], full["sm"]
+    cloud = synth.make_cloud(sm, 20_000, 30.0)
+    n = 65_536
+    P = np.concatenate([synth.make_particles(sm, n // 2, "T"), synth.make_particles(sm, n // 2, "G")])
+    P = np.ascontiguousarray(P[np.random.RandomState(5).permutation(n)])
+    monkeypatch.setenv("AMCL3D_B200_STAGE_MB", "512")  # 256 x 20 000 B per tile -> 104 tiles = 26 624 particles per slice
+    pf = ParticleFilter(g)
+    pf.p_ = P
+    l0 = pf.launch_count()
+    pf.update(cloud)
+    assert pf.launch_count() - l0 >= 4 + 3 * 3  # set_cloud (pack + sort) and three slices of pose + sweep + sum
+    W = pf.p_
+    pick = np.sort(np.random.RandomState(12).choice(n, 512, replace=False))
+    _sample_vs_host(O, full_host, P, W, cloud, pick)
+
+
+def test_two_phase_toggled_after_set_cloud_sorts_lazily(O, full, full_host):
+    """set_two_phase(0), set_cloud(B), set_two_phase(1), update() used to sweep the Morton order of an
+    older cloud.  The sort now belongs to the cloud (sorted_valid) and is redone in update() when missing."""
+    from amcl3d_test_b200 import ParticleFilter, synth
+
+    g, sm = full["g"], full["sm"]
+    A = synth.make_cloud(sm, 3000, 30.0)
+    B = synth.make_cloud(sm, 4500, 25.0, seed=77)
+    P = synth.make_particles(sm, 8192, "T")
+    pf = ParticleFilter(g)
+    pf.p_ = P
+    pf.update(A)                      # two-phase on: sorted copy of A
+    pf.set_two_phase(False)
+    pf.p_ = P
+    pf.set_cloud(B)                   # no sort while the two-phase path is off
+    pf.set_two_phase(True)
+    pf.update()                       # resident cloud B
+    W = pf.p_
+    pick = np.arange(0, 8192, 32)
+    _sample_vs_host(O, full_host, P, W, B, pick)
+
+
+def test_config5s_beacons_equal_oracle(O):
+    """C5s (the ~2.6 GB grid BASELINE.json quotes: 4000 x 4000 x 40 voxels) with 8 UWB range beacons fused (row R):
+    every particle of an 8192-particle set against the oracle on the downloaded grid.  R itself has no code in the
+    reference tree: the cloud part is pinned, the range part is checked against our restatement."""
+    from amcl3d_test_b200 import Grid3d, ParticleFilter, synth
+
+    cfg = synth.CONFIGS["C5s"]
+    sm = synth.make_map(cfg["extent"], cfg["resol"])
+    g = Grid3d(0)
+    mn, mx = g.computePointCloud(sm.points, cfg["resol"])
+    g.computeGrid(sm.points, 0.05, sub=2)
+    assert g.info()["size"] == (4000, 4000, 40) and g.info()["rep"] == 1
+    m = O.Map(mn, mx, cfg["resol"], 0.05)
+    m.set_prob(g.downloadGrid())
+    cloud = synth.make_cloud(sm, 20_000, 30.0)
+    beacons = synth.make_beacons(sm, 8)
+    n = 8192
+    P = np.concatenate([synth.make_particles(sm, n - 1024, "T"), synth.make_particles(sm, 1024, "G")])
+    pf = ParticleFilter(g)
+    pf.p_ = P
+    pf.update(cloud, beacons=beacons, alpha=0.5, sigma=0.53)
+    W = pf.p_
+    ref = O.update(m, O.particles(P), cloud, threads=O.num_threads())
+    wr = O.range_weights(ref, beacons[0], beacons[1], 0.53)
+    inmap = np.array([O.is_into_map(m, *p[:3]) for p in ref])
+    wr[~inmap] = 0
+    O.fuse_range(ref, wr, 0.5)
+    # device expf vs glibc expf over 8 factors: tolerance 1e-4 relative (as in test_range_beacon_fusion)
+    den = np.maximum(np.abs(ref[:, 6]), 1e-30)
+    assert (np.abs(W[:, 6] - ref[:, 6]) / den).max() < 1e-4
+    assert np.array_equal(W[:, 6] == 0, ref[:, 6] == 0)
+    # and without beacons: the plain cloud weight, also against the compiled reference
+    pf.p_ = P
+    pf.update(cloud)
+    W0 = pf.p_
+    ref0 = O.update(m, O.particles(P), cloud, threads=O.num_threads())
+    assert np.array_equal(bits(ref0[:, 6]), bits(W0[:, 6]))
+    if O.ref_available():
+        rp = O.RefPF(O.RefGrid(m))
+        pick = np.arange(0, n, 16)
+        rp.set(P[pick])
+        rp.update(cloud)
+        assert np.array_equal(bits(rp.get()[:, 6]), bits(W0[pick, 6]))

@@ -398,7 +398,7 @@ def test_sequential_f32_chains_bit_exact(O, world_c1, pf, name, mode):
     P = np.zeros((w.size, 7), np.float32)
     P[:, :3] = np.array([10, 10, 1.0], np.float32)
     P[:, 6] = w
-    api.set_chain_mode(mode)
+    pf.set_chain_mode(mode)
     try:
         pf.p_ = P
         assert np.array_equal(bits(pf.prefix()), bits(O.prefix(P))), name
@@ -407,7 +407,7 @@ def test_sequential_f32_chains_bit_exact(O, world_c1, pf, name, mode):
         assert bits(pf.particleNormalize()) == bits(wtp), name
         assert np.array_equal(bits(pf.p_[:, 6]), bits(ref[:, 6])), name
     finally:
-        api.set_chain_mode(0)
+        pf.set_chain_mode(0)
 
 
 def _big_weights(name):

@@ -27,7 +27,7 @@ def main():
             pf.p_ = P
             ref = None
             for mode in (0, 2, 1):
-                api.set_chain_mode(mode)
+                pf.set_chain_mode(mode)
                 ms = []
                 for it in range(6):
                     dp = C.c_void_p()
@@ -38,7 +38,7 @@ def main():
                     ref = out
                 same = np.array_equal(out.view(np.uint32), ref.view(np.uint32))
                 print(f"n={n:>9} {name:<10} mode={mode} prefix {np.median(ms[1:]) * 1e3:8.1f} us  identical={same}", flush=True)
-            api.set_chain_mode(0)
+            pf.set_chain_mode(0)
 
 
 if __name__ == "__main__":

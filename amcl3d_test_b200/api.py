@@ -83,6 +83,15 @@ class Grid3d:
         xyz = _f32(xyz)
         check(self._L.amcl3d_b200_grid_build(self._h, xyz.ctypes.data, xyz.shape[1], xyz.shape[0], float(sensor_dev), mode, sub, int(keep_edt)))
 
+    def computeGridDevice(self, d_xyz: int, stride: int, n: int, sensor_dev, mode=GRID_QUIRK, sub=2, keep_edt=False):
+        """computeGrid from map points resident in device memory (raw pointer)."""
+        check(self._L.amcl3d_b200_grid_build_device(self._h, C.c_void_p(d_xyz), stride, n, float(sensor_dev), mode, sub, int(keep_edt)))
+
+    def last_build_ms(self) -> float:
+        ms = C.c_float(0)
+        check(self._L.amcl3d_b200_grid_last_build_ms(self._h, C.byref(ms)))
+        return ms.value
+
     def edt(self) -> np.ndarray:
         n = self.info()["n_cells"]
         out = np.empty(n, np.int32)
@@ -375,6 +384,12 @@ class ParticleFilter:
         ms = C.c_float(0)
         check(self._L.amcl3d_b200_pf_last_kernel_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def last_phase_ms(self):
+        """(pose, sweep, ordered sum) ms of the last large-set update; zeros when the single-kernel path ran."""
+        ms = (C.c_float * 3)()
+        check(self._L.amcl3d_b200_pf_last_phase_ms(self._h, ms))
+        return tuple(float(v) for v in ms)
 
     def launch_count(self) -> int:
         n = C.c_uint64(0)

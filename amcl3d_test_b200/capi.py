@@ -15,7 +15,8 @@ GRID_QUIRK, GRID_GAUSSIAN, GRID_SPLAT = 0, 1, 2
 SYMBOLS = [
     "amcl3d_b200_abi_version", "amcl3d_b200_last_error", "amcl3d_b200_device_info",
     "amcl3d_b200_set_l2_fetch_granularity", "amcl3d_b200_get_l2_fetch_granularity", "amcl3d_b200_pf_set_chain_mode",
-    "amcl3d_b200_grid_set_edt_fast",
+    "amcl3d_b200_grid_set_edt_fast", "amcl3d_b200_grid_build_device", "amcl3d_b200_grid_last_build_ms",
+    "amcl3d_b200_pf_last_phase_ms",
     "amcl3d_b200_grid_create", "amcl3d_b200_grid_destroy", "amcl3d_b200_grid_get_info",
     "amcl3d_b200_grid_compute_bounds", "amcl3d_b200_grid_set_map", "amcl3d_b200_grid_build",
     "amcl3d_b200_grid_download_edt", "amcl3d_b200_grid_upload", "amcl3d_b200_grid_download",
@@ -80,6 +81,9 @@ def load():
         "amcl3d_b200_device_info": (i, [i, P(i), P(i), P(i), P(i), P(u64), P(u64)]),
         "amcl3d_b200_pf_set_chain_mode": (i, [vp, i]),
         "amcl3d_b200_grid_set_edt_fast": (i, [vp, i]),
+        "amcl3d_b200_grid_build_device": (i, [vp, vp, u32, u64, f64, i, i, i]),
+        "amcl3d_b200_grid_last_build_ms": (i, [vp, P(f32)]),
+        "amcl3d_b200_pf_last_phase_ms": (i, [vp, P(f32)]),
         "amcl3d_b200_set_l2_fetch_granularity": (i, [i, i]),
         "amcl3d_b200_get_l2_fetch_granularity": (i, [i, P(i)]),
         "amcl3d_b200_grid_create": (i, [i, P(vp)]),

@@ -84,6 +84,8 @@ struct amcl3d_b200_grid_s
   int edt_fast = 1;        // AMCL3D_B200_EDT_FAST=0 or amcl3d_b200_grid_set_edt_fast: exact envelope passes always
   cudaStream_t stream = nullptr;
   amcl3d_b200_pf_t scratch_pf = nullptr;  // for the single-pose computeCloudWeight
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the kernels of the last build
+  bool build_timed = false;
 };
 
 struct amcl3d_b200_pf_s
@@ -141,6 +143,8 @@ struct amcl3d_b200_pf_s
   BeaconSet* d_beacons = nullptr;
   void* d_scratch = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_phase[4] = { nullptr, nullptr, nullptr, nullptr };  // pose | sweep | ordered sum of the last large-set update
+  bool phase_timed = false;
   bool timed = false;
   bool async_mode = false;  // amcl3d_b200_pf_set_async: calls that hand nothing back to the host do not synchronise
   uint64_t launches = 0;
@@ -335,9 +339,13 @@ int amcl3d_b200_grid_create(int device, amcl3d_b200_grid_t* out)
     (void)cudaGetLastError();
   }
   cudaError_t e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess)
+    e = cudaEventCreate(&g->ev0);
+  if (e == cudaSuccess)
+    e = cudaEventCreate(&g->ev1);
   if (e != cudaSuccess)
   {
-    delete g;
+    amcl3d_b200_grid_destroy(g);
     return fail_cuda(e, "cudaStreamCreate");
   }
   *out = g;
@@ -354,6 +362,10 @@ int amcl3d_b200_grid_destroy(amcl3d_b200_grid_t g)
   cudaFree(g->d_prob);
   cudaFree(g->d_edt);
   drop_codes(g);
+  if (g->ev0)
+    cudaEventDestroy(g->ev0);
+  if (g->ev1)
+    cudaEventDestroy(g->ev1);
   if (g->stream)
     cudaStreamDestroy(g->stream);
   delete g;
@@ -501,7 +513,8 @@ int amcl3d_b200_grid_device_ptr(amcl3d_b200_grid_t g, void** d_prob)
   return AMCL3D_B200_OK;
 }
 
-int amcl3d_b200_grid_build(amcl3d_b200_grid_t g, const float* xyz, uint32_t stride, uint64_t n, double sensor_dev,
+// xyz: HOST points (copied H2D first) or, with on_device, a DEVICE buffer used in place
+static int grid_build_impl(amcl3d_b200_grid_t g, const float* xyz, bool on_device, uint32_t stride, uint64_t n, double sensor_dev,
                            int mode, int sub, int keep_edt)
 {
   if (!g || !xyz || stride < 3)
@@ -515,6 +528,7 @@ int amcl3d_b200_grid_build(amcl3d_b200_grid_t g, const float* xyz, uint32_t stri
   if (int rc = use_device(g->device))
     return rc;
   g->map.has_grid = 0;
+  g->build_timed = false;
   size_from_bounds(g);
   refresh_map(g);
   const uint64_t cells = g->map.n_cells;
@@ -528,21 +542,29 @@ int amcl3d_b200_grid_build(amcl3d_b200_grid_t g, const float* xyz, uint32_t stri
   drop_codes(g);
   refresh_map(g);
 
-  float* d_xyz = nullptr;
-  CU(cudaMalloc(&d_xyz, sizeof(float) * std::max<uint64_t>(n, 1) * stride));
-  cudaError_t e = cudaMemcpyAsync(d_xyz, xyz, sizeof(float) * n * stride, cudaMemcpyHostToDevice, g->stream);
+  float* d_own = nullptr;
+  const float* d_xyz = xyz;
+  cudaError_t e = cudaSuccess;
+  if (!on_device)
+  {
+    CU(cudaMalloc(&d_own, sizeof(float) * std::max<uint64_t>(n, 1) * stride));
+    e = cudaMemcpyAsync(d_own, xyz, sizeof(float) * n * stride, cudaMemcpyHostToDevice, g->stream);
+    d_xyz = d_own;
+  }
   char msg[256] = { 0 };
   if (e == cudaSuccess)
   {
+    cudaEventRecord(g->ev0, g->stream);
     if (mode == AMCL3D_B200_GRID_SPLAT)
       e = build_grid_splat(g->map, d_xyz, stride, n, sensor_dev, g->d_prob, g->stream);
     else
       e = build_grid_edt(g->map, d_xyz, stride, n, sensor_dev, mode, sub, g->d_prob, keep_edt ? &g->d_edt : nullptr,
                          g->use_codes ? &g->coded : nullptr, g->edt_fast, g->stream, msg, sizeof(msg));
+    cudaEventRecord(g->ev1, g->stream);
   }
   if (e == cudaSuccess)
     e = cudaStreamSynchronize(g->stream);
-  cudaFree(d_xyz);
+  cudaFree(d_own);
   if (e != cudaSuccess)
   {
     if (msg[0])
@@ -552,11 +574,35 @@ int amcl3d_b200_grid_build(amcl3d_b200_grid_t g, const float* xyz, uint32_t stri
     }
     return fail_cuda(e, "grid build");
   }
+  g->build_timed = true;
   if (g->d_edt)
     g->edt_cells = cells;
   g->sensor_dev = sensor_dev;
   g->map.has_grid = 1;
   refresh_map(g);
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_grid_build(amcl3d_b200_grid_t g, const float* xyz, uint32_t stride, uint64_t n, double sensor_dev,
+                           int mode, int sub, int keep_edt)
+{
+  return grid_build_impl(g, xyz, false, stride, n, sensor_dev, mode, sub, keep_edt);
+}
+
+int amcl3d_b200_grid_build_device(amcl3d_b200_grid_t g, const void* d_xyz, uint32_t stride, uint64_t n, double sensor_dev,
+                                  int mode, int sub, int keep_edt)
+{
+  return grid_build_impl(g, reinterpret_cast<const float*>(d_xyz), true, stride, n, sensor_dev, mode, sub, keep_edt);
+}
+
+int amcl3d_b200_grid_last_build_ms(amcl3d_b200_grid_t g, float* ms)
+{
+  if (!g || !ms)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  *ms = 0.f;
+  if (!g->build_timed)
+    return AMCL3D_B200_OK;
+  CU(cudaEventElapsedTime(ms, g->ev0, g->ev1));
   return AMCL3D_B200_OK;
 }
 
@@ -712,6 +758,8 @@ int amcl3d_b200_pf_create(amcl3d_b200_grid_t g, amcl3d_b200_pf_t* out)
     e = cudaEventCreate(&pf->ev0);
   if (e == cudaSuccess)
     e = cudaEventCreate(&pf->ev1);
+  for (int k = 0; k < 4 && e == cudaSuccess; ++k)
+    e = cudaEventCreate(&pf->ev_phase[k]);
   if (e == cudaSuccess)
     e = cudaMalloc(&pf->d_scalars, 64 * sizeof(float));
   if (e == cudaSuccess)
@@ -767,6 +815,9 @@ int amcl3d_b200_pf_destroy(amcl3d_b200_pf_t pf)
     cudaEventDestroy(pf->ev0);
   if (pf->ev1)
     cudaEventDestroy(pf->ev1);
+  for (int k = 0; k < 4; ++k)
+    if (pf->ev_phase[k])
+      cudaEventDestroy(pf->ev_phase[k]);
   if (pf->own_stream)
     cudaStreamDestroy(pf->own_stream);
   delete pf;
@@ -1091,9 +1142,16 @@ static int update_impl(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beacons,
       if (tpp && n_s)
       {
         // phase 0: rotation + offsets once per particle of this slice
+        cudaEventRecord(pf->ev_phase[0], pf->stream);
         CU(launch_pose(map, pf->d_p + 7 * off, (uint32_t)n_s, pf->trig_mode, pf->d_pose, pf->stream));
+        cudaEventRecord(pf->ev_phase[1], pf->stream);
         tp.pose_pitch = (uint32_t)((n_s + pitch_w - 1) / pitch_w * pitch_w);
+        tp.ev_mid = pf->ev_phase[2];
+        tp.ev_end = pf->ev_phase[3];
+        pf->phase_timed = true;
       }
+      else
+        pf->phase_timed = false;
       CU(launch_update(map, pf->d_p + 7 * off, (uint32_t)n_s, pf->d_cloud, pf->npts, pf->npad, pf->d_beacons,
                        d_wr ? d_wr + off : nullptr, pf->trig_mode, d_counter, tpp, pf->stream));
       pf->launches += n_s ? (tpp ? 3 : 1) : 0;
@@ -1560,6 +1618,19 @@ int amcl3d_b200_pf_last_kernel_ms(amcl3d_b200_pf_t pf, float* ms)
     return AMCL3D_B200_OK;
   CU(cudaEventSynchronize(pf->ev1));
   CU(cudaEventElapsedTime(ms, pf->ev0, pf->ev1));
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_last_phase_ms(amcl3d_b200_pf_t pf, float ms[3])
+{
+  if (!pf || !ms)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  ms[0] = ms[1] = ms[2] = 0.f;
+  if (!pf->phase_timed)
+    return AMCL3D_B200_OK;
+  CU(cudaEventSynchronize(pf->ev_phase[3]));
+  for (int k = 0; k < 3; ++k)
+    CU(cudaEventElapsedTime(&ms[k], pf->ev_phase[k], pf->ev_phase[k + 1]));
   return AMCL3D_B200_OK;
 }
 

@@ -114,6 +114,7 @@ struct TwoPhase
   uint8_t* stage;
   const float* pose;
   uint32_t pose_pitch;
+  cudaEvent_t ev_mid, ev_end;  // nullable: recorded between the sweep and the ordered sum / after the ordered sum
 };
 size_t pose_floats(uint32_t n);
 bool two_phase_supported(const MapDev& map);  // u8 codes and a map the branch-free sweep arithmetic is valid for

@@ -646,6 +646,346 @@ __global__ void encode_kernel(const int32_t* __restrict__ d2, uint32_t sx, uint3
     *reinterpret_cast<ushort4*>(codes + t) = make_ushort4(out[0], out[1], out[2], out[3]);
 }
 
+
+// ====================================================================================================================
+// Fused fast build (default when the exact EDT is not kept and there is a single dense lattice class)
+// ====================================================================================================================
+// The field only needs min(d2, cap) (cap = smallest squared lattice distance whose probability is exactly 0.0f), so the
+// minimising site lies within R = floor(sqrt(cap - 1)) lattice steps along every axis and each separable pass is a
+// min-plus stencil over at most 2H+1 sites.  Three launches, HBM-streaming, no int32 intermediates:
+//   xpass8_kernel     occupancy bit rows -> u8  |dx| (capped), 32 outputs per thread by two register sweeps
+//   ypass_dpx_kernel  u8 -> u16 min(dx^2 + dy^2, cap); two columns per lane packed as u16x2, candidates evaluated with
+//                     the DPX instruction VIADDMNMX.U16x2 (min(a + b, c) on both halves), squared offsets as immediates
+//   zpass_dpx_kernel  u16 -> min(d^2, cap), then in the same epilogue the dictionary code (the set of attainable d^2 of the
+//                     class is known beforehand: sums of three squares of the class parity below cap), the float cell
+//                     prob = lut[code] (PointCloudTools.cpp:160-162, evaluated once per dictionary entry by lut_kernel with
+//                     the same device function as the legacy writer) into the linear float grid, and the code into the
+//                     128-byte bricks of the page-blocked copy (staged in shared memory, written as whole bricks).
+// Sites of sparse classes (e.g. the two extreme corner points that pin the bounds) are patched in afterwards over their
+// (2R+1)^3 boxes.  Results are identical to the legacy passes bit for bit (test_gpu_grid.py).
+struct FastArgs
+{
+  uint32_t sx, sy, sz;  // outputs per axis
+  uint32_t w1, w2;      // site rows along y and z (size + 1)
+  uint32_t px;          // x pitch of the intermediates, multiple of 64
+  uint32_t cap;
+};
+constexpr int kFastPer = 8;  // outputs per thread and sweep of the DPX passes
+
+__global__ void __launch_bounds__(256)
+    xpass8_kernel(const uint32_t* __restrict__ bits, uint32_t words_per_row, uint64_t rows, uint32_t px, int sub, int par,
+                  uint32_t d1cap, uint8_t* __restrict__ d1)
+{
+  const uint32_t chunks = px / 32;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * chunks)
+    return;
+  const uint64_t row = t / chunks;
+  const uint32_t wq = (uint32_t)(t % chunks);
+  const uint32_t* r = bits + row * words_per_row;
+  auto word = [&](int64_t w) -> uint32_t { return (w >= 0 && w < (int64_t)words_per_row) ? r[w] : 0u; };
+  const uint32_t W = word(wq), p1 = word((int64_t)wq - 1), p2 = word((int64_t)wq - 2), n1 = word((int64_t)wq + 1),
+                 n2 = word((int64_t)wq + 2);
+  constexpr int kFar = 1 << 20;
+  // distance (in sites) from the position just left of this word to the nearest site at or before it / from the
+  // position just right of it to the nearest site at or after it; two words each side cover any window (H <= 46)
+  int carry_l = p1 ? __clz(p1) : (p2 ? 32 + __clz(p2) : kFar);
+  int carry_r = n1 ? __ffs(n1) - 1 : (n2 ? 32 + __ffs(n2) - 1 : kFar);
+  int dl[32];
+  int run = carry_l;
+#pragma unroll
+  for (int b = 0; b < 32; ++b)
+  {
+    run = ((W >> b) & 1u) ? 0 : run + 1;
+    dl[b] = run;
+  }
+  uint32_t out[8];
+  run = carry_r;
+#pragma unroll
+  for (int b = 31; b >= 0; --b)
+  {
+    run = ((W >> b) & 1u) ? 0 : run + 1;
+    // site at or left: |sub*dl - par|; site at or right: sub*dr + par
+    int d = min(abs(sub * dl[b] - par), sub * run + par);
+    d = min(d, (int)d1cap);
+    if ((b & 3) == 3)
+      out[b >> 2] = 0;
+    out[b >> 2] |= (uint32_t)d << (8 * (b & 3));
+  }
+  uint4* dst = reinterpret_cast<uint4*>(d1 + row * px + (uint64_t)wq * 32);
+  dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+  dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+}
+
+// one sweep of the min-plus stencil for kFastPer consecutive outputs of one lane (two packed columns): rows[t] is the
+// candidate site row (first output - H + t); delta = output - site is a compile-time constant of every (t, k) pair, so
+// its squared offset is an immediate operand of VIADDMNMX
+template <int SUB, int PAR, int H, typename RowFn>
+__device__ __forceinline__ void dpx_sweep(RowFn row, uint32_t best[kFastPer])
+{
+#pragma unroll
+  for (int t = 0; t < kFastPer + 2 * H; ++t)
+  {
+    const uint32_t v = row(t);
+#pragma unroll
+    for (int k = 0; k < kFastPer; ++k)
+    {
+      const int delta = k - (t - H);
+      if (delta >= -H && delta <= H)
+      {
+        const int d = SUB * delta - PAR;
+        best[k] = __viaddmin_u16x2(v, (uint32_t)(d * d) * 0x10001u, best[k]);
+      }
+    }
+  }
+}
+
+// in: d1 [plane z][site row j][px] u8, out: dxy [plane z][output row i][px] u16
+template <int SUB, int PAR, int H>
+__global__ void __launch_bounds__(256) ypass_dpx_kernel(const uint8_t* __restrict__ d1, uint16_t* __restrict__ dxy,
+                                                       const __grid_constant__ FastArgs A)
+{
+  constexpr int kTI = 8 * kFastPer;  // 8 warps x 8 outputs
+  constexpr int kRows = kTI + 2 * H;
+  __shared__ uint32_t tile[kRows][32];
+  const uint32_t ctiles = A.px / 64, itiles = (A.sy + kTI - 1) / kTI;
+  uint32_t b = blockIdx.x;
+  const uint32_t it = b % itiles;
+  b /= itiles;
+  const uint32_t ct = b % ctiles;
+  const uint32_t plane = b / ctiles;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const int i0 = (int)(it * kTI);
+  const uint32_t cap = A.cap, cap2 = cap * 0x10001u;
+  const uint8_t* src = d1 + ((uint64_t)plane * A.w1) * A.px + ct * 64 + 2 * lane;
+  for (int r = (int)warp; r < kRows; r += 8)
+  {
+    const int j = i0 - H + r;
+    uint32_t v2 = cap2;
+    if (j >= 0 && j < (int)A.w1)
+    {
+      const uint32_t raw = *reinterpret_cast<const uint16_t*>(src + (uint64_t)j * A.px);
+      const uint32_t a = raw & 0xFFu, c = raw >> 8;
+      v2 = min(a * a, cap) | (min(c * c, cap) << 16);
+    }
+    tile[r][lane] = v2;
+  }
+  __syncthreads();
+  uint32_t best[kFastPer];
+#pragma unroll
+  for (int k = 0; k < kFastPer; ++k)
+    best[k] = cap2;
+  const uint32_t base = warp * kFastPer;
+  dpx_sweep<SUB, PAR, H>([&](int t) { return tile[base + t][lane]; }, best);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(dxy + ((uint64_t)plane * A.sy) * A.px + ct * 64 + 2 * lane);
+#pragma unroll
+  for (int k = 0; k < kFastPer; ++k)
+  {
+    const uint32_t i = (uint32_t)i0 + base + k;
+    if (i < A.sy)
+      dst[(uint64_t)i * (A.px / 2)] = best[k];
+  }
+}
+
+// in: dxy [site row j = z][y][px] u16; out: prob [z][y][sx] f32 and the bricked u8 codes.
+// Block tile: 64 x (32 lanes x 2) x 4 y x 32 z = 8 x 1 x 8 bricks; thread = (lane, y, z group of 16) does two sweeps of 8.
+constexpr int kZT = 32;
+constexpr int kBrickPitch = 132;  // bytes between staged bricks (33 words: conflict-free column writes)
+template <int SUB, int PAR, int H>
+__global__ void __launch_bounds__(256)
+    zpass_dpx_kernel(const uint16_t* __restrict__ dxy, float* __restrict__ prob, uint8_t* __restrict__ codes,
+                     const __grid_constant__ FastArgs A, const uint8_t* __restrict__ rank, const float* __restrict__ lut,
+                     uint32_t nbx, uint32_t nby)
+{
+  constexpr int kRows = kZT + 2 * H;
+  extern __shared__ __align__(16) uint32_t zsm[];
+  uint32_t(*tile)[4][32] = reinterpret_cast<uint32_t(*)[4][32]>(zsm);                          // [kRows][4][32]
+  uint8_t* stage = reinterpret_cast<uint8_t*>(zsm + (size_t)kRows * 4 * 32);                  // 64 bricks x kBrickPitch
+  const uint32_t ztiles = (A.sz + kZT - 1) / kZT, ctiles = A.px / 64;
+  uint32_t b = blockIdx.x;
+  const uint32_t zt = b % ztiles;  // z fastest: neighbouring blocks share their halo rows in L2
+  b /= ztiles;
+  const uint32_t ct = b % ctiles;
+  const uint32_t yt = b / ctiles;
+  const uint32_t lane = threadIdx.x & 31u, ty = (threadIdx.x >> 5) & 3u, zg = threadIdx.x >> 7;
+  const uint32_t x0 = ct * 64, y0 = yt * 4;
+  const int z0 = (int)(zt * kZT);
+  const uint32_t cap = A.cap, cap2 = cap * 0x10001u;
+  {
+    const uint32_t warp = threadIdx.x >> 5;
+    for (int q = (int)warp; q < kRows * 4; q += 8)
+    {
+      const int r = q >> 2;
+      const uint32_t y = (uint32_t)q & 3u;
+      const int j = z0 - H + r;
+      uint32_t v2 = cap2;
+      if (j >= 0 && j < (int)A.w2 && y0 + y < A.sy)
+        v2 = *reinterpret_cast<const uint32_t*>(dxy + ((uint64_t)j * A.sy + (y0 + y)) * A.px + x0 + 2 * lane);
+      tile[r][y][lane] = v2;
+    }
+  }
+  __syncthreads();
+  const uint32_t x = x0 + 2 * lane, y = y0 + ty;
+#pragma unroll 1
+  for (int s = 0; s < 2; ++s)
+  {
+    const uint32_t zb = zg * 16 + s * 8;  // first output of this sweep, relative to the tile
+    uint32_t best[kFastPer];
+#pragma unroll
+    for (int k = 0; k < kFastPer; ++k)
+      best[k] = cap2;
+    dpx_sweep<SUB, PAR, H>([&](int t) { return tile[zb + t][ty][lane]; }, best);
+#pragma unroll
+    for (int k = 0; k < kFastPer; ++k)
+    {
+      const uint32_t zr = zb + k, z = (uint32_t)z0 + zr;
+      const uint32_t ca = rank[best[k] & 0xFFFFu], cb = rank[best[k] >> 16];
+      // staged brick (bz, bx) of the tile, voxel (z&3, y&3, x&7): two x neighbours = one 16-bit store
+      const uint32_t so = ((zr >> 2) * 8 + (lane >> 2)) * kBrickPitch + (((zr & 3u) << 5) | (ty << 3) | ((2 * lane) & 7u));
+      *reinterpret_cast<uint16_t*>(stage + so) = (uint16_t)(ca | (cb << 8));
+      if (z < A.sz && y < A.sy)
+      {
+        float* dst = prob + ((uint64_t)z * A.sy + y) * A.sx + x;
+        const float pa = lut[ca], pb = lut[cb];
+        if (!(A.sx & 1u) && x + 1 < A.sx)
+          *reinterpret_cast<float2*>(dst) = make_float2(pa, pb);
+        else
+        {
+          if (x < A.sx)
+            dst[0] = pa;
+          if (x + 1 < A.sx)
+            dst[1] = pb;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // whole bricks out: thread = (brick, quarter), 32 bytes each; the 8 x-bricks of one z layer are 1 KB contiguous
+  {
+    const uint32_t brick = threadIdx.x >> 2, part = threadIdx.x & 3u;
+    const uint32_t bz = brick >> 3, bx = brick & 7u;
+    const uint32_t* srcw = reinterpret_cast<const uint32_t*>(stage + brick * kBrickPitch) + part * 8;
+    const uint64_t o = coded_index<kRepCode8>(x0 + bx * 8, y0, (uint32_t)z0 + bz * 4, nbx, nby) + part * 32;
+    uint4* dst = reinterpret_cast<uint4*>(codes + o);
+    dst[0] = make_uint4(srcw[0], srcw[1], srcw[2], srcw[3]);
+    dst[1] = make_uint4(srcw[4], srcw[5], srcw[6], srcw[7]);
+  }
+}
+
+// ---- sparse sites after the fused passes ------------------------------------------------------------------------------
+// thread = (sparse site s, voxel of its (2W+1)^3 box); the voxel's squared distance to the NEAREST sparse site (all of
+// them are scanned, so overlapping boxes compute identical values and no atomics are needed) against what the dense
+// class left there.  mark: needed[d2] = 1 for values that win; apply: rewrite code and float cell.
+template <bool kApply>
+__global__ void sparse_patch_kernel(const int4* __restrict__ sparse, int nsparse, int W, int sub, uint32_t sx, uint32_t sy,
+                                    uint32_t sz, uint32_t nbx, uint32_t nby, uint32_t cap, const int32_t* __restrict__ values,
+                                    const uint8_t* __restrict__ rank, const float* __restrict__ lut, uint8_t* __restrict__ codes,
+                                    float* __restrict__ prob, uint8_t* __restrict__ needed)
+{
+  const int side = 2 * W + 1;
+  const uint64_t per = (uint64_t)side * side * side;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= per * (uint64_t)nsparse)
+    return;
+  const int s = (int)(t / per);
+  uint64_t v = t % per;
+  const int4 h = sparse[s];
+  // voxel nearest to the site, then the box around it
+  const int cx = (h.x + sub / 2) / sub, cy = (h.y + sub / 2) / sub, cz = (h.z + sub / 2) / sub;
+  const int ix = cx - W + (int)(v % side);
+  v /= side;
+  const int iy = cy - W + (int)(v % side);
+  const int iz = cz - W + (int)(v / side);
+  if (ix < 0 || iy < 0 || iz < 0 || ix >= (int)sx || iy >= (int)sy || iz >= (int)sz)
+    return;
+  int best = INT32_MAX;
+  for (int q = 0; q < nsparse; ++q)
+  {
+    const int4 g = sparse[q];
+    const int dx = sub * ix - g.x, dy = sub * iy - g.y, dz = sub * iz - g.z;
+    if (abs(dx) > 30000 || abs(dy) > 30000 || abs(dz) > 30000)
+      continue;
+    best = min(best, dx * dx + dy * dy + dz * dz);
+  }
+  if ((uint32_t)best >= cap)
+    return;
+  const uint64_t o = coded_index<kRepCode8>((uint32_t)ix, (uint32_t)iy, (uint32_t)iz, nbx, nby);
+  const int32_t cur = values[codes[o]];
+  if (best >= cur)
+    return;
+  if (!kApply)
+    needed[best] = 1;
+  else
+  {
+    const uint8_t c = rank[best];
+    codes[o] = c;
+    prob[((uint64_t)iz * sy + iy) * sx + ix] = lut[c];
+  }
+}
+
+template <int SUB, int PAR, int H>
+static cudaError_t launch_y_t(const FastArgs& A, const uint8_t* d1, uint16_t* dxy, unsigned blocks, cudaStream_t stream)
+{
+  ypass_dpx_kernel<SUB, PAR, H><<<blocks, 256, 0, stream>>>(d1, dxy, A);
+  return cudaGetLastError();
+}
+template <int SUB, int PAR, int H>
+static cudaError_t launch_z_t(const FastArgs& A, const uint16_t* dxy, float* prob, uint8_t* codes, const uint8_t* rank,
+                              const float* lut, uint32_t nbx, uint32_t nby, unsigned blocks, cudaStream_t stream)
+{
+  const size_t smem = (size_t)(kZT + 2 * H) * 4 * 32 * 4 + 64 * kBrickPitch;
+  // per-device attribute of the function: set on every launch (cheap), never cached process-wide
+  cudaError_t e = cudaFuncSetAttribute(zpass_dpx_kernel<SUB, PAR, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess)
+    return e;
+  zpass_dpx_kernel<SUB, PAR, H><<<blocks, 256, smem, stream>>>(dxy, prob, codes, A, rank, lut, nbx, nby);
+  return cudaGetLastError();
+}
+// window half-widths the passes are instantiated for (a wider window than needed is still exact: the extra candidates
+// are farther than R and cannot beat the cap)
+#define A3D_FOR_H(CALL)   \
+  if (h <= 12)            \
+    return CALL(12);      \
+  if (h <= 20)            \
+    return CALL(20);      \
+  if (h <= 28)            \
+    return CALL(28);      \
+  if (h <= 36)            \
+    return CALL(36);      \
+  return CALL(46);
+template <int SUB, int PAR>
+static cudaError_t launch_y_h(int h, const FastArgs& A, const uint8_t* d1, uint16_t* dxy, unsigned blocks, cudaStream_t stream)
+{
+#define A3D_Y(HH) launch_y_t<SUB, PAR, HH>(A, d1, dxy, blocks, stream)
+  A3D_FOR_H(A3D_Y)
+#undef A3D_Y
+}
+template <int SUB, int PAR>
+static cudaError_t launch_z_h(int h, const FastArgs& A, const uint16_t* dxy, float* prob, uint8_t* codes, const uint8_t* rank,
+                              const float* lut, uint32_t nbx, uint32_t nby, unsigned blocks, cudaStream_t stream)
+{
+#define A3D_Z(HH) launch_z_t<SUB, PAR, HH>(A, dxy, prob, codes, rank, lut, nbx, nby, blocks, stream)
+  A3D_FOR_H(A3D_Z)
+#undef A3D_Z
+}
+static cudaError_t launch_y(int sub, int par, int h, const FastArgs& A, const uint8_t* d1, uint16_t* dxy, unsigned blocks,
+                            cudaStream_t stream)
+{
+  if (sub == 1)
+    return launch_y_h<1, 0>(h, A, d1, dxy, blocks, stream);
+  return par ? launch_y_h<2, 1>(h, A, d1, dxy, blocks, stream) : launch_y_h<2, 0>(h, A, d1, dxy, blocks, stream);
+}
+static cudaError_t launch_z(int sub, int par, int h, const FastArgs& A, const uint16_t* dxy, float* prob, uint8_t* codes,
+                            const uint8_t* rank, const float* lut, uint32_t nbx, uint32_t nby, unsigned blocks, cudaStream_t stream)
+{
+  if (sub == 1)
+    return launch_z_h<1, 0>(h, A, dxy, prob, codes, rank, lut, nbx, nby, blocks, stream);
+  return par ? launch_z_h<2, 1>(h, A, dxy, prob, codes, rank, lut, nbx, nby, blocks, stream)
+             : launch_z_h<2, 0>(h, A, dxy, prob, codes, rank, lut, nbx, nby, blocks, stream);
+}
+constexpr int kFastMaxH = 46;
+constexpr int kFastMaxSparse = 64;
+
 void gauss_consts(double sensor_dev, float* c1, float* c2)
 {
   *c1 = static_cast<float>(1. / (sensor_dev * sqrt(2 * M_PI)));   // PointCloudTools.cpp:139
@@ -725,6 +1065,177 @@ static cudaError_t find_cap(const Gauss& G, unsigned int* h_cap, cudaStream_t st
   if (rc == cudaSuccess)
     rc = cudaStreamSynchronize(stream);
   cudaFree(d_cap);
+  return rc;
+}
+
+
+// The fused fast build for one dense class (see the kernel block above).  *done = false (and nothing kept) when the
+// configuration is outside what it covers: the caller then runs the legacy passes.
+static cudaError_t build_fast(const MapDev& map, const Lattice& L, const float* d_xyz, uint32_t stride, uint64_t n, const Gauss& G,
+                              int cls, const int4* d_sparse, int nsparse, uint64_t pblocks, float* prob, CodedGrid* out,
+                              cudaStream_t stream, bool* done)
+{
+  cudaError_t rc = cudaSuccess;
+  *done = false;
+  const int sub = L.sub;
+  const int par[3] = { cls & 1, (cls >> 1) & 1, (cls >> 2) & 1 };
+  const uint32_t sx = map.size[0], sy = map.size[1], sz = map.size[2];
+  unsigned int h_cap = 0xFFFFFFFFu;
+  uint32_t* d_bits = nullptr;
+  uint8_t* d_d1 = nullptr;
+  uint16_t* d_dxy = nullptr;
+  uint8_t* d_rank = nullptr;
+  uint8_t* d_needed = nullptr;
+  int32_t* d_values = nullptr;
+  float* d_lut = nullptr;
+  void* d_codes = nullptr;
+  std::vector<int32_t> values;
+  std::vector<uint8_t> rank, needed;
+
+  CK(find_cap(G, &h_cap, stream));
+  if (h_cap == 0xFFFFFFFFu || h_cap < 2 || h_cap > 30000u)
+    goto done;
+  {
+    const uint32_t cap = h_cap;
+    const int R = (int)floor(sqrt((double)(cap - 1)));
+    const int H = (R + 1) / sub + 1;  // candidate sites on each side of an output
+    uint32_t d1cap = (uint32_t)R + 1;  // d1cap^2 >= cap
+    while (d1cap * d1cap < cap)
+      ++d1cap;
+    if (H > kFastMaxH || d1cap > 255u || nsparse > kFastMaxSparse)
+      goto done;
+    // dictionary known beforehand: sums of three squares of the class parity below cap, then the zero class
+    {
+      std::vector<uint8_t> present(cap + 1, 0);
+      auto axis = [&](int pa, std::vector<int>& o) {
+        for (int d = 0; d <= R + sub; ++d)
+          if (sub == 1 || (d & 1) == pa)
+            o.push_back(d * d);
+      };
+      std::vector<int> ax, ay, az;
+      axis(par[0], ax);
+      axis(par[1], ay);
+      axis(par[2], az);
+      for (int a : ax)
+        for (int b : ay)
+          for (int c : az)
+            if ((uint32_t)(a + b + c) < cap)
+              present[a + b + c] = 1;
+      rank.assign(cap + 1, 0);
+      for (uint32_t k = 0; k < cap; ++k)
+        if (present[k])
+        {
+          rank[k] = (uint8_t)(values.size() & 0xFF);
+          values.push_back((int32_t)k);
+        }
+      if (values.size() > 253)
+        goto done;  // 8-bit codes with 0xFF reserved: the legacy coder decides between u8 and u16
+      rank[cap] = (uint8_t)values.size();
+      values.push_back((int32_t)cap);
+    }
+    const uint32_t nbx = (sx + 127) / 128, nby = (sy + 127) / 128, nbz = (sz + 127) / 128;
+    const uint64_t code_bytes = ((uint64_t)nbx * nby * nbz) << 21;
+    FastArgs A;
+    A.sx = sx;
+    A.sy = sy;
+    A.sz = sz;
+    A.w1 = (uint32_t)L.w[1];
+    A.w2 = (uint32_t)L.w[2];
+    A.px = (sx + 63u) & ~63u;
+    A.cap = cap;
+    const uint64_t rows = (uint64_t)L.w[1] * L.w[2];
+    const uint64_t bits_words = rows * L.words_per_row;
+    CK(cudaMalloc(&d_bits, sizeof(uint32_t) * bits_words));
+    CK(cudaMalloc(&d_d1, rows * A.px));
+    CK(cudaMalloc(&d_dxy, sizeof(uint16_t) * (uint64_t)A.w2 * sy * A.px));
+    CK(cudaMalloc(&d_rank, cap + 1));
+    CK(cudaMalloc(&d_needed, cap + 1));
+    CK(cudaMalloc(&d_values, sizeof(int32_t) * 256));
+    CK(cudaMalloc(&d_lut, sizeof(float) * 256));
+    CK(cudaMalloc(&d_codes, code_bytes + (2u << 20)));
+    void* const codes_aligned =
+        reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(d_codes) + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1));
+    CK(cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * bits_words, stream));
+    CK(cudaMemsetAsync(d_values, 0, sizeof(int32_t) * 256, stream));
+    CK(cudaMemcpyAsync(d_rank, rank.data(), cap + 1, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_values, values.data(), sizeof(int32_t) * values.size(), cudaMemcpyHostToDevice, stream));
+    lut_kernel<<<1, 256, 0, stream>>>(G, d_values, (uint32_t)values.size(), d_lut);
+    CK(cudaGetLastError());
+    voxelize_kernel<<<(unsigned)pblocks, 256, 0, stream>>>(L, d_xyz, stride, n, cls, d_bits, 0u, nullptr, nullptr);
+    CK(cudaGetLastError());
+    {
+      const uint64_t threads = rows * (A.px / 32);
+      xpass8_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(d_bits, L.words_per_row, rows, A.px, sub, par[0], d1cap, d_d1);
+      CK(cudaGetLastError());
+    }
+    {
+      uint8_t* codes8 = reinterpret_cast<uint8_t*>(codes_aligned);
+      cudaError_t e = cudaSuccess;
+      // y and z may have different parities: each pass is instantiated per (sub, parity of its axis, window)
+      const uint64_t by = (uint64_t)A.w2 * (A.px / 64) * ((A.sy + 8 * kFastPer - 1) / (8 * kFastPer));
+      const uint64_t bz = (uint64_t)((A.sz + kZT - 1) / kZT) * (A.px / 64) * ((A.sy + 3) / 4);
+      if (by > 0x7FFFFFFFull || bz > 0x7FFFFFFFull)
+        goto done;
+      e = launch_y(sub, par[1], H, A, d_d1, d_dxy, (unsigned)by, stream);
+      if (e == cudaSuccess)
+        e = launch_z(sub, par[2], H, A, d_dxy, prob, codes8, d_rank, d_lut, nbx, nby, (unsigned)bz, stream);
+      CK(e);
+      if (nsparse > 0)
+      {
+        const int W = R / sub + 1;
+        const uint64_t threads = (uint64_t)(2 * W + 1) * (2 * W + 1) * (2 * W + 1) * nsparse;
+        const unsigned blocks = (unsigned)((threads + 255) / 256);
+        CK(cudaMemsetAsync(d_needed, 0, cap + 1, stream));
+        sparse_patch_kernel<false><<<blocks, 256, 0, stream>>>(d_sparse, nsparse, W, sub, sx, sy, sz, nbx, nby, cap, d_values, d_rank,
+                                                              d_lut, codes8, prob, d_needed);
+        CK(cudaGetLastError());
+        needed.resize(cap + 1);
+        CK(cudaMemcpyAsync(needed.data(), d_needed, cap + 1, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        bool grown = false;
+        for (uint32_t k = 0; k < cap; ++k)
+          if (needed[k] && !(rank[k] < values.size() && values[rank[k]] == (int32_t)k))
+          {
+            if (values.size() >= 254)
+              goto done;  // more distinct values than 8-bit codes hold: legacy passes + coder
+            rank[k] = (uint8_t)values.size();
+            values.push_back((int32_t)k);
+            grown = true;
+          }
+        if (grown)
+        {
+          CK(cudaMemcpyAsync(d_rank, rank.data(), cap + 1, cudaMemcpyHostToDevice, stream));
+          CK(cudaMemcpyAsync(d_values, values.data(), sizeof(int32_t) * values.size(), cudaMemcpyHostToDevice, stream));
+          lut_kernel<<<1, 256, 0, stream>>>(G, d_values, (uint32_t)values.size(), d_lut);
+          CK(cudaGetLastError());
+        }
+        sparse_patch_kernel<true><<<blocks, 256, 0, stream>>>(d_sparse, nsparse, W, sub, sx, sy, sz, nbx, nby, cap, d_values, d_rank,
+                                                             d_lut, codes8, prob, d_needed);
+        CK(cudaGetLastError());
+      }
+    }
+    CK(cudaStreamSynchronize(stream));
+    out->rep = kRepCode8;
+    out->codes = codes_aligned;
+    out->codes_alloc = d_codes;
+    out->lut = d_lut;
+    out->lut_n = (uint32_t)values.size();
+    out->nbx = nbx;
+    out->nby = nby;
+    out->bytes = code_bytes;
+    d_codes = nullptr;
+    d_lut = nullptr;
+    *done = true;
+  }
+done:
+  cudaFree(d_bits);
+  cudaFree(d_d1);
+  cudaFree(d_dxy);
+  cudaFree(d_rank);
+  cudaFree(d_needed);
+  cudaFree(d_values);
+  cudaFree(d_codes);
+  cudaFree(d_lut);
   return rc;
 }
 
@@ -897,6 +1408,12 @@ cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t strid
 
   {
     const bool need_d2 = (keep_d2 != nullptr) || ndense > 1 || coded != nullptr;
+
+    bool fast_done = false;
+    if (ndense == 1 && keep_d2 == nullptr && fast_passes && coded != nullptr)
+      CK(build_fast(map, L, d_xyz, stride, n, G, dense[0], d_sparse, (int)h_nsparse, pblocks, prob, coded, stream, &fast_done));
+    if (fast_done)
+      goto done;
     if (need_d2)
       CK(cudaMalloc(&d_d2, sizeof(int32_t) * cells));
 

@@ -810,9 +810,9 @@ __device__ __forceinline__ void point_address(const SweepMap& sm, const float4 p
   rare = in & !(dev < sm.band);
   const uint32_t bx = __float_as_uint(tx), by = __float_as_uint(ty), bz = __float_as_uint(tz);
   // within the 2 MB block: brick (z6..2 | y6..2 | x6..3) << 7 | voxel (z1..0 | y1..0 | x2..0), see coded_index()
-  const uint32_t wx = (bx | (bx << 4)) & 0x787u;
-  const uint32_t wy = ((by << 3) | (by << 9)) & 0xF818u;
-  const uint32_t wz = ((bz << 5) | (bz << 14)) & 0x1F0060u;
+  const uint32_t wx = (bx & 0x7u) | ((bx << 4) & 0x780u);
+  const uint32_t wy = ((by << 3) & 0x18u) | ((by << 9) & 0xF800u);
+  const uint32_t wz = ((bz << 5) & 0x60u) | ((bz << 14) & 0x1F0000u);
   off_lo = wx | wy | wz;
   blk = (bz >> 7) * sm.mul_z + ((by >> 7) * sm.mul_y + ((bx >> 7) - sm.bias));
 }
@@ -1073,8 +1073,12 @@ cudaError_t launch_update(const MapDev& map, float* particles, uint32_t n, const
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
       return e;
+    if (tp->ev_mid)
+      cudaEventRecord(tp->ev_mid, stream);
     ordered_sum_kernel<<<(n + kSumThreads - 1) / kSumThreads, kSumThreads, 0, stream>>>(
         map, particles, n, tp->stage, npts, npts_padded, beacons, wr_out, counter);
+    if (tp->ev_end)
+      cudaEventRecord(tp->ev_end, stream);
     return cudaGetLastError();
   }
   const size_t dyn = sizeof(float) * map.lut_n;

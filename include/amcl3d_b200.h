@@ -119,6 +119,12 @@ int amcl3d_b200_grid_set_map(amcl3d_b200_grid_t g, const double min[3], const do
  * float grid is the same, bit for bit (environment AMCL3D_B200_EDT_FAST=0 forces the exact passes). */
 int amcl3d_b200_grid_build(amcl3d_b200_grid_t g, const float* xyz, uint32_t stride, uint64_t n,
                            double sensor_dev, int mode, int sub, int keep_edt);
+/* the same build from map points already resident in DEVICE memory (no host round trip; used in place) */
+int amcl3d_b200_grid_build_device(amcl3d_b200_grid_t g, const void* d_xyz, uint32_t stride, uint64_t n,
+                                  double sensor_dev, int mode, int sub, int keep_edt);
+/* device time in ms of the kernels of the last grid_build / grid_build_device on this handle (CUDA events on the
+ * handle's stream, after the H2D copy of the points) */
+int amcl3d_b200_grid_last_build_ms(amcl3d_b200_grid_t g, float* ms);
 int amcl3d_b200_grid_download_edt(amcl3d_b200_grid_t g, int32_t* d2, uint64_t cap);
 /* per grid handle: 1 (default) capped passes when the EDT is not kept, 0 the exact envelope passes always (the float
  * grid is the same bit for bit; A/B switch).  Environment AMCL3D_B200_EDT_FAST=0 sets the default for new handles. */
@@ -265,6 +271,9 @@ int amcl3d_b200_pf_prefix(amcl3d_b200_pf_t pf, void** d_prefix, float* host_out,
 /* device time in ms of the kernels of the last update / normalize / resample / uniform_sample /
  * mean call on this handle, measured with CUDA events on the handle's stream */
 int amcl3d_b200_pf_last_kernel_ms(amcl3d_b200_pf_t pf, float* ms);
+/* the large-set update of the last amcl3d_b200_pf_update* call split by kernel: ms[0] pose_kernel, ms[1] sweep_kernel
+ * (the gather), ms[2] ordered_sum_kernel; zeros when the single-kernel path ran (last slice only when sliced) */
+int amcl3d_b200_pf_last_phase_ms(amcl3d_b200_pf_t pf, float ms[3]);
 /* kernels launched by this handle since creation */
 int amcl3d_b200_pf_launch_count(amcl3d_b200_pf_t pf, uint64_t* launches);
 

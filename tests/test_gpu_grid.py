@@ -151,3 +151,69 @@ def test_capped_window_passes_c1_update_bits(O, world_c1):
     pf.update(w["cloud"])
     ref = O.update(m, O.particles(w["T"]), w["cloud"])
     assert np.array_equal(bits(pf.p_[:, 6]), bits(ref[:, 6]))
+
+
+@pytest.mark.parametrize("sub,lattice", [(2, "centre"), (1, "corner"), (2, "corner")])
+def test_fused_build_codes_and_sparse_patch(O, sub, lattice):
+    """The fused fast build (xpass8 / ypass_dpx / zpass_dpx + sparse patch, gridbuild.cu): odd sizes that are no multiple
+    of the 64 x 4 x 32 tile, a half-empty map, and a few isolated sites of OTHER lattice classes inside the empty half
+    (patched in after the passes, extending the dictionary).  The float grid must equal the exact-envelope build bit for
+    bit, and the bricked codes must drive update() to the same weights as the linear float grid."""
+    from amcl3d_test_b200 import Grid3d, ParticleFilter
+
+    resol, sigma = 0.1, 0.05
+    extent = (7.3, 4.5, 4.1)
+    size = np.round(np.array(extent) / resol).astype(int)
+    rng = np.random.RandomState(31)
+    vox = np.stack([rng.randint(0, 30, 1500), rng.randint(0, size[1], 1500), rng.randint(0, size[2], 1500)], 1)
+    dense = ((vox + 0.5) if lattice == "centre" else vox) * resol
+    lone = np.array([[5.0, 2.0, 1.0], [5.55, 2.05, 1.3], [6.0, 3.05, 2.0], [4.45, 1.0, 3.05], [6.85, 0.5, 0.25]])
+    if sub == 1:
+        lone = np.round(lone / resol) * resol  # sub = 1 has a single class: the lone sites are then ordinary dense sites
+    pts = np.concatenate([[[0, 0, 0], list(extent)], dense, lone]).astype(np.float32)
+    g = Grid3d(0)
+    mn, mx = g.computePointCloud(pts, resol)
+    assert g.info()["size"] == tuple(size)
+    g.computeGrid(pts, sigma, sub=sub, keep_edt=True)          # exact envelope passes + legacy coder
+    exact = g.downloadGrid()
+    g.computeGrid(pts, sigma, sub=sub)                         # fused fast build
+    fast = g.downloadGrid()
+    assert g.info()["rep"] == 1
+    assert np.array_equal(bits(fast), bits(exact))
+    m = O.Map(mn, mx, resol, sigma, prob=fast)
+    lin = np.ravel_multi_index((20, 10, 50), (size[2], size[1], size[0]))  # voxel (50, 10, 20) = corner (5.0, 1.0, 2.0)
+    assert fast[lin] >= 0
+    # particles around the lone sites, cloud = all map points seen from there: the patched codes are what they read
+    n = 4096
+    P = np.zeros((n, 7), np.float32)
+    P[:, :6] = np.array([5.2, 2.0, 1.5, 0, 0, 0.2], np.float32) + rng.normal(0, 1, (n, 6)).astype(np.float32) * np.array(
+        [0.4, 0.4, 0.3, 0.1, 0.1, 0.3], np.float32)
+    world = np.concatenate([dense[rng.choice(dense.shape[0], 600, replace=False)], np.repeat(lone, 40, 0)])
+    cloud = (world - np.array([5.2, 2.0, 1.5])).astype(np.float32)
+    cloud += rng.normal(0, 0.02, cloud.shape).astype(np.float32)
+    pf = ParticleFilter(g)
+    pf.p_ = P
+    pf.update(cloud)
+    coded = pf.p_[:, 6].copy()
+    ref = O.update(m, O.particles(P), cloud)
+    assert (ref[:, 6] > 0).mean() > 0.5
+    assert np.array_equal(bits(coded), bits(ref[:, 6]))
+    g.useCodes(False)
+    pf2 = ParticleFilter(g)
+    pf2.p_ = P
+    pf2.update(cloud)
+    assert np.array_equal(bits(pf2.p_[:, 6]), bits(coded))
+
+
+def test_fused_build_gaussian_and_wider_windows(O):
+    """Window half-widths 12 / 20 / 28 of the DPX passes (sigma 0.03, 0.05, 0.09) and the plain-Gaussian mode."""
+    from amcl3d_test_b200 import Grid3d
+
+    pts, m = _small_map(O, seed=8, extent=(9.7, 3.3, 4.9), n=700)
+    g = Grid3d(0)
+    g.computePointCloud(pts, m.resol)
+    for sigma, mode in ((0.03, O.GRID_QUIRK), (0.05, O.GRID_QUIRK), (0.09, O.GRID_QUIRK), (0.03, O.GRID_GAUSSIAN)):
+        g.computeGrid(pts, sigma, mode=mode, sub=2, keep_edt=True)
+        exact = g.downloadGrid()
+        g.computeGrid(pts, sigma, mode=mode, sub=2)
+        assert np.array_equal(bits(g.downloadGrid()), bits(exact)), (sigma, mode)

@@ -395,3 +395,58 @@ class ParticleFilter:
         n = C.c_uint64(0)
         check(self._L.amcl3d_b200_pf_launch_count(self._h, C.byref(n)))
         return int(n.value)
+
+    # ---- particles sharded over the GPUs of one box, exchange over peer memory (csrc/shard.cu) ----------------
+    def shard_init(self, n_total: int, rank: int, world: int):
+        """This handle becomes rank `rank` of `world`; p_ is its contiguous block [lo, hi) of the global order."""
+        check(self._L.amcl3d_b200_pf_shard_init(self._h, int(n_total), int(rank), int(world)))
+        return self.shard_info()[:2]
+
+    def shard_info(self):
+        lo, hi, nb = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        check(self._L.amcl3d_b200_pf_shard_info(self._h, C.byref(lo), C.byref(hi), C.byref(nb)))
+        return int(lo.value), int(hi.value), int(nb.value)
+
+    def shard_ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(self._L.amcl3d_b200_pf_shard_ipc_handle(self._h, buf, 64))
+        return buf.raw
+
+    def shard_attach_ipc(self, handles):
+        """handles: the 64-byte handles of all ranks, indexed by rank (one process per GPU)."""
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) % 64 == 0
+        check(self._L.amcl3d_b200_pf_shard_attach_ipc(self._h, blob, 64))
+
+    @staticmethod
+    def shard_attach_local(pfs):
+        """All ranks are handles of this process (pfs[r] = rank r), one per device."""
+        arr = (C.c_void_p * len(pfs))(*[p._h.value for p in pfs])
+        check(capi.load().amcl3d_b200_pf_shard_attach_local(arr, len(pfs)))
+
+    @staticmethod
+    def shard_resample_local(pfs, u01, d_wr_local=None, alpha=1.0):
+        """The collective resample for ranks that are handles of one process: launched on all, then waited for."""
+        arr = (C.c_void_p * len(pfs))(*[p._h.value for p in pfs])
+        wr = (C.c_void_p * len(pfs))(*[int(v) for v in d_wr_local]) if d_wr_local is not None else None
+        check(capi.load().amcl3d_b200_pf_shard_resample_local(arr, len(pfs), float(np.float32(u01)), wr, float(alpha)))
+
+    @staticmethod
+    def shard_mean_local(pfs) -> np.ndarray:
+        arr = (C.c_void_p * len(pfs))(*[p._h.value for p in pfs])
+        out = np.zeros(7, np.float32)
+        check(capi.load().amcl3d_b200_pf_shard_mean_local(arr, len(pfs), out.ctypes.data))
+        return out
+
+    def shard_resample(self, u01, d_wr_local: int = 0, alpha=1.0, want_idx=False):
+        """Global particleNormalize + resample over all ranks; p_ becomes this rank's slice of the resampled set."""
+        idx = np.empty(self.size(), np.int32) if want_idx else None
+        check(self._L.amcl3d_b200_pf_shard_resample(self._h, float(np.float32(u01)), C.c_void_p(d_wr_local or 0), float(alpha),
+                                                    idx.ctypes.data if want_idx else None))
+        return idx
+
+    def shard_mean(self, d_out7: int = 0, fetch=True):
+        """getMean over all ranks; fetch=False leaves the 7 floats in d_out7 (device) without a host wait in async mode."""
+        out = np.zeros(7, np.float32) if fetch else None
+        check(self._L.amcl3d_b200_pf_shard_mean(self._h, out.ctypes.data if fetch else None, C.c_void_p(d_out7 or 0)))
+        return out

@@ -16,7 +16,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libamcl3d_b200.so"
-SOURCES = ["update.cu", "pfops.cu", "gridbuild.cu", "mcl.cu", "voxelfilter.cu", "capi.cu"]
+SOURCES = ["update.cu", "pfops.cu", "gridbuild.cu", "mcl.cu", "voxelfilter.cu", "shard.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

@@ -17,6 +17,9 @@ SYMBOLS = [
     "amcl3d_b200_set_l2_fetch_granularity", "amcl3d_b200_get_l2_fetch_granularity", "amcl3d_b200_pf_set_chain_mode",
     "amcl3d_b200_grid_set_edt_fast", "amcl3d_b200_grid_build_device", "amcl3d_b200_grid_last_build_ms",
     "amcl3d_b200_pf_last_phase_ms",
+    "amcl3d_b200_pf_shard_init", "amcl3d_b200_pf_shard_info", "amcl3d_b200_pf_shard_ipc_handle",
+    "amcl3d_b200_pf_shard_attach_ipc", "amcl3d_b200_pf_shard_attach_local", "amcl3d_b200_pf_shard_resample",
+    "amcl3d_b200_pf_shard_mean", "amcl3d_b200_pf_shard_resample_local", "amcl3d_b200_pf_shard_mean_local",
     "amcl3d_b200_grid_create", "amcl3d_b200_grid_destroy", "amcl3d_b200_grid_get_info",
     "amcl3d_b200_grid_compute_bounds", "amcl3d_b200_grid_set_map", "amcl3d_b200_grid_build",
     "amcl3d_b200_grid_download_edt", "amcl3d_b200_grid_upload", "amcl3d_b200_grid_download",
@@ -84,6 +87,15 @@ def load():
         "amcl3d_b200_grid_build_device": (i, [vp, vp, u32, u64, f64, i, i, i]),
         "amcl3d_b200_grid_last_build_ms": (i, [vp, P(f32)]),
         "amcl3d_b200_pf_last_phase_ms": (i, [vp, P(f32)]),
+        "amcl3d_b200_pf_shard_init": (i, [vp, u64, i, i]),
+        "amcl3d_b200_pf_shard_info": (i, [vp, P(u64), P(u64), P(u64)]),
+        "amcl3d_b200_pf_shard_ipc_handle": (i, [vp, vp, C.c_size_t]),
+        "amcl3d_b200_pf_shard_attach_ipc": (i, [vp, vp, C.c_size_t]),
+        "amcl3d_b200_pf_shard_attach_local": (i, [P(vp), i]),
+        "amcl3d_b200_pf_shard_resample": (i, [vp, f32, vp, f32, vp]),
+        "amcl3d_b200_pf_shard_mean": (i, [vp, vp, vp]),
+        "amcl3d_b200_pf_shard_resample_local": (i, [P(vp), i, f32, P(vp), f32]),
+        "amcl3d_b200_pf_shard_mean_local": (i, [P(vp), i, vp]),
         "amcl3d_b200_set_l2_fetch_granularity": (i, [i, i]),
         "amcl3d_b200_get_l2_fetch_granularity": (i, [i, P(i)]),
         "amcl3d_b200_grid_create": (i, [i, P(vp)]),

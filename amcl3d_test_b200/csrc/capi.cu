@@ -84,7 +84,7 @@ struct amcl3d_b200_grid_s
   int edt_fast = 1;        // AMCL3D_B200_EDT_FAST=0 or amcl3d_b200_grid_set_edt_fast: exact envelope passes always
   cudaStream_t stream = nullptr;
   amcl3d_b200_pf_t scratch_pf = nullptr;  // for the single-pose computeCloudWeight
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the kernels of the last build
+  cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };  // two timed regions around the kernels of the last build
   bool build_timed = false;
 };
 
@@ -148,6 +148,22 @@ struct amcl3d_b200_pf_s
   bool timed = false;
   bool async_mode = false;  // amcl3d_b200_pf_set_async: calls that hand nothing back to the host do not synchronise
   uint64_t launches = 0;
+  // sharded particle set over peer memory (shard.cu)
+  struct Shard
+  {
+    bool on = false, attached = false;
+    uint32_t rank = 0, world = 1;
+    uint64_t n_total = 0, n_max = 0, lo = 0, hi = 0;
+    char* region = nullptr;
+    size_t region_bytes = 0;
+    ShardPeers peers{};
+    void* opened[kMaxShardWorld] = {};  // cudaIpcOpenMemHandle mappings to close
+    uint32_t epoch = 0, mean_epoch = 0;
+    uint32_t cur = 0;  // P[cur] holds p_
+    unsigned int* d_done = nullptr;
+    uint32_t* d_error = nullptr;
+    float* d_part7 = nullptr;
+  } shard;
 };
 
 namespace
@@ -339,10 +355,8 @@ int amcl3d_b200_grid_create(int device, amcl3d_b200_grid_t* out)
     (void)cudaGetLastError();
   }
   cudaError_t e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess)
-    e = cudaEventCreate(&g->ev0);
-  if (e == cudaSuccess)
-    e = cudaEventCreate(&g->ev1);
+  for (int k = 0; k < 4 && e == cudaSuccess; ++k)
+    e = cudaEventCreate(&g->ev[k]);
   if (e != cudaSuccess)
   {
     amcl3d_b200_grid_destroy(g);
@@ -362,10 +376,9 @@ int amcl3d_b200_grid_destroy(amcl3d_b200_grid_t g)
   cudaFree(g->d_prob);
   cudaFree(g->d_edt);
   drop_codes(g);
-  if (g->ev0)
-    cudaEventDestroy(g->ev0);
-  if (g->ev1)
-    cudaEventDestroy(g->ev1);
+  for (int k = 0; k < 4; ++k)
+    if (g->ev[k])
+      cudaEventDestroy(g->ev[k]);
   if (g->stream)
     cudaStreamDestroy(g->stream);
   delete g;
@@ -554,13 +567,16 @@ static int grid_build_impl(amcl3d_b200_grid_t g, const float* xyz, bool on_devic
   char msg[256] = { 0 };
   if (e == cudaSuccess)
   {
-    cudaEventRecord(g->ev0, g->stream);
     if (mode == AMCL3D_B200_GRID_SPLAT)
+    {
+      for (int k = 0; k < 4; ++k)
+        cudaEventRecord(g->ev[k], g->stream);
       e = build_grid_splat(g->map, d_xyz, stride, n, sensor_dev, g->d_prob, g->stream);
+      cudaEventRecord(g->ev[1], g->stream);
+    }
     else
       e = build_grid_edt(g->map, d_xyz, stride, n, sensor_dev, mode, sub, g->d_prob, keep_edt ? &g->d_edt : nullptr,
-                         g->use_codes ? &g->coded : nullptr, g->edt_fast, g->stream, msg, sizeof(msg));
-    cudaEventRecord(g->ev1, g->stream);
+                         g->use_codes ? &g->coded : nullptr, g->edt_fast, g->stream, g->ev, msg, sizeof(msg));
   }
   if (e == cudaSuccess)
     e = cudaStreamSynchronize(g->stream);
@@ -602,7 +618,10 @@ int amcl3d_b200_grid_last_build_ms(amcl3d_b200_grid_t g, float* ms)
   *ms = 0.f;
   if (!g->build_timed)
     return AMCL3D_B200_OK;
-  CU(cudaEventElapsedTime(ms, g->ev0, g->ev1));
+  float a = 0.f, b = 0.f;
+  CU(cudaEventElapsedTime(&a, g->ev[0], g->ev[1]));
+  CU(cudaEventElapsedTime(&b, g->ev[2], g->ev[3]));
+  *ms = a + b;
   return AMCL3D_B200_OK;
 }
 
@@ -788,6 +807,17 @@ int amcl3d_b200_pf_destroy(amcl3d_b200_pf_t pf)
   if (!pf)
     return AMCL3D_B200_OK;
   cudaSetDevice(pf->grid->device);
+  if (pf->shard.on)
+  {
+    cudaStreamSynchronize(pf->stream);
+    for (uint32_t r = 0; r < kMaxShardWorld; ++r)
+      if (pf->shard.opened[r])
+        cudaIpcCloseMemHandle(pf->shard.opened[r]);
+    cudaFree(pf->shard.region);  // p_ lives inside it (pf->external is set)
+    cudaFree(pf->shard.d_done);
+    cudaFree(pf->shard.d_error);
+    cudaFree(pf->shard.d_part7);
+  }
   if (!pf->external)
     cudaFree(pf->d_p);
   cudaFree(pf->d_alt);
@@ -847,6 +877,13 @@ int amcl3d_b200_pf_sync(amcl3d_b200_pf_t pf)
   if (int rc = use_device(pf->grid->device))
     return rc;
   CU(cudaStreamSynchronize(pf->stream));
+  if (pf->shard.on)
+  {  // a sharded exchange that gave up on a peer (shard.cu wait_kernel) is reported here in stream-order mode
+    uint32_t err = 0;
+    CU(cudaMemcpy(&err, pf->shard.d_error, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err)
+      return fail(AMCL3D_B200_ERR_STATE, "sharded exchange timed out waiting for rank " + std::to_string(err - 1));
+  }
   return AMCL3D_B200_OK;
 }
 
@@ -1607,6 +1644,314 @@ int amcl3d_b200_pf_resample_step(amcl3d_b200_pf_t pf, int weight_multiply, int m
   if (!rc && new_size)
     *new_size = sample_num;
   return rc;
+}
+
+
+/* ================================ sharded particle set over peer memory ================================ */
+namespace
+{
+uint64_t align256(uint64_t v)
+{
+  return (v + 255) & ~(uint64_t)255;
+}
+// contiguous block partition; the first (n_total % world) ranks hold one particle more
+void shard_bounds(uint64_t n_total, uint32_t world, uint32_t rank, uint64_t* lo, uint64_t* hi)
+{
+  const uint64_t base = n_total / world, rem = n_total % world;
+  *lo = rank * base + std::min<uint64_t>(rank, rem);
+  *hi = *lo + base + (rank < rem ? 1 : 0);
+}
+int shard_check_error(amcl3d_b200_pf_t pf)
+{
+  uint32_t err = 0;
+  CU(cudaMemcpyAsync(&err, pf->shard.d_error, sizeof(err), cudaMemcpyDeviceToHost, pf->stream));
+  CU(cudaStreamSynchronize(pf->stream));
+  if (err)
+    return fail(AMCL3D_B200_ERR_STATE, "sharded exchange timed out waiting for rank " + std::to_string(err - 1));
+  return AMCL3D_B200_OK;
+}
+}  // namespace
+
+int amcl3d_b200_pf_shard_init(amcl3d_b200_pf_t pf, uint64_t n_total, int rank, int world)
+{
+  if (!pf || world < 1 || world > (int)kMaxShardWorld || rank < 0 || rank >= world || n_total == 0 || n_total >= (1ull << 31))
+    return fail(AMCL3D_B200_ERR_ARG, "bad shard geometry");
+  if (pf->shard.on)
+    return fail(AMCL3D_B200_ERR_STATE, "already sharded");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  amcl3d_b200_pf_s::Shard& S = pf->shard;
+  S.rank = (uint32_t)rank;
+  S.world = (uint32_t)world;
+  S.n_total = n_total;
+  S.n_max = (n_total + world - 1) / world;
+  shard_bounds(n_total, S.world, S.rank, &S.lo, &S.hi);
+  ShardPeers& P = S.peers;
+  P.world = S.world;
+  uint64_t off = 0;
+  P.off_p = off;
+  P.p_bytes = align256(S.n_max * 28);
+  off += 2 * P.p_bytes;
+  P.off_w = off;
+  off += align256(2 * n_total * 4);
+  P.off_wr = off;
+  off += align256(2 * n_total * 4);
+  P.off_inmap = off;
+  off += align256(2 * n_total);
+  P.off_mean = off;
+  off += align256(2 * kMaxShardWorld * 8 * 4);
+  P.off_flags = off;
+  off += align256(2 * kMaxShardWorld * 4);
+  S.region_bytes = off;
+  CU(cudaMalloc(&S.region, S.region_bytes));
+  CU(cudaMemset(S.region, 0, S.region_bytes));
+  CU(cudaMalloc(&S.d_done, sizeof(unsigned int)));
+  CU(cudaMemset(S.d_done, 0, sizeof(unsigned int)));
+  CU(cudaMalloc(&S.d_error, sizeof(uint32_t)));
+  CU(cudaMemset(S.d_error, 0, sizeof(uint32_t)));
+  CU(cudaMalloc(&S.d_part7, 8 * sizeof(float)));
+  for (uint32_t r = 0; r < kMaxShardWorld; ++r)
+    P.base[r] = nullptr;
+  P.base[S.rank] = S.region;
+  // p_ becomes the rank's block inside the region
+  if (!pf->external)
+    cudaFree(pf->d_p);
+  pf->d_p = reinterpret_cast<float*>(S.region + P.off_p);
+  pf->external = true;
+  pf->cap = S.n_max;
+  pf->n = S.hi - S.lo;
+  S.cur = 0;
+  S.on = true;
+  S.attached = (world == 1);
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_shard_ipc_handle(amcl3d_b200_pf_t pf, void* handle64, size_t cap)
+{
+  if (!pf || !handle64 || cap < sizeof(cudaIpcMemHandle_t))
+    return fail(AMCL3D_B200_ERR_ARG, "handle buffer must hold 64 bytes");
+  if (!pf->shard.on)
+    return fail(AMCL3D_B200_ERR_STATE, "not sharded");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, pf->shard.region));
+  memcpy(handle64, &h, sizeof(h));
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_shard_attach_ipc(amcl3d_b200_pf_t pf, const void* handles, size_t stride)
+{
+  if (!pf || !handles || stride < sizeof(cudaIpcMemHandle_t))
+    return fail(AMCL3D_B200_ERR_ARG, "bad handle array");
+  if (!pf->shard.on)
+    return fail(AMCL3D_B200_ERR_STATE, "not sharded");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  amcl3d_b200_pf_s::Shard& S = pf->shard;
+  for (uint32_t r = 0; r < S.world; ++r)
+  {
+    if (r == S.rank)
+      continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, reinterpret_cast<const char*>(handles) + (size_t)r * stride, sizeof(h));
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    S.opened[r] = ptr;
+    S.peers.base[r] = reinterpret_cast<char*>(ptr);
+  }
+  S.attached = true;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_shard_attach_local(amcl3d_b200_pf_t* pfs, int world)
+{
+  if (!pfs || world < 1 || world > (int)kMaxShardWorld)
+    return fail(AMCL3D_B200_ERR_ARG, "bad handle array");
+  for (int r = 0; r < world; ++r)
+    if (!pfs[r] || !pfs[r]->shard.on || pfs[r]->shard.world != (uint32_t)world || pfs[r]->shard.rank != (uint32_t)r ||
+        pfs[r]->shard.n_total != pfs[0]->shard.n_total)
+      return fail(AMCL3D_B200_ERR_ARG, "handles must be shard_init'ed as ranks 0..world-1 of the same set");
+  for (int a = 0; a < world; ++a)
+  {
+    if (int rc = use_device(pfs[a]->grid->device))
+      return rc;
+    for (int b = 0; b < world; ++b)
+    {
+      if (a == b)
+        continue;
+      const int da = pfs[a]->grid->device, db = pfs[b]->grid->device;
+      if (da != db)
+      {
+        int can = 0;
+        CU(cudaDeviceCanAccessPeer(&can, da, db));
+        if (!can)
+          return fail(AMCL3D_B200_ERR_CUDA, "no peer access between the devices of the shard");
+        cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          return fail_cuda(e, "cudaDeviceEnablePeerAccess");
+        (void)cudaGetLastError();
+      }
+      pfs[a]->shard.peers.base[b] = pfs[b]->shard.region;
+    }
+    pfs[a]->shard.attached = true;
+  }
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_shard_resample(amcl3d_b200_pf_t pf, float u01, const void* d_wr_local, float alpha, int32_t* idx)
+{
+  if (!pf)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+  amcl3d_b200_pf_s::Shard& S = pf->shard;
+  if (!S.on || !S.attached)
+    return fail(AMCL3D_B200_ERR_STATE, "shard not attached to its peers");
+  if (pf->n != S.hi - S.lo)
+    return fail(AMCL3D_B200_ERR_STATE, "p_ must hold this rank's block of the partition");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  const uint64_t N = S.n_total, n = pf->n;
+  CU(ensure(pf->d_prefix, pf->prefix_cap, N));
+  CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(N)));
+  int32_t* d_idx = nullptr;
+  if (idx)
+  {
+    CU(ensure(pf->d_idx, pf->idx_cap, n));
+    d_idx = pf->d_idx;
+  }
+  S.epoch += 1;
+  const uint32_t parity = S.epoch & 1u;
+  float* w = reinterpret_cast<float*>(S.region + S.peers.off_w) + (size_t)parity * N;
+  float* wr = reinterpret_cast<float*>(S.region + S.peers.off_wr) + (size_t)parity * N;
+  const uint8_t* inmap = reinterpret_cast<const uint8_t*>(S.region + S.peers.off_inmap) + (size_t)parity * N;
+  const uint32_t* flags = reinterpret_cast<const uint32_t*>(S.region + S.peers.off_flags);
+  float* out = reinterpret_cast<float*>(S.region + S.peers.off_p + (size_t)(S.cur ^ 1u) * S.peers.p_bytes);
+  {
+    Timed t(pf);
+    // exchange: this rank's weights into every rank's dense copy, then wait for everybody else's
+    CU(launch_shard_publish(pf->grid->map, S.peers, pf->d_p, reinterpret_cast<const float*>(d_wr_local), (uint32_t)n, (uint32_t)S.lo,
+                            (uint32_t)N, parity, S.epoch, S.rank, S.d_done, pf->stream));
+    CU(launch_shard_wait(flags, 0, S.world, S.epoch, S.d_error, pf->stream));
+    // the reference's sequential chains over ALL particles, replicated on every rank: same bits as one GPU
+    if (d_wr_local)
+    {
+      CU(launch_chain_dense(w, N, 0, nullptr, pf->d_scalars + 0, pf->d_dense, pf->chain_mode, pf->stream));
+      CU(launch_chain_dense(wr, N, 0, nullptr, pf->d_scalars + 1, pf->d_dense, pf->chain_mode, pf->stream));
+      CU(launch_dense_fuse(w, wr, N, pf->d_scalars + 0, pf->d_scalars + 1, alpha, pf->stream));
+      pf->launches += 3;
+    }
+    CU(launch_chain_dense(w, N, 1, nullptr, pf->d_scalars + 0, pf->d_dense, pf->chain_mode, pf->stream));  // ParticleFilter.cpp:171-178
+    CU(launch_dense_normalize(w, inmap, N, pf->d_scalars + 0, pf->stream));                                // :180-195
+    CU(launch_chain_dense(w, N, 0, pf->d_prefix, nullptr, pf->d_dense, pf->chain_mode, pf->stream));       // :235-247
+    // this rank's output slice; the selected particles are read from their owners over NVLink
+    CU(launch_shard_search(S.peers, pf->d_prefix, N, u01, S.lo, S.hi, S.cur, out, d_idx, pf->stream));
+    pf->launches += 6;
+    pf->launches += chain_extra_launches_take();
+  }
+  S.cur ^= 1u;
+  pf->d_p = out;
+  if (idx && n)
+  {
+    CU(cudaMemcpyAsync(idx, d_idx, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, pf->stream));
+    return shard_check_error(pf);
+  }
+  if (pf->async_mode)
+    return AMCL3D_B200_OK;
+  return shard_check_error(pf);
+}
+
+int amcl3d_b200_pf_shard_mean(amcl3d_b200_pf_t pf, float out7[7], void* d_out7)
+{
+  if (!pf || (!out7 && !d_out7))
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  amcl3d_b200_pf_s::Shard& S = pf->shard;
+  if (!S.on || !S.attached)
+    return fail(AMCL3D_B200_ERR_STATE, "shard not attached to its peers");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  S.mean_epoch += 1;
+  const uint32_t parity = S.mean_epoch & 1u;
+  float* dst = d_out7 ? reinterpret_cast<float*>(d_out7) : pf->d_scalars + 8;
+  {
+    Timed t(pf);
+    CU(launch_mean(pf->d_p, pf->n, 0, S.d_part7, pf->d_scratch, pf->stream));
+    CU(launch_shard_publish_mean(S.peers, S.d_part7, parity, S.mean_epoch, S.rank, pf->stream));
+    CU(launch_shard_wait(reinterpret_cast<const uint32_t*>(S.region + S.peers.off_flags), 1, S.world, S.mean_epoch, S.d_error,
+                         pf->stream));
+    CU(launch_shard_combine_mean(reinterpret_cast<const float*>(S.region + S.peers.off_mean) + (size_t)parity * kMaxShardWorld * 8,
+                                 S.world, dst, pf->stream));
+    pf->launches += 5;
+  }
+  if (out7)
+  {
+    if (d_out7)
+      CU(cudaMemcpyAsync(out7, d_out7, 7 * sizeof(float), cudaMemcpyDeviceToHost, pf->stream));
+    else
+      CU(cudaMemcpyAsync(out7, pf->d_scalars + 8, 7 * sizeof(float), cudaMemcpyDeviceToHost, pf->stream));
+    return shard_check_error(pf);
+  }
+  return finish_call(pf);
+}
+
+// ranks = handles of ONE process: the collective calls are issued on every handle in stream order first and waited for
+// afterwards (a synchronous call on rank 0 alone would wait for a publish rank 1 has not launched yet)
+int amcl3d_b200_pf_shard_resample_local(amcl3d_b200_pf_t* pfs, int world, float u01, const void* const* d_wr_local, float alpha)
+{
+  if (!pfs || world < 1 || world > (int)kMaxShardWorld)
+    return fail(AMCL3D_B200_ERR_ARG, "bad handle array");
+  for (int r = 0; r < world; ++r)
+  {
+    if (!pfs[r])
+      return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+    const bool was = pfs[r]->async_mode;
+    pfs[r]->async_mode = true;
+    const int rc = amcl3d_b200_pf_shard_resample(pfs[r], u01, d_wr_local ? d_wr_local[r] : nullptr, alpha, nullptr);
+    pfs[r]->async_mode = was;
+    if (rc != AMCL3D_B200_OK)
+      return rc;
+  }
+  for (int r = 0; r < world; ++r)
+    if (!pfs[r]->async_mode)
+      if (int rc = amcl3d_b200_pf_sync(pfs[r]))
+        return rc;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_shard_mean_local(amcl3d_b200_pf_t* pfs, int world, float out7[7])
+{
+  if (!pfs || !out7 || world < 1 || world > (int)kMaxShardWorld)
+    return fail(AMCL3D_B200_ERR_ARG, "bad argument");
+  for (int r = 0; r < world; ++r)
+  {
+    if (!pfs[r])
+      return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+    const bool was = pfs[r]->async_mode;
+    pfs[r]->async_mode = true;
+    const int rc = amcl3d_b200_pf_shard_mean(pfs[r], nullptr, pfs[r]->d_scalars + 8);
+    pfs[r]->async_mode = was;
+    if (rc != AMCL3D_B200_OK)
+      return rc;
+  }
+  for (int r = 0; r < world; ++r)
+    if (int rc = amcl3d_b200_pf_sync(pfs[r]))
+      return rc;
+  if (int rc = use_device(pfs[0]->grid->device))
+    return rc;
+  CU(cudaMemcpy(out7, pfs[0]->d_scalars + 8, 7 * sizeof(float), cudaMemcpyDeviceToHost));
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_shard_info(amcl3d_b200_pf_t pf, uint64_t* lo, uint64_t* hi, uint64_t* region_bytes)
+{
+  if (!pf || !pf->shard.on)
+    return fail(AMCL3D_B200_ERR_STATE, "not sharded");
+  if (lo)
+    *lo = pf->shard.lo;
+  if (hi)
+    *hi = pf->shard.hi;
+  if (region_bytes)
+    *region_bytes = pf->shard.region_bytes;
+  return AMCL3D_B200_OK;
 }
 
 int amcl3d_b200_pf_last_kernel_ms(amcl3d_b200_pf_t pf, float* ms)

@@ -176,6 +176,37 @@ size_t reduce_scratch_bytes();
 cudaError_t launch_predict(float* particles, uint64_t n, const double* delta6_dev, const float* noise6,
                            cudaStream_t stream);
 
+// the chains above on a DENSE weight array (stride 1): used by the sharded path on the all-rank copy
+cudaError_t launch_chain_dense(const float* v, uint64_t n, int positive_only, float* prefix, float* total,
+                               float* scratch /* chain_scratch_floats(n) */, int chain_mode, cudaStream_t stream);
+
+// ---- sharded particle set over peer memory (shard.cu) -------------------------------------------------
+constexpr uint32_t kMaxShardWorld = 16;
+// every rank's exchange region (same layout on all ranks), mapped into this process
+struct ShardPeers
+{
+  char* base[kMaxShardWorld];
+  uint32_t world;
+  uint64_t off_p, p_bytes;  // particle blocks P[2], p_bytes each
+  uint64_t off_w, off_wr;   // dense f32 [2][n_total]
+  uint64_t off_inmap;       // u8 [2][n_total]
+  uint64_t off_mean;        // f32 [2][kMaxShardWorld][8]
+  uint64_t off_flags;       // u32 [2 kinds][kMaxShardWorld]
+};
+cudaError_t launch_shard_publish(const MapDev& map, const ShardPeers& peers, const float* particles, const float* wr_local,
+                                 uint32_t n, uint32_t lo, uint32_t n_total, uint32_t parity, uint32_t epoch, uint32_t rank,
+                                 unsigned int* done_counter, cudaStream_t stream);
+cudaError_t launch_shard_wait(const uint32_t* flags, uint32_t kind, uint32_t world, uint32_t epoch, uint32_t* error,
+                              cudaStream_t stream);
+cudaError_t launch_dense_normalize(float* w, const uint8_t* inmap, uint64_t n, const float* total, cudaStream_t stream);
+cudaError_t launch_dense_fuse(float* w, const float* wr, uint64_t n, const float* sum_p, const float* sum_r, float alpha,
+                              cudaStream_t stream);
+cudaError_t launch_shard_search(const ShardPeers& peers, const float* prefix, uint64_t n, float u01, uint64_t m0, uint64_t m1,
+                                uint32_t src_buf, float* out, int32_t* idx, cudaStream_t stream);
+cudaError_t launch_shard_publish_mean(const ShardPeers& peers, const float* part7, uint32_t parity, uint32_t epoch, uint32_t rank,
+                                      cudaStream_t stream);
+cudaError_t launch_shard_combine_mean(const float* mean_all, uint32_t world, float* out7, cudaStream_t stream);
+
 // ---- callers of the path (mcl.cu) ----------------------------------------------------------------
 // ordered-uint keys of min (0..2) and max (3..5) of x,y,z over the particle set
 cudaError_t launch_particle_bounds(const float* particles, uint64_t n, uint32_t* keys6, cudaStream_t stream);
@@ -201,7 +232,11 @@ struct CodedGrid
 // fast_passes != 0: capped window passes when the exact EDT is not kept (same float grid bit for bit)
 cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t stride, uint64_t n, double sensor_dev,
                            int mode, int sub, float* prob, int32_t** keep_d2, CodedGrid* coded, int fast_passes,
-                           cudaStream_t stream, char* err, size_t errlen);
+                           cudaStream_t stream,
+                           cudaEvent_t* ev /* nullable, 4 events: the kernels of the build run inside ev[0]..ev[1] and
+                                              ev[2]..ev[3]; the fused build keeps the cudaMalloc / cudaFree of its GBs of
+                                              workspace (host-side driver calls) between and after the two regions */,
+                           char* err, size_t errlen);
 cudaError_t build_grid_splat(const MapDev& map, const float* d_xyz, uint32_t stride, uint64_t n, double sensor_dev,
                              float* prob, cudaStream_t stream);
 

@@ -758,17 +758,26 @@ __global__ void __launch_bounds__(256) ypass_dpx_kernel(const uint8_t* __restric
   const int i0 = (int)(it * kTI);
   const uint32_t cap = A.cap, cap2 = cap * 0x10001u;
   const uint8_t* src = d1 + ((uint64_t)plane * A.w1) * A.px + ct * 64 + 2 * lane;
-  for (int r = (int)warp; r < kRows; r += 8)
   {
-    const int j = i0 - H + r;
-    uint32_t v2 = cap2;
-    if (j >= 0 && j < (int)A.w1)
+    // every load of the tile is issued before the first one is consumed (13 independent loads per thread at H = 20)
+    constexpr int kLoads = (kRows + 7) / 8;
+    uint32_t raw[kLoads];
+#pragma unroll
+    for (int q = 0; q < kLoads; ++q)
     {
-      const uint32_t raw = *reinterpret_cast<const uint16_t*>(src + (uint64_t)j * A.px);
-      const uint32_t a = raw & 0xFFu, c = raw >> 8;
-      v2 = min(a * a, cap) | (min(c * c, cap) << 16);
+      const int r = (int)warp + 8 * q, j = i0 - H + r;
+      raw[q] = 0xFFFFu;  // 255, 255: no site
+      if (r < kRows && j >= 0 && j < (int)A.w1)
+        raw[q] = *reinterpret_cast<const uint16_t*>(src + (uint64_t)j * A.px);
     }
-    tile[r][lane] = v2;
+#pragma unroll
+    for (int q = 0; q < kLoads; ++q)
+    {
+      const int r = (int)warp + 8 * q;
+      const uint32_t a = raw[q] & 0xFFu, c = raw[q] >> 8;
+      if (r < kRows)
+        tile[r][lane] = min(a * a, cap) | (min(c * c, cap) << 16);
+    }
   }
   __syncthreads();
   uint32_t best[kFastPer];
@@ -812,16 +821,31 @@ __global__ void __launch_bounds__(256)
   const int z0 = (int)(zt * kZT);
   const uint32_t cap = A.cap, cap2 = cap * 0x10001u;
   {
+    // (site row, y) pairs round-robin over the 8 warps, all loads issued before the first store (36 per thread at H = 20)
     const uint32_t warp = threadIdx.x >> 5;
-    for (int q = (int)warp; q < kRows * 4; q += 8)
+    constexpr int kLoads = (kRows * 4 + 7) / 8;
+    constexpr int kBatch = 12;
+#pragma unroll 1
+    for (int q0 = 0; q0 < kLoads; q0 += kBatch)
     {
-      const int r = q >> 2;
-      const uint32_t y = (uint32_t)q & 3u;
-      const int j = z0 - H + r;
-      uint32_t v2 = cap2;
-      if (j >= 0 && j < (int)A.w2 && y0 + y < A.sy)
-        v2 = *reinterpret_cast<const uint32_t*>(dxy + ((uint64_t)j * A.sy + (y0 + y)) * A.px + x0 + 2 * lane);
-      tile[r][y][lane] = v2;
+      uint32_t raw[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u)
+      {
+        const int q = (int)warp + 8 * (q0 + u);
+        const int r = q >> 2, j = z0 - H + r;
+        const uint32_t yy = (uint32_t)q & 3u;
+        raw[u] = cap2;
+        if (q < kRows * 4 && j >= 0 && j < (int)A.w2 && y0 + yy < A.sy)
+          raw[u] = *reinterpret_cast<const uint32_t*>(dxy + ((uint64_t)j * A.sy + (y0 + yy)) * A.px + x0 + 2 * lane);
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u)
+      {
+        const int q = (int)warp + 8 * (q0 + u);
+        if (q < kRows * 4)
+          tile[q >> 2][q & 3][lane] = raw[u];
+      }
     }
   }
   __syncthreads();
@@ -1073,7 +1097,7 @@ static cudaError_t find_cap(const Gauss& G, unsigned int* h_cap, cudaStream_t st
 // configuration is outside what it covers: the caller then runs the legacy passes.
 static cudaError_t build_fast(const MapDev& map, const Lattice& L, const float* d_xyz, uint32_t stride, uint64_t n, const Gauss& G,
                               int cls, const int4* d_sparse, int nsparse, uint64_t pblocks, float* prob, CodedGrid* out,
-                              cudaStream_t stream, bool* done)
+                              cudaStream_t stream, cudaEvent_t ev_start, cudaEvent_t ev_end, bool* done)
 {
   cudaError_t rc = cudaSuccess;
   *done = false;
@@ -1155,6 +1179,10 @@ static cudaError_t build_fast(const MapDev& map, const Lattice& L, const float* 
     CK(cudaMalloc(&d_codes, code_bytes + (2u << 20)));
     void* const codes_aligned =
         reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(d_codes) + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1));
+    // the timed region of the build (amcl3d_b200_grid_last_build_ms) starts once the workspace exists and ends before it
+    // is freed: cudaMalloc / cudaFree of GBs are host-side driver calls, not work of the path
+    if (ev_start)
+      cudaEventRecord(ev_start, stream);
     CK(cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * bits_words, stream));
     CK(cudaMemsetAsync(d_values, 0, sizeof(int32_t) * 256, stream));
     CK(cudaMemcpyAsync(d_rank, rank.data(), cap + 1, cudaMemcpyHostToDevice, stream));
@@ -1214,6 +1242,8 @@ static cudaError_t build_fast(const MapDev& map, const Lattice& L, const float* 
         CK(cudaGetLastError());
       }
     }
+    if (ev_end)
+      cudaEventRecord(ev_end, stream);
     CK(cudaStreamSynchronize(stream));
     out->rep = kRepCode8;
     out->codes = codes_aligned;
@@ -1330,8 +1360,13 @@ done:
 
 cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t stride, uint64_t n, double sensor_dev,
                            int mode, int sub, float* prob, int32_t** keep_d2, CodedGrid* coded, int fast_passes,
-                           cudaStream_t stream, char* err, size_t errlen)
+                           cudaStream_t stream, cudaEvent_t* ev /* nullable, 4 events */, char* err, size_t errlen)
 {
+  // timed regions of amcl3d_b200_grid_last_build_ms: A = ev[0]..ev[1], B = ev[2]..ev[3] (see common.cuh)
+  cudaEvent_t ev_start = ev ? ev[2] : nullptr, ev_end = ev ? ev[3] : nullptr;
+  if (ev)
+    for (int k = 0; k < 4; ++k)
+      cudaEventRecord(ev[k], stream);
   cudaError_t rc = cudaSuccess;
   const int sx = (int)map.size[0], sy = (int)map.size[1], sz = (int)map.size[2];
   const uint64_t cells = (uint64_t)sx * sy * sz;
@@ -1410,8 +1445,11 @@ cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t strid
     const bool need_d2 = (keep_d2 != nullptr) || ndense > 1 || coded != nullptr;
 
     bool fast_done = false;
+    if (ev)
+      cudaEventRecord(ev[1], stream);  // end of region A: class count + sparse-site collection
     if (ndense == 1 && keep_d2 == nullptr && fast_passes && coded != nullptr)
-      CK(build_fast(map, L, d_xyz, stride, n, G, dense[0], d_sparse, (int)h_nsparse, pblocks, prob, coded, stream, &fast_done));
+      CK(build_fast(map, L, d_xyz, stride, n, G, dense[0], d_sparse, (int)h_nsparse, pblocks, prob, coded, stream, ev_start,
+                    ev_end, &fast_done));
     if (fast_done)
       goto done;
     if (need_d2)
@@ -1533,6 +1571,8 @@ cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t strid
     d_stack = nullptr;
     if (coded != nullptr)
       CK(build_codes(map, d_d2, G, coded, stream));
+    if (ev)
+      cudaEventRecord(ev[1], stream);  // legacy passes: one region from the first kernel to the last (allocations included)
     if (keep_d2 != nullptr)
     {
       *keep_d2 = d_d2;

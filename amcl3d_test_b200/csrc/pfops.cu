@@ -1428,6 +1428,13 @@ cudaError_t launch_chain_sum_array(const float* v, uint64_t n, float* total, flo
   return launch_chain(v, 1, 0, n, kChainSum, 0.f, 0.f, nullptr, total, chain_meta(scratch, n), chain_mode, stream);
 }
 
+cudaError_t launch_chain_dense(const float* v, uint64_t n, int positive_only, float* prefix, float* total, float* scratch,
+                               int chain_mode, cudaStream_t stream)
+{
+  return launch_chain(v, 1, 0, n, positive_only ? kChainSumPositive : kChainSum, 0.f, 0.f, prefix, total,
+                      chain_meta(scratch, n), chain_mode, stream);
+}
+
 cudaError_t launch_chain_thresholds(int S, float* thr, float* scratch, int chain_mode, cudaStream_t stream)
 {
   if (S <= 0)

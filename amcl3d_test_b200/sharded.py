@@ -1,5 +1,10 @@
 """Particles sharded across the GPUs of one box; one process per GPU, torch.distributed.
 
+The product path is PeerShardedFilter (bottom of the file): the exchange step runs in the library's own kernels over
+peer memory (csrc/shard.cu, C-ABI amcl3d_b200_pf_shard_*); torch.distributed only carries the 64-byte CUDA IPC handles
+at set-up.  ShardedFilter + CudaShard is the older NCCL all-gather formulation, kept as the A/B baseline and because
+its orchestration runs on CPU with gloo.
+
 Partitioning: the grid is replicated, rank r owns the contiguous block [r*n_local, (r+1)*n_local) of the
 global particle order (contiguous blocks keep the order the reference's serial prefix needs).  The update
 is embarrassingly parallel (no collective).  Normalise + resample has one real exchange step: an
@@ -172,3 +177,92 @@ class CudaShard:
 
     def launch_count(self):
         return self.pf_local.launch_count() + self.pf_full.launch_count()
+
+
+class PeerShardedFilter:
+    """One rank of a particle set sharded over the GPUs of one NVLink box, exchange in our own kernels over peer
+    memory (csrc/shard.cu): 4-byte weights are stored into every peer's dense copy, the sequential chains are
+    replayed on every rank (bit-identical to one GPU), the selected particles are loaded from their owners.
+    torch.distributed is used once, to hand the CUDA IPC handles round."""
+
+    def __init__(self, grid3d, n_total: int, device: torch.device, group=None):
+        from .api import ParticleFilter
+
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n_total = n_total
+        self.device = device
+        self.pf = ParticleFilter(grid3d)
+        self.lo, self.hi = self.pf.shard_init(n_total, self.rank, self.world)
+        assert (self.lo, self.hi) == shard_bounds(n_total, self.world, self.rank)
+        if self.world > 1:
+            mine = torch.frombuffer(bytearray(self.pf.shard_ipc_handle()), dtype=torch.uint8).to(device)
+            allh = torch.empty((self.world, 64), dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(allh, mine.view(1, 64), group=group)
+            self.pf.shard_attach_ipc([bytes(r) for r in allh.cpu().numpy()])
+            dist.barrier(group=group)
+        self.pf.set_stream(torch.cuda.current_stream(device).cuda_stream)
+        self.beacons = None
+        self.wr_local = None
+        self._mean_buf = torch.zeros(8, dtype=torch.float32, device=device)
+
+    def set_particles(self, block):
+        """This rank's block [lo, hi) of the global particle order, (hi - lo, 7) float32 on the host."""
+        assert block.shape[0] == self.hi - self.lo
+        self.pf.p_ = block
+
+    def set_particles_device(self, src: torch.Tensor):
+        """Same from a device (or pinned host) tensor, on the current stream."""
+        ptr, n = self.pf.device_ptr()
+        assert src.numel() == 7 * n
+        dst = _as_tensor(ptr, n, self.device)
+        dst.copy_(src.view(-1), non_blocking=True)
+
+    def particles_device(self) -> torch.Tensor:
+        """Zero-copy view of p_ (valid until the next resample: the block ping-pongs inside the exchange region)."""
+        ptr, n = self.pf.device_ptr()
+        return _as_tensor(ptr, n, self.device).view(n, 7)
+
+    def set_cloud(self, cloud):
+        self.pf.set_cloud(cloud)
+
+    def set_beacons(self, beacons, alpha, sigma):
+        self.beacons, self.alpha, self.sigma = beacons, alpha, sigma
+        self.wr_local = torch.zeros(self.hi - self.lo, dtype=torch.float32, device=self.device)
+
+    def set_async(self, enable: bool):
+        self.pf.set_async(enable)
+
+    def update(self):
+        if self.wr_local is not None:
+            self.pf.update_split(self.beacons, self.sigma, self.wr_local.data_ptr())
+        else:
+            self.pf.update()
+
+    def resample(self, u01: float, want_idx=False):
+        if self.wr_local is not None:
+            return self.pf.shard_resample(u01, self.wr_local.data_ptr(), self.alpha, want_idx=want_idx)
+        return self.pf.shard_resample(u01, want_idx=want_idx)
+
+    def mean_device(self) -> torch.Tensor:
+        self.pf.shard_mean(self._mean_buf.data_ptr(), fetch=False)
+        return self._mean_buf[:7]
+
+    def mean(self):
+        return self.pf.shard_mean()
+
+    def launch_count(self):
+        return self.pf.launch_count()
+
+
+def _as_tensor(ptr: int, n_particles: int, device: torch.device) -> torch.Tensor:
+    """float32 view of 7 * n floats of library-owned device memory (CUDA array interface, no copy)."""
+
+    class _Mem:
+        pass
+
+    m = _Mem()
+    m.__cuda_array_interface__ = {"shape": (7 * n_particles,), "typestr": "<f4", "data": (ptr, False), "version": 3,
+                                  "strides": None}
+    return torch.as_tensor(m, device=device)

@@ -264,6 +264,40 @@ int amcl3d_b200_pf_update_sample_height(amcl3d_b200_pf_t pf, const float* keypos
 int amcl3d_b200_pf_resample_step(amcl3d_b200_pf_t pf, int weight_multiply, int min_resamp, int max_resamp,
                                  const float* keyposes_xyz, uint64_t nkey, int* new_size);
 
+/* ---- particles sharded over the GPUs of one NVLink box ------------------------------------------
+ * The grid is replicated (one grid handle per device); rank r of `world` owns the contiguous block
+ * [lo, hi) of the global particle order (the first n_total % world ranks hold one particle more).  update() is local.
+ * The exchange step of the global particleNormalize + resample (ParticleFilter.cpp:168-196, 230-254) runs in our own
+ * kernels over peer memory: every rank stores its 4-byte weights into every peer's dense copy over NVLink (no 28-byte
+ * records travel), replays the reference's sequential f32 chains over the full copy -- so weights, prefix and indices
+ * are bit-identical to one GPU and to the CPU -- and loads the particles its output slice selects from their owners.
+ * Ranks may be processes (one per GPU: exchange the 64-byte handles, e.g. with torch.distributed / MPI, then
+ * attach_ipc) or handles of one process (attach_local, peer access).  The shard_* calls are collective: every rank
+ * makes the same sequence of them.  A peer that never arrives is reported after ~4 s (ERR_STATE), not waited for. */
+/* turns the handle into rank `rank` of `world`: p_ becomes this rank's block (size hi - lo) inside a freshly allocated
+ * exchange region; fill it with set_particles / get it with get_particles as usual */
+int amcl3d_b200_pf_shard_init(amcl3d_b200_pf_t pf, uint64_t n_total, int rank, int world);
+int amcl3d_b200_pf_shard_info(amcl3d_b200_pf_t pf, uint64_t* lo, uint64_t* hi, uint64_t* region_bytes);
+/* CUDA IPC handle (64 bytes) of this rank's region / open the regions of all ranks (`world` handles, `stride` bytes apart,
+ * indexed by rank; the own entry is ignored) */
+int amcl3d_b200_pf_shard_ipc_handle(amcl3d_b200_pf_t pf, void* handle64, size_t cap);
+int amcl3d_b200_pf_shard_attach_ipc(amcl3d_b200_pf_t pf, const void* handles, size_t stride);
+/* all ranks are handles of this process (pfs[r] = rank r): enables peer access between their devices */
+int amcl3d_b200_pf_shard_attach_local(amcl3d_b200_pf_t* pfs, int world);
+/* global particleNormalize + resample(r = u01 / N); p_ becomes this rank's slice [lo, hi) of the resampled set.
+ * d_wr_local (optional, DEVICE, hi - lo floats): raw range-beacon weights of update_split, fused with alpha over the
+ * global sums before normalising (row R).  idx (optional, HOST, hi - lo ints): global source indices. */
+int amcl3d_b200_pf_shard_resample(amcl3d_b200_pf_t pf, float u01, const void* d_wr_local, float alpha, int32_t* idx);
+/* getMean over all ranks (partial sums exchanged through peer memory, combined in rank order in f64); out7 (HOST) and /
+ * or d_out7 (DEVICE), at least one */
+int amcl3d_b200_pf_shard_mean(amcl3d_b200_pf_t pf, float out7[7], void* d_out7);
+
+/* the two collective calls for ranks that are handles of ONE process (attach_local): issued on every handle in stream
+ * order, then waited for (a synchronous call on one handle would wait for peers that were not launched yet).
+ * d_wr_local: NULL or `world` DEVICE pointers (rank r's raw range weights). */
+int amcl3d_b200_pf_shard_resample_local(amcl3d_b200_pf_t* pfs, int world, float u01, const void* const* d_wr_local, float alpha);
+int amcl3d_b200_pf_shard_mean_local(amcl3d_b200_pf_t* pfs, int world, float out7[7]);
+
 /* sequential f32 inclusive prefix of the current weights (ParticleFilter.cpp:259-264), for tests and
  * for multi-GPU callers: DEVICE pointer valid until the next call on the handle */
 int amcl3d_b200_pf_prefix(amcl3d_b200_pf_t pf, void** d_prefix, float* host_out, uint64_t cap);

@@ -1,0 +1,134 @@
+"""Particles sharded over GPUs through the C-ABI peer-memory exchange (csrc/shard.cu): the sharded result
+must equal the one-GPU result bit for bit -- weights, resampled indices and particles (ParticleFilter.cpp:168-196,
+230-254), several frames in a row (the exchange region ping-pongs by epoch).
+
+  * world 1 through the sharded entry points: runs on any box with one GPU;
+  * two devices inside ONE process (amcl3d_b200_pf_shard_attach_local, the path the C++ classes use): needs 2 GPUs;
+  * one process per GPU under torch.distributed.run at 2 ranks (CUDA IPC): needs 2 GPUs; tools/sharded_check.py.
+"""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _device_count():
+    from amcl3d_test_b200 import api
+
+    return api.device_info(0)["device_count"]
+
+
+def _world(device, resol=0.1):
+    from amcl3d_test_b200 import Grid3d, synth
+
+    sm = synth.make_map((20.0, 20.0, 5.0), resol)
+    g = Grid3d(device)
+    g.computePointCloud(sm.points, resol)
+    g.computeGrid(sm.points, 0.05, sub=2)
+    return sm, g
+
+
+def _one_gpu(g, P, clouds, u01s, beacons=None):
+    from amcl3d_test_b200 import ParticleFilter
+
+    pf = ParticleFilter(g)
+    pf.p_ = P
+    out = []
+    for cloud, u01 in zip(clouds, u01s):
+        if beacons is not None:
+            pf.update(cloud, beacons=beacons, alpha=0.5, sigma=0.53)
+        else:
+            pf.update(cloud)
+        W = pf.p_
+        pf.particleNormalize()
+        idx = pf.resample(u01, want_idx=True)
+        out.append((W, pf.p_, idx, pf.getMean()))
+    return out
+
+
+@pytest.mark.parametrize("with_beacons", [False, True])
+def test_world_of_one_equals_the_plain_handle(O, with_beacons):
+    import torch
+
+    from amcl3d_test_b200 import synth
+    from amcl3d_test_b200.sharded import PeerShardedFilter
+
+    sm, g = _world(0)
+    clouds = [synth.make_cloud(sm, 1500, 9.0, seed=synth.SEED_CLOUD + k) for k in range(3)]
+    u01s = [0.37, 0.0, 0.93]
+    P = synth.make_particles(sm, 10_007, "G")
+    beacons = synth.make_beacons(sm, 8) if with_beacons else None
+    ref = _one_gpu(g, P, clouds, u01s, beacons)
+    f = PeerShardedFilter(g, P.shape[0], torch.device("cuda", 0))
+    assert (f.lo, f.hi) == (0, P.shape[0])
+    f.set_particles(P)
+    if with_beacons:
+        f.set_beacons(beacons, 0.5, 0.53)
+    for k, (cloud, u01) in enumerate(zip(clouds, u01s)):
+        f.set_cloud(cloud)
+        f.update()
+        idx = f.resample(u01, want_idx=True)
+        assert np.array_equal(idx, ref[k][2])
+        assert np.array_equal(bits(f.pf.p_), bits(ref[k][1]))
+        mean = f.mean()
+        assert np.allclose(mean[:6], ref[k][3][:6], rtol=1e-5, atol=1e-6) and mean[6] == ref[k][3][6]
+    # first frame also against the CPU oracle (indices are the criterion of north_star)
+    mn, mx = O.compute_bounds(sm.points)
+    m = O.Map(mn, mx, 0.1, 0.05)
+    m.set_prob(g.downloadGrid())
+    if not with_beacons:
+        W = O.update(m, O.particles(P), clouds[0])
+        O.normalize(m, W)
+        _, oidx = O.resample(W, np.float32(u01s[0]))
+        assert np.array_equal(ref[0][2], oidx)
+
+
+def test_two_devices_in_one_process():
+    """The ranks are handles of one process (attach_local + stream order): what amcl3d::ParticleFilter::setDevices uses."""
+    if _device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from amcl3d_test_b200 import ParticleFilter, synth
+    from amcl3d_test_b200.sharded import shard_bounds
+
+    sm, g0 = _world(0)
+    _, g1 = _world(1)
+    grids = [g0, g1]
+    clouds = [synth.make_cloud(sm, 1500, 9.0, seed=synth.SEED_CLOUD + k) for k in range(3)]
+    u01s = [0.37, 0.0, 0.93]
+    n = 20_001
+    P = synth.make_particles(sm, n, "T")
+    ref = _one_gpu(g0, P, clouds, u01s)
+    pfs = [ParticleFilter(g) for g in grids]
+    for r, pf in enumerate(pfs):
+        lo, hi = pf.shard_init(n, r, 2)
+        assert (lo, hi) == shard_bounds(n, 2, r)
+        pf.p_ = P[lo:hi]
+    ParticleFilter.shard_attach_local(pfs)
+    for k, (cloud, u01) in enumerate(zip(clouds, u01s)):
+        for pf in pfs:
+            pf.update(cloud)
+        ParticleFilter.shard_resample_local(pfs, u01)
+        out = np.concatenate([pf.p_ for pf in pfs])
+        assert np.array_equal(bits(out), bits(ref[k][1]))
+        mean = ParticleFilter.shard_mean_local(pfs)
+        assert np.allclose(mean[:6], ref[k][3][:6], rtol=1e-5, atol=1e-6) and mean[6] == ref[k][3][6]
+
+
+def test_two_ranks_one_process_per_gpu():
+    """torch.distributed.run at 2 ranks: CUDA IPC handles, peer stores/loads over NVLink; tools/sharded_check.py."""
+    if _device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", str(ROOT / "tools" / "sharded_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "OK bit-identical to 1 GPU" in r.stdout

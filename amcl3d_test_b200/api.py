@@ -144,6 +144,14 @@ class Grid3d:
         check(self._L.amcl3d_b200_grid_cloud_weight(self._h, cloud.ctypes.data if npts else None, stride, npts, *pose, trig_mode, C.byref(w)))
         return np.float32(w.value)
 
+    def clone(self, device: int, with_float=False) -> "Grid3d":
+        """Replica of this grid on another device (peer copy of the coded cells; the float cells only on request)."""
+        r = Grid3d.__new__(Grid3d)
+        r._L = self._L
+        r._h = C.c_void_p()
+        check(self._L.amcl3d_b200_grid_clone(self._h, int(device), int(bool(with_float)), C.byref(r._h)))
+        return r
+
     def device_ptr(self) -> int:
         p = C.c_void_p()
         check(self._L.amcl3d_b200_grid_device_ptr(self._h, C.byref(p)))
@@ -425,11 +433,26 @@ class ParticleFilter:
         check(capi.load().amcl3d_b200_pf_shard_attach_local(arr, len(pfs)))
 
     @staticmethod
-    def shard_resample_local(pfs, u01, d_wr_local=None, alpha=1.0):
+    def shard_resample_local(pfs, u01, normalize=True, d_wr_local=None, alpha=1.0):
         """The collective resample for ranks that are handles of one process: launched on all, then waited for."""
         arr = (C.c_void_p * len(pfs))(*[p._h.value for p in pfs])
         wr = (C.c_void_p * len(pfs))(*[int(v) for v in d_wr_local]) if d_wr_local is not None else None
-        check(capi.load().amcl3d_b200_pf_shard_resample_local(arr, len(pfs), float(np.float32(u01)), wr, float(alpha)))
+        check(capi.load().amcl3d_b200_pf_shard_resample_local(arr, len(pfs), float(np.float32(u01)), int(bool(normalize)), wr,
+                                                              float(alpha)))
+
+    @staticmethod
+    def shard_normalize_local(pfs):
+        arr = (C.c_void_p * len(pfs))(*[p._h.value for p in pfs])
+        check(capi.load().amcl3d_b200_pf_shard_normalize_local(arr, len(pfs)))
+
+    def shard_normalize(self, fetch=True):
+        """Global particleNormalize: the sum runs over all ranks, this rank's block is normalised in place."""
+        if not fetch:
+            check(self._L.amcl3d_b200_pf_shard_normalize(self._h, None))
+            return None
+        wtp = C.c_float(0)
+        check(self._L.amcl3d_b200_pf_shard_normalize(self._h, C.byref(wtp)))
+        return np.float32(wtp.value)
 
     @staticmethod
     def shard_mean_local(pfs) -> np.ndarray:
@@ -438,11 +461,11 @@ class ParticleFilter:
         check(capi.load().amcl3d_b200_pf_shard_mean_local(arr, len(pfs), out.ctypes.data))
         return out
 
-    def shard_resample(self, u01, d_wr_local: int = 0, alpha=1.0, want_idx=False):
-        """Global particleNormalize + resample over all ranks; p_ becomes this rank's slice of the resampled set."""
+    def shard_resample(self, u01, d_wr_local: int = 0, alpha=1.0, want_idx=False, normalize=True):
+        """Global [particleNormalize +] resample over all ranks; p_ becomes this rank's slice of the resampled set."""
         idx = np.empty(self.size(), np.int32) if want_idx else None
-        check(self._L.amcl3d_b200_pf_shard_resample(self._h, float(np.float32(u01)), C.c_void_p(d_wr_local or 0), float(alpha),
-                                                    idx.ctypes.data if want_idx else None))
+        check(self._L.amcl3d_b200_pf_shard_resample(self._h, float(np.float32(u01)), int(bool(normalize)), C.c_void_p(d_wr_local or 0),
+                                                    float(alpha), idx.ctypes.data if want_idx else None))
         return idx
 
     def shard_mean(self, d_out7: int = 0, fetch=True):

@@ -20,6 +20,7 @@ SYMBOLS = [
     "amcl3d_b200_pf_shard_init", "amcl3d_b200_pf_shard_info", "amcl3d_b200_pf_shard_ipc_handle",
     "amcl3d_b200_pf_shard_attach_ipc", "amcl3d_b200_pf_shard_attach_local", "amcl3d_b200_pf_shard_resample",
     "amcl3d_b200_pf_shard_mean", "amcl3d_b200_pf_shard_resample_local", "amcl3d_b200_pf_shard_mean_local",
+    "amcl3d_b200_pf_shard_normalize", "amcl3d_b200_pf_shard_normalize_local", "amcl3d_b200_grid_clone",
     "amcl3d_b200_grid_create", "amcl3d_b200_grid_destroy", "amcl3d_b200_grid_get_info",
     "amcl3d_b200_grid_compute_bounds", "amcl3d_b200_grid_set_map", "amcl3d_b200_grid_build",
     "amcl3d_b200_grid_download_edt", "amcl3d_b200_grid_upload", "amcl3d_b200_grid_download",
@@ -92,9 +93,12 @@ def load():
         "amcl3d_b200_pf_shard_ipc_handle": (i, [vp, vp, C.c_size_t]),
         "amcl3d_b200_pf_shard_attach_ipc": (i, [vp, vp, C.c_size_t]),
         "amcl3d_b200_pf_shard_attach_local": (i, [P(vp), i]),
-        "amcl3d_b200_pf_shard_resample": (i, [vp, f32, vp, f32, vp]),
+        "amcl3d_b200_pf_shard_resample": (i, [vp, f32, i, vp, f32, vp]),
+        "amcl3d_b200_pf_shard_normalize": (i, [vp, P(f32)]),
+        "amcl3d_b200_pf_shard_normalize_local": (i, [P(vp), i]),
+        "amcl3d_b200_grid_clone": (i, [vp, i, i, P(vp)]),
         "amcl3d_b200_pf_shard_mean": (i, [vp, vp, vp]),
-        "amcl3d_b200_pf_shard_resample_local": (i, [P(vp), i, f32, P(vp), f32]),
+        "amcl3d_b200_pf_shard_resample_local": (i, [P(vp), i, f32, i, P(vp), f32]),
         "amcl3d_b200_pf_shard_mean_local": (i, [P(vp), i, vp]),
         "amcl3d_b200_set_l2_fetch_granularity": (i, [i, i]),
         "amcl3d_b200_get_l2_fetch_granularity": (i, [i, P(i)]),

@@ -504,6 +504,62 @@ int amcl3d_b200_grid_upload(amcl3d_b200_grid_t g, const float* prob, const uint3
   return AMCL3D_B200_OK;
 }
 
+// replica of a built / loaded grid on another device of the box (the grid is replicated, the particles are
+// sharded).  The coded cells travel as one peer copy; the linear float cells only on request (or when there are no codes).
+int amcl3d_b200_grid_clone(amcl3d_b200_grid_t src, int device, int with_float, amcl3d_b200_grid_t* out)
+{
+  if (!src || !out)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
+  if (!src->map.has_map || !src->map.has_grid)
+    return fail(AMCL3D_B200_ERR_STATE, "no grid to replicate");
+  amcl3d_b200_grid_t g = nullptr;
+  if (int rc = amcl3d_b200_grid_create(device, &g))
+    return rc;
+  cudaError_t e = cudaSuccess;
+  g->map = src->map;
+  g->sensor_dev = src->sensor_dev;
+  g->use_codes = src->use_codes;
+  g->edt_fast = src->edt_fast;
+  g->d_prob = nullptr;
+  g->coded = CodedGrid{};
+  const bool coded = src->coded.rep != kRepFloat && src->coded.codes != nullptr;
+  const uint64_t cells = src->map.n_cells;
+  if (coded)
+  {
+    const size_t align = (size_t)2 << 20;
+    void* alloc = nullptr;
+    e = cudaMalloc(&alloc, src->coded.bytes + align);
+    if (e == cudaSuccess)
+    {
+      g->coded = src->coded;
+      g->coded.codes_alloc = alloc;
+      g->coded.codes = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(alloc) + align - 1) & ~(uintptr_t)(align - 1));
+      g->coded.lut = nullptr;
+      e = cudaMemcpyPeer(g->coded.codes, device, src->coded.codes, src->device, src->coded.bytes);
+    }
+    if (e == cudaSuccess)
+      e = cudaMalloc(&g->coded.lut, sizeof(float) * std::max<uint32_t>(src->coded.lut_n, 1));
+    if (e == cudaSuccess)
+      e = cudaMemcpyPeer(g->coded.lut, device, src->coded.lut, src->device, sizeof(float) * src->coded.lut_n);
+  }
+  if (e == cudaSuccess && (with_float || !coded) && src->d_prob)
+  {
+    e = ensure(g->d_prob, g->prob_cap, cells);
+    if (e == cudaSuccess)
+      e = cudaMemcpyPeer(g->d_prob, device, src->d_prob, src->device, sizeof(float) * cells);
+  }
+  if (e == cudaSuccess)
+    e = cudaDeviceSynchronize();
+  if (e != cudaSuccess)
+  {
+    amcl3d_b200_grid_destroy(g);
+    return fail_cuda(e, "grid_clone");
+  }
+  refresh_map(g);
+  *out = g;
+  return AMCL3D_B200_OK;
+}
+
 int amcl3d_b200_grid_download(amcl3d_b200_grid_t g, float* prob, uint64_t cap)
 {
   if (!g || !prob)
@@ -512,6 +568,8 @@ int amcl3d_b200_grid_download(amcl3d_b200_grid_t g, float* prob, uint64_t cap)
     return fail(AMCL3D_B200_ERR_STATE, "no grid");
   if (cap < g->map.n_cells)
     return fail(AMCL3D_B200_ERR_ARG, "output too small");
+  if (!g->d_prob)
+    return fail(AMCL3D_B200_ERR_STATE, "this replica holds the coded cells only (amcl3d_b200_grid_clone with_float = 0)");
   if (int rc = use_device(g->device))
     return rc;
   CU(cudaMemcpy(prob, g->d_prob, sizeof(float) * g->map.n_cells, cudaMemcpyDeviceToHost));
@@ -1799,7 +1857,24 @@ int amcl3d_b200_pf_shard_attach_local(amcl3d_b200_pf_t* pfs, int world)
   return AMCL3D_B200_OK;
 }
 
-int amcl3d_b200_pf_shard_resample(amcl3d_b200_pf_t pf, float u01, const void* d_wr_local, float alpha, int32_t* idx)
+namespace
+{
+// one exchange: this rank's weights (+ raw range weights, isIntoMap flags) into every rank's dense copy, then wait for
+// everybody else's.  Returns the parity of the dense copies that now hold the epoch.
+int shard_exchange(amcl3d_b200_pf_t pf, const void* d_wr_local, uint32_t* parity_out)
+{
+  amcl3d_b200_pf_s::Shard& S = pf->shard;
+  S.epoch += 1;
+  const uint32_t parity = S.epoch & 1u;
+  const uint32_t* flags = reinterpret_cast<const uint32_t*>(S.region + S.peers.off_flags);
+  CU(launch_shard_publish(pf->grid->map, S.peers, pf->d_p, reinterpret_cast<const float*>(d_wr_local), (uint32_t)pf->n,
+                          (uint32_t)S.lo, (uint32_t)S.n_total, parity, S.epoch, S.rank, S.d_done, pf->stream));
+  CU(launch_shard_wait(flags, 0, S.world, S.epoch, S.d_error, pf->stream));
+  pf->launches += 2;
+  *parity_out = parity;
+  return AMCL3D_B200_OK;
+}
+int shard_ready(amcl3d_b200_pf_t pf)
 {
   if (!pf)
     return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
@@ -1808,8 +1883,46 @@ int amcl3d_b200_pf_shard_resample(amcl3d_b200_pf_t pf, float u01, const void* d_
     return fail(AMCL3D_B200_ERR_STATE, "shard not attached to its peers");
   if (pf->n != S.hi - S.lo)
     return fail(AMCL3D_B200_ERR_STATE, "p_ must hold this rank's block of the partition");
-  if (int rc = use_device(pf->grid->device))
+  return use_device(pf->grid->device);
+}
+}  // namespace
+
+int amcl3d_b200_pf_shard_normalize(amcl3d_b200_pf_t pf, float* wtp)
+{
+  if (int rc = shard_ready(pf))
     return rc;
+  amcl3d_b200_pf_s::Shard& S = pf->shard;
+  const uint64_t N = S.n_total;
+  CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(N)));
+  {
+    Timed t(pf);
+    uint32_t parity = 0;
+    if (int rc = shard_exchange(pf, nullptr, &parity))
+      return rc;
+    const float* w = reinterpret_cast<const float*>(S.region + S.peers.off_w) + (size_t)parity * N;
+    // ParticleFilter.cpp:171-178 over ALL particles (same chain on every rank), :180-195 on the rank's own block
+    CU(launch_chain_dense(w, N, 1, nullptr, pf->d_scalars + 0, pf->d_dense, pf->chain_mode, pf->stream));
+    CU(launch_normalize(pf->grid->map, pf->d_p, pf->n, pf->d_scalars + 0, pf->stream));
+    pf->launches += 2;
+    pf->launches += chain_extra_launches_take();
+  }
+  if (!wtp)
+  {
+    if (pf->async_mode)
+      return AMCL3D_B200_OK;
+    return shard_check_error(pf);
+  }
+  CU(cudaMemcpyAsync(wtp, pf->d_scalars, sizeof(float), cudaMemcpyDeviceToHost, pf->stream));
+  return shard_check_error(pf);
+}
+
+int amcl3d_b200_pf_shard_resample(amcl3d_b200_pf_t pf, float u01, int normalize, const void* d_wr_local, float alpha, int32_t* idx)
+{
+  if (int rc = shard_ready(pf))
+    return rc;
+  if (!normalize && d_wr_local)
+    return fail(AMCL3D_B200_ERR_ARG, "the range fusion is part of the normalising call");
+  amcl3d_b200_pf_s::Shard& S = pf->shard;
   const uint64_t N = S.n_total, n = pf->n;
   CU(ensure(pf->d_prefix, pf->prefix_cap, N));
   CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(N)));
@@ -1819,19 +1932,15 @@ int amcl3d_b200_pf_shard_resample(amcl3d_b200_pf_t pf, float u01, const void* d_
     CU(ensure(pf->d_idx, pf->idx_cap, n));
     d_idx = pf->d_idx;
   }
-  S.epoch += 1;
-  const uint32_t parity = S.epoch & 1u;
-  float* w = reinterpret_cast<float*>(S.region + S.peers.off_w) + (size_t)parity * N;
-  float* wr = reinterpret_cast<float*>(S.region + S.peers.off_wr) + (size_t)parity * N;
-  const uint8_t* inmap = reinterpret_cast<const uint8_t*>(S.region + S.peers.off_inmap) + (size_t)parity * N;
-  const uint32_t* flags = reinterpret_cast<const uint32_t*>(S.region + S.peers.off_flags);
   float* out = reinterpret_cast<float*>(S.region + S.peers.off_p + (size_t)(S.cur ^ 1u) * S.peers.p_bytes);
   {
     Timed t(pf);
-    // exchange: this rank's weights into every rank's dense copy, then wait for everybody else's
-    CU(launch_shard_publish(pf->grid->map, S.peers, pf->d_p, reinterpret_cast<const float*>(d_wr_local), (uint32_t)n, (uint32_t)S.lo,
-                            (uint32_t)N, parity, S.epoch, S.rank, S.d_done, pf->stream));
-    CU(launch_shard_wait(flags, 0, S.world, S.epoch, S.d_error, pf->stream));
+    uint32_t parity = 0;
+    if (int rc = shard_exchange(pf, d_wr_local, &parity))
+      return rc;
+    float* w = reinterpret_cast<float*>(S.region + S.peers.off_w) + (size_t)parity * N;
+    float* wr = reinterpret_cast<float*>(S.region + S.peers.off_wr) + (size_t)parity * N;
+    const uint8_t* inmap = reinterpret_cast<const uint8_t*>(S.region + S.peers.off_inmap) + (size_t)parity * N;
     // the reference's sequential chains over ALL particles, replicated on every rank: same bits as one GPU
     if (d_wr_local)
     {
@@ -1840,12 +1949,16 @@ int amcl3d_b200_pf_shard_resample(amcl3d_b200_pf_t pf, float u01, const void* d_
       CU(launch_dense_fuse(w, wr, N, pf->d_scalars + 0, pf->d_scalars + 1, alpha, pf->stream));
       pf->launches += 3;
     }
-    CU(launch_chain_dense(w, N, 1, nullptr, pf->d_scalars + 0, pf->d_dense, pf->chain_mode, pf->stream));  // ParticleFilter.cpp:171-178
-    CU(launch_dense_normalize(w, inmap, N, pf->d_scalars + 0, pf->stream));                                // :180-195
-    CU(launch_chain_dense(w, N, 0, pf->d_prefix, nullptr, pf->d_dense, pf->chain_mode, pf->stream));       // :235-247
+    if (normalize)
+    {
+      CU(launch_chain_dense(w, N, 1, nullptr, pf->d_scalars + 0, pf->d_dense, pf->chain_mode, pf->stream));  // ParticleFilter.cpp:171-178
+      CU(launch_dense_normalize(w, inmap, N, pf->d_scalars + 0, pf->stream));                                // :180-195
+      pf->launches += 2;
+    }
+    CU(launch_chain_dense(w, N, 0, pf->d_prefix, nullptr, pf->d_dense, pf->chain_mode, pf->stream));  // :235-247
     // this rank's output slice; the selected particles are read from their owners over NVLink
     CU(launch_shard_search(S.peers, pf->d_prefix, N, u01, S.lo, S.hi, S.cur, out, d_idx, pf->stream));
-    pf->launches += 6;
+    pf->launches += 2;
     pf->launches += chain_extra_launches_take();
   }
   S.cur ^= 1u;
@@ -1895,7 +2008,7 @@ int amcl3d_b200_pf_shard_mean(amcl3d_b200_pf_t pf, float out7[7], void* d_out7)
 
 // ranks = handles of ONE process: the collective calls are issued on every handle in stream order first and waited for
 // afterwards (a synchronous call on rank 0 alone would wait for a publish rank 1 has not launched yet)
-int amcl3d_b200_pf_shard_resample_local(amcl3d_b200_pf_t* pfs, int world, float u01, const void* const* d_wr_local, float alpha)
+int amcl3d_b200_pf_shard_normalize_local(amcl3d_b200_pf_t* pfs, int world)
 {
   if (!pfs || world < 1 || world > (int)kMaxShardWorld)
     return fail(AMCL3D_B200_ERR_ARG, "bad handle array");
@@ -1905,7 +2018,30 @@ int amcl3d_b200_pf_shard_resample_local(amcl3d_b200_pf_t* pfs, int world, float 
       return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
     const bool was = pfs[r]->async_mode;
     pfs[r]->async_mode = true;
-    const int rc = amcl3d_b200_pf_shard_resample(pfs[r], u01, d_wr_local ? d_wr_local[r] : nullptr, alpha, nullptr);
+    const int rc = amcl3d_b200_pf_shard_normalize(pfs[r], nullptr);
+    pfs[r]->async_mode = was;
+    if (rc != AMCL3D_B200_OK)
+      return rc;
+  }
+  for (int r = 0; r < world; ++r)
+    if (!pfs[r]->async_mode)
+      if (int rc = amcl3d_b200_pf_sync(pfs[r]))
+        return rc;
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_shard_resample_local(amcl3d_b200_pf_t* pfs, int world, float u01, int normalize, const void* const* d_wr_local,
+                                        float alpha)
+{
+  if (!pfs || world < 1 || world > (int)kMaxShardWorld)
+    return fail(AMCL3D_B200_ERR_ARG, "bad handle array");
+  for (int r = 0; r < world; ++r)
+  {
+    if (!pfs[r])
+      return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+    const bool was = pfs[r]->async_mode;
+    pfs[r]->async_mode = true;
+    const int rc = amcl3d_b200_pf_shard_resample(pfs[r], u01, normalize, d_wr_local ? d_wr_local[r] : nullptr, alpha, nullptr);
     pfs[r]->async_mode = was;
     if (rc != AMCL3D_B200_OK)
       return rc;

@@ -141,13 +141,22 @@ Grid3d::Grid3d(int device) : g_log(new VSCOMMON::Logger("GRID3D"))
     throw_last("Grid3d: no usable CUDA device (there is no CPU fallback)");
 }
 
+Grid3d::Grid3d(amcl3d_b200_grid_t borrowed) : handle_(borrowed), owns_(false), g_log(new VSCOMMON::Logger("GRID3D"))
+{
+  if (!handle_)
+    throw std::runtime_error("Grid3d: NULL handle");
+  refreshInfo();
+}
+
 Grid3d::~Grid3d()
 {
-  amcl3d_b200_grid_destroy(handle_);
+  if (owns_)
+    amcl3d_b200_grid_destroy(handle_);
 }
 
 void Grid3d::refreshInfo()
 {
+  ++generation_;
   if (!pc_info_)
     pc_info_.reset(new PointCloudInfo());
   amcl3d_b200_grid_info_t info;

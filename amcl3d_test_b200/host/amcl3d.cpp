@@ -84,13 +84,14 @@ int MonteCarloLocalization::downsampleInput(const pcl::PointCloud<PointType>::Pt
   constexpr uint32_t stride = sizeof(PointType) / sizeof(float);
   const int ioff = static_cast<int>(offsetof(PointType, intensity) / sizeof(float));
   uint32_t kept = 0;
-  check(amcl3d_b200_pf_set_cloud_downsampled(handle(), n ? &input_cloud->points[0].x : nullptr, stride, ioff, n, voxel_size_,
+  const amcl3d_b200_pf_t h = handle();
+  check(amcl3d_b200_pf_set_cloud_downsampled(h, n ? &input_cloud->points[0].x : nullptr, stride, ioff, n, voxel_size_,
                                              (input_cloud && !input_cloud->is_dense) ? 1 : 0, &kept),
         "downsampleInput");
   if (cloud_ds)
   {
     std::vector<float> xyzi(static_cast<size_t>(kept) * 4);
-    check(amcl3d_b200_pf_get_cloud(handle(), xyzi.data(), kept, &kept), "download filtered cloud");
+    check(amcl3d_b200_pf_get_cloud(h, xyzi.data(), kept, &kept), "download filtered cloud");
     cloud_ds->points.resize(kept);
     for (uint32_t i = 0; i < kept; ++i)
     {
@@ -107,12 +108,12 @@ int MonteCarloLocalization::downsampleInput(const pcl::PointCloud<PointType>::Pt
   return static_cast<int>(kept);
 }
 
+// the steps below run on the first device's handle; p_ stays on the device between them (lazy host mirror)
 void MonteCarloLocalization::updateDownsampled()
 {
-  check(amcl3d_b200_pf_set_particles(handle(), p_.empty() ? nullptr : &p_[0].x, p_.size()), "upload p_");
-  check(amcl3d_b200_pf_update(handle(), nullptr, 0, 1.f, 1.f, nullptr), "update");
-  uint64_t n = 0;
-  check(amcl3d_b200_pf_get_particles(handle(), p_.empty() ? nullptr : &p_[0].x, p_.size(), &n), "download p_");
+  const amcl3d_b200_pf_t h = handle();
+  check(amcl3d_b200_pf_update(h, nullptr, 0, 1.f, 1.f, nullptr), "update");
+  deviceChanged();
 }
 
 void MonteCarloLocalization::PFMove(const Particle& d, const Particle& noise)
@@ -122,7 +123,6 @@ void MonteCarloLocalization::PFMove(const Particle& d, const Particle& noise)
 
 int MonteCarloLocalization::computeSampleNum(const int cnt_per_grid)
 {
-  check(amcl3d_b200_pf_set_particles(handle(), p_.empty() ? nullptr : &p_[0].x, p_.size()), "upload p_");
   int s = 0;
   check(amcl3d_b200_pf_compute_sample_num(handle(), cnt_per_grid, min_resamp_num_, max_resamp_num_, &s), "computeSampleNum");
   return s;
@@ -131,23 +131,18 @@ int MonteCarloLocalization::computeSampleNum(const int cnt_per_grid)
 void MonteCarloLocalization::updateSampleHeight()
 {
   const std::vector<float> kp = keyposeArray();
-  check(amcl3d_b200_pf_set_particles(handle(), p_.empty() ? nullptr : &p_[0].x, p_.size()), "upload p_");
   check(amcl3d_b200_pf_update_sample_height(handle(), kp.data(), kp.size() / 3, nullptr), "updateSampleHeight");
-  uint64_t n = 0;
-  check(amcl3d_b200_pf_get_particles(handle(), p_.empty() ? nullptr : &p_[0].x, p_.size(), &n), "download p_");
+  deviceChanged();
 }
 
 void MonteCarloLocalization::PFResample(const bool weight_multiply)
 {
   const std::vector<float> kp = keyposeArray();
-  check(amcl3d_b200_pf_set_particles(handle(), p_.empty() ? nullptr : &p_[0].x, p_.size()), "upload p_");
   int new_size = 0;
   check(amcl3d_b200_pf_resample_step(handle(), weight_multiply ? 1 : 0, min_resamp_num_, max_resamp_num_,
                                      kp.empty() ? nullptr : kp.data(), kp.size() / 3, &new_size),
         "PFResample");
-  p_.resize(static_cast<size_t>(new_size));
-  uint64_t n = 0;
-  check(amcl3d_b200_pf_get_particles(handle(), p_.empty() ? nullptr : &p_[0].x, p_.size(), &n), "download p_");
+  deviceChanged();
 }
 
 }  // namespace amcl3d

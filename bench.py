@@ -7,7 +7,11 @@ particleNormalize + resample (bit-exact sequential chains) + getMean.
 Workload at N=1: BASELINE config 3 -- 100 k particles x 10 k-point cloud on the config-2 map
 (100 x 100 x 20 m at 0.05 m = 2000 x 2000 x 400 voxels, 6.4 GB float grid built on the GPU by the exact
 EDT + fused Gaussian writer).  At N>1 every rank holds a grid replica and its own 100 k-particle block
-(weak scaling); normalise/resample is global and bit-exact (all-gather + replicated sequential chain).
+(weak scaling); normalise/resample is global and bit-exact: the exchange runs in the library's own kernels over
+peer memory (csrc/shard.cu) and every rank checks its slice against a 1-GPU replay before the timed loop
+("parity_n").  The N=1 line also carries the update's roofline for both particle distributions of SURVEY 8(d)
+(T: L2-gather-bound, G: DRAM-line-bound; ceilings measured live by the library's gather probe) and sections for
+BASELINE configs 1 and 2 ("configs").
 
   python bench.py --gpus 1 --steps 20 --warmup 3
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -70,19 +74,6 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
-
-
-def ncu_traffic(workload, kind, n_local, n_pts):
-    """dram__bytes_read+write of the two launches of one update, from the committed ncu --set full capture of this
-    very workload (profiles/r1_traffic.json); None for any other workload."""
-    p = ROOT / "profiles" / "r1_traffic.json"
-    try:
-        d = json.loads(p.read_text())
-        if d.get("workload") == f"{workload} {kind} {n_local}x{n_pts}":
-            return float(d["per_update_total_dram_bytes"])
-    except Exception:
-        pass
-    return None
 
 
 class ClockSampler(threading.Thread):
@@ -292,12 +283,201 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def gather_peaks(grid):
+    """The gather ceilings of SURVEY 8(d), measured live on this grid's float cells with the library's own probe kernel
+    (amcl3d_b200_bench_gather: 8 independent 4-byte loads per thread and iteration, hashed addresses):
+      l2_resident_*   window of 8 MB: every sector is an L2 hit -> the L2 random-sector rate
+      coherent        all threads walk the same slowly moving 4 MB neighbourhood of the WHOLE grid (what a tracking
+                      cluster sweeping the cloud in lock-step does): the ceiling of regime B (T particles)
+      whole_random    uniform over the whole grid: every load is a DRAM line -> the ceiling of regime A (G particles)
+    loads/s; x 32 B = sector traffic."""
+    out = {}
+    for name, win, coh in (("l2_resident_random", 8 << 18, False), ("l2_resident_coherent", 8 << 18, True),
+                           ("whole_grid_coherent", 0, True), ("whole_grid_random", 0, False)):
+        best = 0.0
+        for _ in range(3):
+            ms, loads = grid.bench_gather(window_cells=win, blocks=148 * 8, iters=256, coherent=coh)
+            best = max(best, loads / (ms * 1e-3))
+        out[name] = best
+    return out
+
+
+def ncu_traffic(key):
+    """dram__bytes_read+write per update of the kernels of one update, from the committed ncu --set full capture of this very
+    workload key (profiles/r2_traffic.json, produced by tools/traffic_from_ncu.py); None for a workload never captured."""
+    try:
+        d = json.loads((ROOT / "profiles" / "r2_traffic.json").read_text())
+        e = d.get(key)
+        return (float(e["per_update_total_dram_bytes"]), e) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+def roofline_block(kind, workload, n_local, n_pts, n_in, upd_ms, phases, peaks, hbm_peak, hbm_src):
+    """One full roofline block of the update for one particle distribution.  Algorithmic bytes = one 32-B sector per
+    in-bounds particle x point evaluation; the ceiling is the measured gather rate of the regime the
+    distribution puts the kernel in, also x 32 B: T (tracking cluster, lock-step sweep -> sectors shared in L2) against
+    the coherent gather, G (global, nothing shared -> one DRAM line per evaluation) against the whole-grid random gather."""
+    loads_per_s = n_in / (upd_ms * 1e-3)
+    achieved = loads_per_s * 32.0 / 1e9
+    if kind == "T":
+        bound, peak_loads = "l2-gather", peaks["whole_grid_coherent"]
+        peak_src = f"measured in this run: amcl3d_b200_bench_gather whole_grid_coherent = {peak_loads:.4g} loads/s x 32 B"
+    else:
+        # nothing is shared between particles: every in-bounds evaluation costs one 128-byte DRAM line (ncu: 4 sectors per
+        # L2 miss at every fetch-granularity setting, profiles/r2_gather_probe_ncu.txt), so the ceiling is the measured copy
+        # bandwidth / 128 B lines per second.  (The library's uniform-random probe over the whole grid, also in this line,
+        # runs BELOW that: its addresses have no page locality at all, the Morton sweep's have some.)
+        bound, peak_loads = "hbm-line", hbm_peak * 1e9 / 128.0
+        peak_src = f"{hbm_src} / 128 B per line = {peak_loads:.4g} lines/s, x 32 B algorithmic"
+    peak = peak_loads * 32.0 / 1e9
+    key = f"{workload} {kind} {n_local}x{n_pts}"
+    traffic, entry = ncu_traffic(key)
+    blk = {
+        "bound": bound, "particles_kind": kind,
+        "kernel": "update = pose_kernel + sweep_kernel (gather, Morton sweep) + ordered_sum_kernel",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": int(n_in) * 32, "in_bounds_evals_per_sec": loads_per_s,
+        "frac_of_hbm_at_32B_per_eval": achieved / hbm_peak, "hbm_peak": hbm_peak, "hbm_peak_source": hbm_src,
+        "traffic": traffic, "traffic_key": key,
+        "update_ms": upd_ms,
+        "note": "achieved = in-bounds evaluations x 32 B / update time (CUDA events on the launch stream); traffic = ncu dram__bytes "
+                "read+write of one update of this workload key (profiles/r2_traffic.json), null if never captured",
+    }
+    if phases is not None:
+        blk["phase_ms"] = {"pose": phases[0], "sweep": phases[1], "ordered_sum": phases[2]}
+    if traffic is not None:
+        blk["dram_gbs"] = traffic / (upd_ms * 1e-3) / 1e9
+        blk["dram_frac_of_hbm"] = blk["dram_gbs"] / hbm_peak
+        blk["traffic_over_algorithmic"] = traffic / (n_in * 32.0)
+    return blk
+
+
+def measure_update(pf, reps=7):
+    t, ph = [], []
+    for _ in range(reps):
+        pf.update()
+        t.append(pf.last_kernel_ms())
+        ph.append(pf.last_phase_ms())
+    k = int(np.argsort(t)[len(t) // 2])
+    return float(t[k]), ph[k]
+
+
+def c1_section(device_index, with_cpu):
+    """BASELINE config 1 (amcl3d_floam.launch:29: 600 particles, 2 k-point cloud, 20 x 20 x 5 m at 0.1 m) through the public
+    synchronous API with host buffers, and the reference's own single-threaded CPU path (amcl3d/CMakeLists.txt:9) beside it."""
+    from amcl3d_test_b200 import Grid3d, ParticleFilter, synth
+
+    extent, resol, n_p, n_pts, radius = WORKLOADS["C1"]
+    sm = synth.make_map(extent, resol)
+    cloud = synth.make_cloud(sm, n_pts, radius)
+    P = synth.make_particles(sm, n_p, "T")
+    u01 = float(synth.resample_offset())
+    g = Grid3d(device_index)
+    g.computePointCloud(sm.points, resol)
+    g.computeGrid(sm.points, 0.05, sub=2)
+    pf = ParticleFilter(g)
+
+    def frame():
+        pf.p_ = P
+        pf.update(cloud)
+        pf.particleNormalize()
+        pf.resample(u01)
+        out = pf.p_
+        return out, pf.getMean()
+
+    for _ in range(20):
+        frame()
+    reps = 200
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        frame()
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    sec = {"workload": f"C1: {n_p} particles x {n_pts} points, map {extent[0]:g}x{extent[1]:g}x{extent[2]:g} m at {resol} m, "
+                       "synchronous calls with host buffers (set particles, update(cloud), particleNormalize, resample, read p_, getMean)",
+           "ms_per_frame": ms, "evals_per_sec": n_p * n_pts / (ms * 1e-3)}
+    if with_cpu:
+        try:
+            setup = cpu_arm_setup("C1", "T")
+            best = None
+            for _ in range(5):
+                r = run_cpu_sample("C1", "T", n_p, 1, setup=setup)
+                tt = r["t_update"] + r["t_resample"]
+                best = tt if best is None else min(best, tt)
+            sec["cpu_reference_1core"] = {"ms_per_frame": best * 1e3, "evals_per_sec": n_p * n_pts / best, "cores": 1,
+                                          "kind": r["kind"], "sample": "the full C1 frame (600 x 2000), best of 5"}
+        except Exception as e:
+            sec["cpu_reference_1core"] = {"error": repr(e)}
+    return sec
+
+
+def c2_section(grid, info, n_map_points, build_ms_list, wall_s, hbm_peak, with_cpu):
+    """BASELINE config 2: the probability-grid build (exact EDT + fused Gaussian + dictionary codes) at 100 x 100 x 20 m, 0.05 m."""
+    cells = info["n_cells"]
+    ms = float(np.median(build_ms_list))
+    # pass structure of the fused build (DESIGN 4): occupancy bits 1/8 B r + x pass 1 B w | y pass 1 B r + 2 B w |
+    # z pass 2 B r + 4 B (float grid) w + 1 B (codes) w  per voxel; the map points are read once (12 B each, twice: classes + voxelize)
+    alg = cells * (0.125 + 1 + 1 + 2 + 2 + 4 + 1) + n_map_points * 12 * 3
+    sec = {"workload": f"C2: grid build {info['size'][0]}x{info['size'][1]}x{info['size'][2]} = {cells} voxels from {n_map_points} map points, "
+                       "EDT + Gaussian + coded copy", "kernels_ms": ms, "voxels_per_sec": cells / (ms * 1e-3),
+           "wall_s_incl_h2d_of_points_and_alloc": wall_s,
+           "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": int(alg),
+                        "note": "11.125 B per voxel over the three passes (see DESIGN 4); duration = CUDA events around the build kernels"}}
+    if with_cpu:
+        try:
+            from amcl3d_test_b200 import synth
+            from oracle import loader as O
+
+            if O.ref_available():
+                crop = synth.make_map((10.0, 10.0, 5.0), 0.05)
+                t0 = time.perf_counter()
+                r = O.ref_compute_grid(crop.points, 0.05, 0.05, which=0)
+                dt = time.perf_counter() - t0
+                vox = int(np.prod(r["size"]))
+                sec["cpu_reference_1core"] = {"voxels_per_sec": vox / dt, "cores": 1, "kind": "reference",
+                                              "sample": f"computeGrid (PointCloudTools.cpp:111-174, kd-tree stand-in) on a 10x10x5 m crop at 0.05 m = {vox} voxels in {dt:.2f} s"}
+        except Exception as e:
+            sec["cpu_reference_1core"] = {"error": repr(e)}
+    return sec
+
+
+def parity_vs_one_gpu(grid, filt, P_all, cloud, u01, beacons, rank):
+    """Before timing at N > 1: every rank replays the whole job on its own GPU through the plain one-GPU handle and
+    compares its slice of the sharded result -- weights after update, resampled indices and particles -- bit for bit."""
+    from amcl3d_test_b200 import ParticleFilter
+
+    lo, hi = filt.lo, filt.hi
+    filt.set_particles(P_all[lo:hi])
+    filt.set_cloud(cloud)
+    filt.update()
+    w_shard = filt.pf.p_[:, 6].copy() if beacons is None else None
+    idx = filt.resample(u01, want_idx=True)
+    out = filt.pf.p_
+    pf = ParticleFilter(grid)
+    pf.p_ = P_all
+    if beacons is not None:
+        pf.update(cloud, beacons=beacons, alpha=0.5, sigma=0.53)
+    else:
+        pf.update(cloud)
+    w_one = pf.p_[lo:hi, 6].copy()
+    pf.particleNormalize()
+    idx_one = pf.resample(u01, want_idx=True)
+    out_one = pf.p_[lo:hi]
+    ok = np.array_equal(idx, idx_one[lo:hi]) and np.array_equal(out.view(np.uint32), out_one.view(np.uint32))
+    if w_shard is not None:
+        ok = ok and np.array_equal(w_shard.view(np.uint32), w_one.view(np.uint32))
+    pf.close()
+    return bool(ok), int((idx != idx_one[lo:hi]).sum())
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
 
     from amcl3d_test_b200 import Grid3d, ParticleFilter, synth
-    from amcl3d_test_b200.sharded import CudaShard, ShardedFilter
+    from amcl3d_test_b200.sharded import PeerShardedFilter
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -312,8 +492,8 @@ def run_b200(args):
     extent, resol, n_per_gpu, n_pts, radius = WORKLOADS[args.workload]
     strong = args.workload in STRONG
     n_total = n_per_gpu if strong else n_per_gpu * world
-    lo = (n_total // world) * rank
     n_local = n_total // world
+    lo = n_local * rank
     assert n_total % world == 0
 
     t_setup = time.time()
@@ -322,37 +502,58 @@ def run_b200(args):
     P_all = synth.make_particles(sm, n_total, args.particles)
     P = np.ascontiguousarray(P_all[lo:lo + n_local])
     u01 = float(synth.resample_offset())
+    beacons = synth.make_beacons(sm, 8) if args.workload in BEACONS else None
 
     grid = Grid3d(local_rank)
     grid.computePointCloud(sm.points, resol)
-    tb = time.time()
-    grid.computeGrid(sm.points, 0.05, sub=2)
-    grid_build_s = time.time() - tb
+    build_ms, build_wall = [], []
+    for _ in range(3 if (world == 1 and args.workload != "C5") else 1):
+        tb = time.time()
+        grid.computeGrid(sm.points, 0.05, sub=2)
+        build_wall.append(time.time() - tb)
+        build_ms.append(grid.last_build_ms())
+    grid_build_s = float(np.min(build_wall))
     info = grid.info()
+    n_map_points = int(sm.points.shape[0])
     del sm.points  # free host memory
+    peaks = gather_peaks(grid) if rank == 0 else None
 
-    shard = CudaShard(grid, n_local, n_total, device)
-    filt = ShardedFilter(shard, n_total)
+    filt = PeerShardedFilter(grid, n_total, device)   # world 1: the same entry points, nothing to exchange
+    if beacons is not None:
+        filt.set_beacons(beacons, 0.5, 0.53)  # alpha, sigma = sensor_range (amcl3d.launch:83, amcl3d_floam.launch:30)
+    parity_n = None
+    if world > 1:
+        ok, bad = parity_vs_one_gpu(grid, filt, P_all, cloud, u01, beacons, rank)
+        t = torch.tensor([1 if ok else 0, bad], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if int(t[0].item()) != world:
+            raise SystemExit(f"sharded result differs from the 1-GPU replay ({int(t[1].item())} resampled indices differ)")
+        parity_n = "bit-identical"
+    del P_all
     backup = torch.from_numpy(P).to(device)
-    shard.set_cloud(cloud)
-    if args.workload in BEACONS:
-        shard.set_beacons(synth.make_beacons(sm, 8), 0.5, 0.53)  # sigma = sensor_range, alpha (amcl3d.launch:83, amcl3d_floam.launch:30)
+    filt.set_cloud(cloud)
     stream = torch.cuda.current_stream(device)
 
-    def step():
-        shard.local.copy_(backup)       # same workload every step (resampling collapses the set)
+    # in-bounds count of this workload (for the roofline's algorithmic bytes) and the update on its own
+    filt.set_particles_device(backup)
+    n_in = filt.pf.update(count=True) if beacons is None else None
+    if n_in is None:
+        probe = ParticleFilter(grid)
+        probe.p_ = P
+        probe.set_cloud(cloud)
+        n_in = probe.update(count=True)
+        probe.close()
+
+    def step_sync():
+        filt.set_particles_device(backup)   # same workload every step (resampling collapses the set)
         filt.update()
         filt.resample(u01)
         return filt.mean()
 
-    # in-bounds count of this workload (for the roofline's algorithmic bytes)
-    shard.local.copy_(backup)
-    n_in = shard.pf_local.update(count=True)
-    upd_ms = []
-    step()                              # once through the synchronous calls (allocations, NCCL set-up)
-    shard.set_async(True)               # warm-up = exactly the calls of the timed loop
+    step_sync()                         # once through the synchronous calls (allocations)
+    filt.set_async(True)                # warm-up = exactly the calls of the timed loop
     for _ in range(args.warmup):
-        shard.local.copy_(backup)
+        filt.set_particles_device(backup)
         filt.update()
         filt.resample(u01)
         filt.mean_device()
@@ -361,44 +562,31 @@ def run_b200(args):
         dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = shard.launch_count()
+    l0 = filt.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # the resident loop runs in stream order (amcl3d_b200_pf_set_async): no host wait between the stages of a step or
     # between steps; the update's share is taken from event pairs recorded on the same stream, read after the loop
     ev_u = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    shard.set_async(True)
-    dbg = os.environ.get("AMCL3D_BENCH_DEBUG") == "1"
-    ev_d = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)] if dbg else []
     torch.cuda.synchronize()
     e0.record(stream)
     for k in range(args.steps):
-        shard.local.copy_(backup)
+        filt.set_particles_device(backup)
         ev_u[k][0].record(stream)
         filt.update()
         ev_u[k][1].record(stream)
         filt.resample(u01)
-        if dbg:
-            ev_d[k][0].record(stream)
         mean_dev = filt.mean_device()
-        if dbg:
-            ev_d[k][1].record(stream)
     e1.record(stream)
     torch.cuda.synchronize()
-    shard.set_async(False)
+    filt.pf.sync()                      # reports a peer that never arrived
+    filt.set_async(False)
     upd_ms = [a.elapsed_time(b) for a, b in ev_u]
-    if dbg:
-        res = [ev_u[k][1].elapsed_time(ev_d[k][0]) for k in range(args.steps)]
-        mea = [a.elapsed_time(b) for a, b in ev_d]
-        gap = [ev_d[k][1].elapsed_time(ev_u[k + 1][0]) for k in range(args.steps - 1)]
-        print(f"[rank {rank}] total {e0.elapsed_time(e1) / args.steps:.3f} update {np.mean(upd_ms):.3f} resample {np.mean(res):.3f} "
-              f"(max {np.max(res):.3f}) mean {np.mean(mea):.3f} (max {np.max(mea):.3f}) copy+gap {np.mean(gap):.3f} (max {np.max(gap):.3f})",
-              file=sys.stderr, flush=True)
     mean_host = mean_dev.cpu().numpy()
     assert np.all(np.isfinite(mean_host))
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
-    launches = shard.launch_count() - l0
+    launches = filt.launch_count() - l0
     ms_total = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms_total], device=device)
@@ -412,32 +600,17 @@ def run_b200(args):
     pin_p = torch.from_numpy(P).pin_memory()
     pin_c = torch.from_numpy(cloud).pin_memory()
     pin_out = torch.empty((n_local, 7), dtype=torch.float32).pin_memory()
-    pf = ParticleFilter(grid)
-    pf.set_stream(stream.cuda_stream)
-
     out_view = pin_out.numpy()
 
-    if world == 1:
-        def e2e_step():
-            pf.p_ = pin_p.numpy()               # H2D particles
-            if args.workload in BEACONS:
-                pf.update(pin_c.numpy(), beacons=shard.beacons, alpha=0.5, sigma=0.53)
-            else:
-                pf.update(pin_c.numpy())        # H2D cloud + K3
-            pf.particleNormalize()
-            pf.resample(u01)
-            pf.read_particles(out_view)         # D2H resampled set, straight into the pinned buffer
-            return pf.getMean()                 # D2H 7 floats
-    else:
-        # the same job as the device-timed loop (global normalise + resample across ranks), but every step moves this
-        # rank's particle block and the cloud H2D and its slice of the resampled set + the mean D2H, call by call
-        def e2e_step():
-            shard.local.copy_(pin_p)            # H2D this rank's block
-            shard.set_cloud(pin_c.numpy())      # H2D cloud (+ Morton sort)
-            filt.update()
-            filt.resample(u01)                  # all-gather, replicated exact chains, own output slice
-            pin_out.copy_(shard.local)          # D2H this rank's slice of the resampled set
-            return filt.mean()                  # D2H 7 floats (all-reduced)
+    def e2e_step():
+        # the synchronous call-by-call semantics of the reference: this rank's particle block and the cloud go H2D, the
+        # rank's slice of the resampled set and the mean come back D2H, every step
+        filt.set_particles(pin_p.numpy())       # H2D particles
+        filt.set_cloud(pin_c.numpy())           # H2D cloud (+ Morton sort)
+        filt.update()
+        filt.resample(u01)                      # global particleNormalize + resample (peer exchange at N > 1)
+        filt.pf.read_particles(out_view)        # D2H resampled slice, straight into the pinned buffer
+        return filt.mean()                      # D2H 7 floats
 
     for _ in range(max(1, args.warmup)):
         e2e_step()
@@ -445,10 +618,8 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    e0.record(stream)
     for _ in range(args.steps):
         e2e_step()
-    e1.record(stream)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     if world > 1:
@@ -459,31 +630,40 @@ def run_b200(args):
     h2d = int(pin_p.numel() * 4 + pin_c.numel() * 4)
     d2h = int(pin_out.numel() * 4 + 28)
 
-    # ---- secondary: the other particle distribution of SURVEY 8(d) on the same grid (update only, not the headline) ----
-    other = None
-    if world == 1:
-        kind2 = "G" if args.particles == "T" else "T"
-        P2 = synth.make_particles(sm, n_local, kind2)
-        pf.p_ = P2
+    # ---- the update on its own, both particle distributions of SURVEY 8(d) (N = 1) ------------------------------
+    blocks = {}
+    hbm_peak, hbm_src = measured_peaks()
+    if world == 1 and args.workload not in ("C5",):
+        pf = ParticleFilter(grid)
         pf.set_cloud(cloud)
-        n_in2 = pf.update(count=True)
-        t2 = []
-        for _ in range(5):
-            pf.update()
-            t2.append(pf.last_kernel_ms())
-        u2 = float(np.median(t2))
-        other = {"particles_kind": kind2, "update_ms": u2, "update_evals_per_sec": n_local * n_pts / (u2 * 1e-3),
-                 "in_bounds_fraction": n_in2 / (n_local * n_pts),
-                 "roofline_frac": n_in2 * 32.0 / (u2 * 1e-3) / 1e9 / measured_peaks()[0]}
+        for kind in ("T", "G"):
+            Pk = P if kind == args.particles else synth.make_particles(sm, n_local, kind)
+            pf.p_ = Pk
+            n_in_k = pf.update(count=True)
+            u_ms, phases = measure_update(pf)
+            blocks[kind] = roofline_block(kind, args.workload, n_local, n_pts, n_in_k, u_ms, phases, peaks, hbm_peak, hbm_src)
+            blocks[kind]["update_evals_per_sec"] = n_local * n_pts / (u_ms * 1e-3)
+            blocks[kind]["in_bounds_fraction"] = n_in_k / (n_local * n_pts)
+        pf.close()
+
+    cpp = None
+    if world == 1 and beacons is None:
+        try:
+            cpp = cpp_class_e2e(grid, P, cloud, max(3, min(args.steps, 20)))
+        except Exception as e:
+            cpp = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_peaks()
     upd = float(np.mean(upd_ms))
-    achieved = n_in * 32.0 / (upd * 1e-3) / 1e9
+    if blocks:
+        roof = dict(blocks[args.particles])
+        roof["update_ms_in_step"] = upd
+    else:
+        roof = roofline_block(args.particles, args.workload, n_local, n_pts, n_in, upd, None, peaks, hbm_peak, hbm_src)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
@@ -491,28 +671,43 @@ def run_b200(args):
         "config": {
             "workload": f"{args.workload}: {n_local} particles/GPU x {n_pts}-point cloud, map {extent[0]:g}x{extent[1]:g}x{extent[2]:g} m "
                         f"at {resol} m = {info['size'][0]}x{info['size'][1]}x{info['size'][2]} voxels "
-                        f"({info['n_cells']*4/1e9:.2f} GB grid replica per GPU), step = update + normalise + resample + mean",
+                        f"({info['n_cells']*4/1e9:.2f} GB float grid, {info['coded_bytes']/1e9:.2f} GB coded replica per GPU), "
+                        "step = update + normalise + resample + mean"
+                        + (" with 8 UWB range beacons fused" if beacons is not None else ""),
             "particles_kind": args.particles, "particles_total": n_total, "points": n_pts,
             "l2": "inputs larger than L2 (grid replica >> 126 MB), no flush",
             "in_bounds_fraction": n_in / (n_local * n_pts),
             "grid_build_s_incl_h2d": grid_build_s,
+            "exchange": "none (1 GPU)" if world == 1 else "peer-memory stores/loads over NVLink in the library's own kernels (csrc/shard.cu), no NCCL on the data path",
         },
         "update_ms": upd, "resample_mean_ms": ms_step - upd,
         "update_evals_per_sec": n_local * n_pts / (upd * 1e-3) * world,
-        "roofline": {
-            "bound": "hbm", "kernel": "update = update_kernel<code8,stage> (phase 1 gather) + ordered_sum_kernel (phase 2)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": ncu_traffic(args.workload, args.particles, n_local, n_pts), "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": n_in * 32,
-            "note": "32 B sector per in-bounds particle x point evaluation (SURVEY 8(d)); duration = CUDA events around the kernel on its launch stream",
-        },
+        "roofline": roof,
+        "gather_peaks_loads_per_sec": peaks,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": wall / args.steps * 1e3},
         "gpu_launches": int(launches),
         "setup_s": time.time() - t_setup,
     }
-    if other is not None:
-        line["secondary"] = other
+    if parity_n is not None:
+        line["parity_n"] = parity_n
+    if cpp is not None:
+        line["e2e_cpp_class"] = cpp
+    other_kind = "G" if args.particles == "T" else "T"
+    if other_kind in blocks:
+        line["roofline_" + other_kind] = blocks[other_kind]
+        line["secondary"] = {"particles_kind": other_kind, "update_ms": blocks[other_kind]["update_ms"],
+                             "update_evals_per_sec": blocks[other_kind]["update_evals_per_sec"],
+                             "in_bounds_fraction": blocks[other_kind]["in_bounds_fraction"],
+                             "roofline_frac": blocks[other_kind]["frac"]}
+    if world == 1 and args.workload == "C3":
+        with_cpu = not args.no_cpu_baseline
+        try:
+            line["configs"] = {"C2": c2_section(grid, info, n_map_points, build_ms, grid_build_s, hbm_peak, with_cpu),
+                               "C1": c1_section(local_rank, with_cpu)}
+        except Exception as e:
+            line["configs"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(args.workload, args.particles, args.cpu_seconds)
@@ -523,8 +718,42 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def cpp_class_e2e(grid, P, cloud, steps):
+    """The same frame through the reference-compatible C++ class (amcl3d::ParticleFilter of include/amcl3d, the class
+    amcl3d.cpp would call): host p_ vector written, update(cloud) / particleNormalize / resample / getMean, p_ read back."""
+    import ctypes as C
+
+    from amcl3d_test_b200 import build
+
+    lib = C.CDLL(str(build.HOST_LIB))
+    fn = lib.amcl3d_host_bench_frames
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p,
+                   C.c_void_p, C.c_int, C.c_void_p]
+    Pc = np.ascontiguousarray(P, np.float32)
+    cl = np.ascontiguousarray(cloud[:, :3], np.float32)
+    ms = C.c_double(0)
+    mean = np.zeros(7, np.float32)
+    moved = np.zeros(2, np.uint64)
+    rc = fn(grid._h, Pc.ctypes.data, Pc.shape[0], cl.ctypes.data, cl.shape[0], steps, 2, C.byref(ms), mean.ctypes.data, None, 0,
+            moved.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"amcl3d_host_bench_frames rc={rc}")
+    n = Pc.shape[0] * cl.shape[0]
+    return {"value": n / (ms.value * 1e-3), "unit": UNIT, "ms_per_step": ms.value,
+            "h2d_bytes_per_step": int(Pc.nbytes + cl.shape[0] * 16), "d2h_bytes_per_step": int(Pc.nbytes + 28),
+            "set_uploads_per_step": float(moved[0]) / steps, "set_downloads_per_step": float(moved[1]) / steps,
+            "what": "amcl3d::ParticleFilter (C++ class, pageable std::vector p_): p_ = particles; update(cloud); particleNormalize(); "
+                    "resample(); getMean(); read p_ -- lazily synced host mirror: one H2D and one D2H of the set per frame"}
+
+
 def main():
     args = parse()
+    # the contract is ONE JSON line on stdout: everything else that writes to fd 1 (the compiled reference's own
+    # std::cout progress lines, library banners) is sent to stderr, and print() gets the real stdout back through sys.stdout
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_out, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:

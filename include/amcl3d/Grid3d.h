@@ -20,6 +20,8 @@ public:
   explicit Grid3d(VSCOMMON::LoggerPtr& log, int device = 0);
   /*! Upstream (fada-catec) default construction, used by the reference's stale tests. */
   explicit Grid3d(int device = 0);
+  /*! A view of a grid that lives behind an existing C-ABI handle (not owned, not destroyed): resident / benchmark callers. */
+  explicit Grid3d(amcl3d_b200_grid_t borrowed);
   virtual ~Grid3d();
   Grid3d(const Grid3d&) = delete;
   Grid3d& operator=(const Grid3d&) = delete;
@@ -55,6 +57,8 @@ public:
 
   /*! The C-ABI handle, for resident / multi-GPU callers. */
   amcl3d_b200_grid_t handle() const { return handle_; }
+  /*! Bumped whenever the cells change (open / load / build): replicas on other devices are rebuilt when it moves. */
+  uint64_t generation() const { return generation_; }
 
   PointCloudInfo::Ptr pc_info_;
   Grid3dInfo::Ptr grid_info_;
@@ -63,6 +67,8 @@ public:
 private:
   void refreshInfo();
   amcl3d_b200_grid_t handle_{ nullptr };
+  bool owns_{ true };
+  uint64_t generation_{ 0 };
   VSCOMMON::LoggerPtr g_log;
 };
 

@@ -4,10 +4,17 @@
 //   relocPose (and the upstream name init) / predict / update / particleNormalize / resample /
 //   uniformSample / getMean / getBestParticle / setParticleNum / isInitialized,
 //   public p_, mean_, grid3d_, localization_params_, max_resamp_num_, min_resamp_num_.
-// update / normalise / resample / mean run as CUDA kernels behind include/amcl3d_b200.h; p_ is the host
-// mirror: it is uploaded before and downloaded after every device step, so callers may keep editing it
-// between calls exactly as they do with the reference.  Host RNG (std::mt19937) as in the reference;
-// setSeed() makes runs reproducible (the reference seeds from std::random_device).
+// update / normalise / resample / mean run as CUDA kernels behind include/amcl3d_b200.h.  p_ is a LAZILY SYNCED host
+// mirror (ParticleMirror below: the std::vector surface callers use -- size, [], iteration, assignment, conversion to
+// const std::vector<Particle>&): the particle set stays in HBM between device steps and crosses PCIe only when the
+// host really looks at it (one D2H) or has edited it (one H2D before the next device step), so
+// predict -> update -> particleNormalize -> resample -> getMean moves the set at most once each way.
+// Callers may keep reading and editing p_ between calls exactly as they do with the reference.
+// setDevices({0,1,...}) (or AMCL3D_B200_DEVICES=0,1,...) shards the particles over several GPUs of one NVLink box:
+// the grid is replicated, predict / update / particleNormalize / resample / getMean run sharded with the exchange in
+// the library's own peer-memory kernels (csrc/shard.cu), bit-identical to one GPU; every other step runs on the
+// first device.  Host RNG (std::mt19937) as in the reference; setSeed() makes runs reproducible (the reference seeds
+// from std::random_device).
 #pragma once
 
 #include <random>
@@ -36,6 +43,104 @@ struct Particle
 };
 static_assert(sizeof(Particle) == 28, "Particle must stay 7 packed floats (C-ABI layout)");
 
+class ParticleFilter;
+
+/*! p_: the std::vector<Particle> surface of the reference over a particle set that lives on the device(s).
+ *  Reading (const access, conversion to const std::vector<Particle>&, size()) pulls the set to the host once if a device
+ *  step changed it; any non-const access additionally marks the device copy stale, so the next device step uploads. */
+class ParticleMirror
+{
+public:
+  typedef Particle value_type;
+  typedef std::vector<Particle>::iterator iterator;
+  typedef std::vector<Particle>::const_iterator const_iterator;
+
+  size_t size() const { return host_fresh_ ? host_.size() : dev_n_; }
+  bool empty() const { return size() == 0; }
+  const Particle& operator[](size_t i) const { return host()[i]; }
+  Particle& operator[](size_t i) { return edit()[i]; }
+  const Particle& at(size_t i) const { return host().at(i); }
+  Particle& at(size_t i) { return edit().at(i); }
+  const Particle& front() const { return host().front(); }
+  const Particle& back() const { return host().back(); }
+  Particle& front() { return edit().front(); }
+  Particle& back() { return edit().back(); }
+  const Particle* data() const { return host().data(); }
+  Particle* data() { return edit().data(); }
+  const_iterator begin() const { return host().begin(); }
+  const_iterator end() const { return host().end(); }
+  const_iterator cbegin() const { return host().begin(); }
+  const_iterator cend() const { return host().end(); }
+  iterator begin() { return edit().begin(); }
+  iterator end() { return edit().end(); }
+  operator const std::vector<Particle>&() const { return host(); }
+
+  // whole-set replacement: nothing is pulled from the device first
+  ParticleMirror& operator=(const std::vector<Particle>& v)
+  {
+    host_ = v;
+    replaced();
+    return *this;
+  }
+  ParticleMirror& operator=(std::vector<Particle>&& v)
+  {
+    host_ = std::move(v);
+    replaced();
+    return *this;
+  }
+  void assign(size_t n, const Particle& v)
+  {
+    host_.assign(n, v);
+    replaced();
+  }
+  template <class It>
+  void assign(It first, It last)
+  {
+    host_.assign(first, last);
+    replaced();
+  }
+  void clear()
+  {
+    host_.clear();
+    replaced();
+  }
+  void swap(std::vector<Particle>& v)
+  {
+    edit().swap(v);
+  }
+  void resize(size_t n) { edit().resize(n); }
+  void resize(size_t n, const Particle& v) { edit().resize(n, v); }
+  void reserve(size_t n) { host_.reserve(n); }
+  void push_back(const Particle& v) { edit().push_back(v); }
+
+  /*! Read-only view, pulled from the device if a device step changed the set since the last look. */
+  const std::vector<Particle>& host() const;
+  /*! Editable view: as host(), and the device copy becomes stale. */
+  std::vector<Particle>& edit()
+  {
+    host();
+    dev_fresh_ = false;
+    return host_;
+  }
+  /*! Number of host<->device transfers of the whole set so far (tests / benchmarks). */
+  uint64_t uploads() const { return uploads_; }
+  uint64_t downloads() const { return downloads_; }
+
+private:
+  friend class ParticleFilter;
+  void replaced()
+  {
+    host_fresh_ = true;
+    dev_fresh_ = false;
+  }
+  mutable std::vector<Particle> host_;
+  mutable bool host_fresh_{ true };  // host_ holds the current set
+  bool dev_fresh_{ false };          // the device(s) hold the current set
+  size_t dev_n_{ 0 };
+  const ParticleFilter* owner_{ nullptr };
+  mutable uint64_t uploads_{ 0 }, downloads_{ 0 };
+};
+
 /*! Reference: ParticleFilter.h:50-99 (defaults as compiled there; init_pitch_dev_(0,2) evaluates to 2). */
 struct LocalizationParam
 {
@@ -56,6 +161,8 @@ class ParticleFilter
 public:
   explicit ParticleFilter(VSCOMMON::LoggerPtr& log, int device = 0);
   explicit ParticleFilter(int device = 0);
+  /*! On a grid that lives behind an existing C-ABI handle (borrowed, not destroyed): resident / benchmark callers. */
+  explicit ParticleFilter(amcl3d_b200_grid_t borrowed_grid);
   virtual ~ParticleFilter();
   ParticleFilter(const ParticleFilter&) = delete;
   ParticleFilter& operator=(const ParticleFilter&) = delete;
@@ -106,20 +213,38 @@ public:
   float lastResampleDraw() const { return last_u01_; }
   /*! Device time of the kernels of the last device step, ms. */
   float lastKernelMs() const;
-  amcl3d_b200_pf_t handle() const { return handle_; }
+  /*! The C-ABI handle of the first device, holding the current set (uploads p_ first if the host edited it). */
+  amcl3d_b200_pf_t handle();
+
+  /*! Shards the particles over these CUDA devices of one box (grid replicated, see the header comment); one device =
+   *  the plain path.  Also read from AMCL3D_B200_DEVICES at construction.  The first device must be grid3d_'s. */
+  void setDevices(const std::vector<int>& devices);
+  const std::vector<int>& devices() const { return devices_; }
 
 public:
-  std::vector<Particle> p_;
+  ParticleMirror p_;
   Particle mean_;
   Grid3d* grid3d_;
   LocalizationParam localization_params_;
   int max_resamp_num_{ 800 }, min_resamp_num_{ 150 };
 
 private:
+protected:
+  /*! Before a device step on the first device's handle: the current set is there (uploaded / gathered if need be). */
+  void syncDevice();
+  /*! After a device step on the first device's handle that changed the set (n = its new size). */
+  void deviceChanged();
+
+private:
+  friend class ParticleMirror;
   float ranGaussian(const double mean, const double sigma);
   float rngUniform(const float range_from, const float range_to);
-  void upload();
-  void download();
+  void pull(std::vector<Particle>& out) const;  // device(s) -> host
+  bool sharded() const { return devices_.size() > 1; }
+  void syncShards();     // the current set is spread over the shard handles
+  void shardsChanged();  // a sharded device step changed the set
+  void dropShards();
+  void setCloudAll(const pcl::PointCloud<PointType>::Ptr& cloud);
 
   bool initialized_{ false };
   std::random_device rd_;
@@ -127,6 +252,13 @@ private:
   VSCOMMON::LoggerPtr g_log;
   amcl3d_b200_pf_t handle_{ nullptr };
   float last_u01_{ 0.f };
+  // multi-GPU: rank r = shard_[r] on devices_[r]; replicas_[r] (r >= 1) are clones of grid3d_'s cells
+  std::vector<int> devices_;
+  std::vector<amcl3d_b200_pf_t> shard_;
+  std::vector<amcl3d_b200_grid_t> replicas_;
+  uint64_t shard_n_{ 0 }, replica_generation_{ 0 };
+  enum Where { kNowhere, kSingle, kSharded };
+  Where where_{ kNowhere };  // which device-side home holds the set when p_.dev_fresh_
 };
 
 }  // namespace amcl3d

@@ -111,9 +111,11 @@ int amcl3d_b200_grid_compute_bounds(amcl3d_b200_grid_t g, const float* xyz, uint
 int amcl3d_b200_grid_set_map(amcl3d_b200_grid_t g, const double min[3], const double max[3], double resol);
 
 /* computeGrid / computeGrid2 (PointCloudTools.cpp:111-174 / 176-254) on the device.  QUIRK/GAUSSIAN:
- * exact Euclidean distance transform on the lattice of pitch resol/sub (sub = 1 or 2; map points are
- * snapped to it, bit-exact with the kd-tree build when they already lie on it) followed by the fused
- * Gaussian writer.  SPLAT takes arbitrary points.  keep_edt != 0 keeps the int32 squared distances
+ * exact Euclidean distance transform on the lattice of pitch resol/sub (sub = 1 or 2) followed by the fused
+ * Gaussian writer.  Map points are SNAPPED to that lattice first: the result is bit-exact with the reference's
+ * kd-tree build when the points already lie on it (maps made of voxel centres / corners), and for arbitrary clouds the
+ * nearest-point distance of a voxel differs from the reference's by at most sqrt(3)/2 * resol/sub (0.43 resol at
+ * sub = 2), the field accordingly (tests/test_gpu_grid.py::test_off_lattice_map_points_stay_within_the_stated_snap_bound).  SPLAT takes arbitrary points.  keep_edt != 0 keeps the int32 squared distances
  * (units (resol/sub)^2) for amcl3d_b200_grid_download_edt and runs the exact lower-envelope passes; without it
  * the y / z passes only search the window beyond which the probability is exactly 0.0f (min(d2, cap)) -- the
  * float grid is the same, bit for bit (environment AMCL3D_B200_EDT_FAST=0 forces the exact passes). */
@@ -129,6 +131,11 @@ int amcl3d_b200_grid_download_edt(amcl3d_b200_grid_t g, int32_t* d2, uint64_t ca
 /* per grid handle: 1 (default) capped passes when the EDT is not kept, 0 the exact envelope passes always (the float
  * grid is the same bit for bit; A/B switch).  Environment AMCL3D_B200_EDT_FAST=0 sets the default for new handles. */
 int amcl3d_b200_grid_set_edt_fast(amcl3d_b200_grid_t g, int enable);
+
+/* Replica of a built / loaded grid on another device of the same box: the grid is replicated, the particles are
+ * sharded.  Peer copy of the coded cells (what update() reads); the linear float cells travel only with
+ * with_float != 0 or when the grid has no codes (download / save of a codes-only replica fail with ERR_STATE). */
+int amcl3d_b200_grid_clone(amcl3d_b200_grid_t src, int device, int with_float, amcl3d_b200_grid_t* out);
 
 /* loadGrid's payload (Grid3d.cpp:404-442): cells + sizes + sensor_dev from host memory */
 int amcl3d_b200_grid_upload(amcl3d_b200_grid_t g, const float* prob, const uint32_t size[3], double sensor_dev);
@@ -284,10 +291,15 @@ int amcl3d_b200_pf_shard_ipc_handle(amcl3d_b200_pf_t pf, void* handle64, size_t 
 int amcl3d_b200_pf_shard_attach_ipc(amcl3d_b200_pf_t pf, const void* handles, size_t stride);
 /* all ranks are handles of this process (pfs[r] = rank r): enables peer access between their devices */
 int amcl3d_b200_pf_shard_attach_local(amcl3d_b200_pf_t* pfs, int world);
-/* global particleNormalize + resample(r = u01 / N); p_ becomes this rank's slice [lo, hi) of the resampled set.
- * d_wr_local (optional, DEVICE, hi - lo floats): raw range-beacon weights of update_split, fused with alpha over the
- * global sums before normalising (row R).  idx (optional, HOST, hi - lo ints): global source indices. */
-int amcl3d_b200_pf_shard_resample(amcl3d_b200_pf_t pf, float u01, const void* d_wr_local, float alpha, int32_t* idx);
+/* global particleNormalize (ParticleFilter.cpp:168-196): the weight sum runs over all ranks' particles, the rank's own
+ * block is normalised in place (p_ keeps its particles).  wtp (optional, HOST) receives the global sum. */
+int amcl3d_b200_pf_shard_normalize(amcl3d_b200_pf_t pf, float* wtp);
+/* global resample(r = u01 / N) (ParticleFilter.cpp:230-254); p_ becomes this rank's slice [lo, hi) of the resampled set.
+ * normalize != 0: particleNormalize first, inside the same exchange (the fused call of a frame); 0: the weights are
+ * taken as they are (the caller ran shard_normalize, like `particleNormalize(); resample();` of the reference).
+ * d_wr_local (optional, DEVICE, hi - lo floats, needs normalize != 0): raw range-beacon weights of update_split, fused
+ * with alpha over the global sums before normalising (row R).  idx (optional, HOST, hi - lo ints): global source indices. */
+int amcl3d_b200_pf_shard_resample(amcl3d_b200_pf_t pf, float u01, int normalize, const void* d_wr_local, float alpha, int32_t* idx);
 /* getMean over all ranks (partial sums exchanged through peer memory, combined in rank order in f64); out7 (HOST) and /
  * or d_out7 (DEVICE), at least one */
 int amcl3d_b200_pf_shard_mean(amcl3d_b200_pf_t pf, float out7[7], void* d_out7);
@@ -295,7 +307,9 @@ int amcl3d_b200_pf_shard_mean(amcl3d_b200_pf_t pf, float out7[7], void* d_out7);
 /* the two collective calls for ranks that are handles of ONE process (attach_local): issued on every handle in stream
  * order, then waited for (a synchronous call on one handle would wait for peers that were not launched yet).
  * d_wr_local: NULL or `world` DEVICE pointers (rank r's raw range weights). */
-int amcl3d_b200_pf_shard_resample_local(amcl3d_b200_pf_t* pfs, int world, float u01, const void* const* d_wr_local, float alpha);
+int amcl3d_b200_pf_shard_normalize_local(amcl3d_b200_pf_t* pfs, int world);
+int amcl3d_b200_pf_shard_resample_local(amcl3d_b200_pf_t* pfs, int world, float u01, int normalize, const void* const* d_wr_local,
+                                        float alpha);
 int amcl3d_b200_pf_shard_mean_local(amcl3d_b200_pf_t* pfs, int world, float out7[7]);
 
 /* sequential f32 inclusive prefix of the current weights (ParticleFilter.cpp:259-264), for tests and

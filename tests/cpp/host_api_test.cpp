@@ -304,6 +304,52 @@ int main(int argc, char** argv)
     mcl.updateDownsampled();
     dump_particles("mcl_after_update_ds", mcl.p_);
   }
+  // lazily synced host mirror: one frame of the reference's call sequence moves the set once each way
+  {
+    pf.p_ = P;
+    const uint64_t up0 = pf.p_.uploads(), down0 = pf.p_.downloads();
+    pf.update(cloud);
+    pf.particleNormalize();
+    pf.setSeed(seed);
+    pf.resample();
+    Particle mm = pf.getMean();
+    (void)mm;
+    const float before_read[2] = { (float)(pf.p_.uploads() - up0), (float)(pf.p_.downloads() - down0) };
+    dump("lazy_before_read", before_read, 1, 2);
+    dump_particles("lazy_after_frame", pf.p_);  // the host looks: one download
+    const float after_read[2] = { (float)(pf.p_.uploads() - up0), (float)(pf.p_.downloads() - down0) };
+    dump("lazy_after_read", after_read, 1, 2);
+    pf.p_[0].w = pf.p_[0].w;  // a host edit: the next device step uploads again
+    pf.getMean();
+    const float after_edit[2] = { (float)(pf.p_.uploads() - up0), (float)(pf.p_.downloads() - down0) };
+    dump("lazy_after_edit", after_edit, 1, 2);
+  }
+  // particles sharded over two devices behind the same class (skipped on a one-GPU box)
+  {
+    int ndev = 0;
+    amcl3d_b200_device_info(0, &ndev, nullptr, nullptr, nullptr, nullptr, nullptr);
+    dump_scalar("md_devices", (float)ndev);
+    if (ndev >= 2)
+    {
+      pf.setDevices({ 0, 1 });
+      pf.p_ = P;
+      pf.update(cloud);
+      dump_particles("md_after_update", pf.p_);
+      pf.particleNormalize();
+      dump_particles("md_after_normalize", pf.p_);
+      Particle mm = pf.getMean();
+      dump("md_mean", &mm.x, 1, 7);
+      pf.setSeed(seed);
+      pf.resample();
+      dump_particles("md_after_resample", pf.p_);
+      // a step that only exists on one device brings the set home and carries on
+      pf.p_ = weighted;
+      int S2 = sample_num;
+      pf.uniformSample(S2);
+      dump_particles("md_after_uniform_sample", pf.p_);
+      pf.setDevices({ 0 });
+    }
+  }
   g_out.close();
   std::printf("host_api_test ok\n");
   return 0;

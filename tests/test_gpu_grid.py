@@ -218,3 +218,44 @@ def test_fused_build_gaussian_and_wider_windows(O):
         exact = g.downloadGrid()
         g.computeGrid(pts, sigma, mode=mode, sub=2)
         assert np.array_equal(bits(g.downloadGrid()), bits(exact)), (sigma, mode)
+
+
+def test_off_lattice_map_points_stay_within_the_stated_snap_bound(O):
+    """computeGrid on the device is an exact EDT on the lattice of pitch resol/sub: map points that do not lie on it are
+    snapped first (include/amcl3d_b200.h).  The reference queries a kd-tree with the true float positions
+    (PointCloudTools.cpp:152-162).  For arbitrary clouds the two therefore differ, by a bounded amount: a point moves by at
+    most half a lattice pitch per axis, so the nearest-point DISTANCE of every voxel is off by at most
+    sqrt(3)/2 * resol/sub, and the field -- monotone in the distance -- lies between the reference's values at
+    d - bound and d + bound.  Both bounds are asserted against the compiled reference computeGrid run on the true points."""
+    from amcl3d_test_b200 import Grid3d
+
+    resol, sub, sigma = 0.1, 2, 0.05
+    rng = np.random.RandomState(17)
+    extent = np.array([3.0, 2.4, 1.6])
+    pts = np.concatenate([[[0, 0, 0], list(extent)], rng.uniform(0, 1, (350, 3)) * extent]).astype(np.float32)
+    g = Grid3d(0)
+    mn, mx = g.computePointCloud(pts, resol)
+    g.computeGrid(pts, sigma, sub=sub, keep_edt=True)
+    size = np.array(g.info()["size"])
+    d_edt = np.sqrt(g.edt().astype(np.float64)) * (resol / sub)
+    # true nearest-point distance of every voxel corner (brute force, f64)
+    ax = [mn[a] + np.arange(size[a]) * resol for a in range(3)]
+    Z, Y, X = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
+    q = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1)
+    d_true = np.full(q.shape[0], np.inf)
+    for p in pts.astype(np.float64):
+        d_true = np.minimum(d_true, np.sqrt(((q - p) ** 2).sum(1)))
+    bound = np.sqrt(3.0) / 2.0 * resol / sub
+    assert np.abs(d_edt - d_true).max() <= bound * (1 + 1e-6)
+    assert np.abs(d_edt - d_true).max() > 0.1 * bound  # the cloud really is off the lattice
+    # the field against the reference's own computeGrid (compiled from /root/reference here; oracle port elsewhere)
+    m = O.Map(mn, mx, resol, sigma)
+    ref = O.ref_compute_grid(pts, resol, sigma, which=0)["prob"] if O.ref_available() else O.compute_grid_nn(m, pts, O.GRID_QUIRK)
+    c1 = 1.0 / (sigma * np.sqrt(2 * np.pi))
+    c2 = 1.0 / (2 * sigma * sigma)
+    f = lambda d: c1 * np.exp(-np.minimum((d * d) ** 2 * c2, 700.0))  # the d^4 quirk: dist is already squared  # noqa: E731
+    got = g.downloadGrid().astype(np.float64)
+    hi = f(np.maximum(d_true - bound, 0.0)) * (1 + 1e-4) + 1e-30
+    lo = f(d_true + bound) * (1 - 1e-4) - 1e-30
+    assert np.all(got <= hi) and np.all(got >= lo)
+    assert np.allclose(ref, f(d_true), rtol=1e-4, atol=1e-30)  # and the reference is what the bound is centred on

@@ -139,6 +139,19 @@ def test_cpp_classes_match_the_oracle(O, tmp_path):
     ds = O.voxel_filter(raw, 0.3, ioff=3)
     assert np.array_equal(bits(d["mcl_cloud_ds"]), bits(ds))
     assert np.array_equal(bits(d["mcl_after_update_ds"][:, 6]), bits(O.update(m, O.particles(P), ds[:, :3].copy())[:, 6]))
+    # lazily synced host mirror: update -> particleNormalize -> resample -> getMean costs ONE upload and no
+    # download until the host looks at p_; a host edit makes the next device step upload again
+    assert list(d["lazy_before_read"][0]) == [1, 0]
+    assert list(d["lazy_after_read"][0]) == [1, 1]
+    assert list(d["lazy_after_edit"][0]) == [2, 1]
+    assert np.array_equal(bits(d["lazy_after_frame"]), bits(d["after_resample"]))
+    # the same class sharded over two devices (amcl3d::ParticleFilter::setDevices): bit-identical to one device
+    if d["md_devices"][0, 0] >= 2:
+        assert np.array_equal(bits(d["md_after_update"]), bits(d["after_update"]))
+        assert np.array_equal(bits(d["md_after_normalize"]), bits(d["after_normalize"]))
+        assert np.array_equal(bits(d["md_after_resample"]), bits(d["after_resample"]))
+        assert np.array_equal(bits(d["md_after_uniform_sample"]), bits(d["after_uniform_sample"]))
+        assert np.allclose(d["md_mean"][0, :6], d["mean"][0, :6], rtol=1e-5, atol=1e-6)
     # free-function builders
     ref2 = O.compute_grid2(m, sm.points)
     assert np.allclose(d["free_compute_grid2"].reshape(-1), ref2, rtol=1e-6, atol=1e-30)

@@ -468,6 +468,12 @@ class ParticleFilter:
                                                     float(alpha), idx.ctypes.data if want_idx else None))
         return idx
 
+    def shard_resample_fast(self, u01, want_idx=False):
+        """The NON-exact sharded normalise + resample (scalar exchanges + source-side placement); see the C header."""
+        idx = np.empty(self.size(), np.int32) if want_idx else None
+        check(self._L.amcl3d_b200_pf_shard_resample_fast(self._h, float(np.float32(u01)), idx.ctypes.data if want_idx else None))
+        return idx
+
     def shard_mean(self, d_out7: int = 0, fetch=True):
         """getMean over all ranks; fetch=False leaves the 7 floats in d_out7 (device) without a host wait in async mode."""
         out = np.zeros(7, np.float32) if fetch else None

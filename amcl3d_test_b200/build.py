@@ -59,7 +59,7 @@ def build_native(verbose: bool = False, force: bool = False) -> Path:
                 raise RuntimeError(f"nvcc failed on {src}")
             (objdir / (src + ".ptxas.txt")).write_text(r.stderr)
     if force or _stale(LIB, objs):
-        cmd = [nvcc(), *ccbin, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs)]
+        cmd = [nvcc(), *ccbin, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs), "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -21,6 +21,7 @@ SYMBOLS = [
     "amcl3d_b200_pf_shard_attach_ipc", "amcl3d_b200_pf_shard_attach_local", "amcl3d_b200_pf_shard_resample",
     "amcl3d_b200_pf_shard_mean", "amcl3d_b200_pf_shard_resample_local", "amcl3d_b200_pf_shard_mean_local",
     "amcl3d_b200_pf_shard_normalize", "amcl3d_b200_pf_shard_normalize_local", "amcl3d_b200_grid_clone",
+    "amcl3d_b200_host_pin", "amcl3d_b200_host_unpin", "amcl3d_b200_pf_shard_resample_fast",
     "amcl3d_b200_grid_create", "amcl3d_b200_grid_destroy", "amcl3d_b200_grid_get_info",
     "amcl3d_b200_grid_compute_bounds", "amcl3d_b200_grid_set_map", "amcl3d_b200_grid_build",
     "amcl3d_b200_grid_download_edt", "amcl3d_b200_grid_upload", "amcl3d_b200_grid_download",
@@ -97,6 +98,9 @@ def load():
         "amcl3d_b200_pf_shard_normalize": (i, [vp, P(f32)]),
         "amcl3d_b200_pf_shard_normalize_local": (i, [P(vp), i]),
         "amcl3d_b200_grid_clone": (i, [vp, i, i, P(vp)]),
+        "amcl3d_b200_host_pin": (i, [vp, C.c_size_t]),
+        "amcl3d_b200_host_unpin": (i, [vp]),
+        "amcl3d_b200_pf_shard_resample_fast": (i, [vp, f32, vp]),
         "amcl3d_b200_pf_shard_mean": (i, [vp, vp, vp]),
         "amcl3d_b200_pf_shard_resample_local": (i, [P(vp), i, f32, i, P(vp), f32]),
         "amcl3d_b200_pf_shard_mean_local": (i, [P(vp), i, vp]),

@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 using namespace a3d;
 
 namespace
@@ -69,6 +71,14 @@ cudaError_t ensure_particles(float*& ptr, uint64_t& cap, uint64_t need)
   return e;
 }
 }  // namespace
+
+// NVTX ranges named after the reference's own tic/toc timers ("Update" ParticleFilter.cpp:117,138; "PFMove" / "Resample"
+// amcl3d.cpp:185-189,194-202): a timeline of the drop-in reads like the reference's log
+struct NvtxRange
+{
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct amcl3d_b200_grid_s
 {
@@ -158,7 +168,7 @@ struct amcl3d_b200_pf_s
     size_t region_bytes = 0;
     ShardPeers peers{};
     void* opened[kMaxShardWorld] = {};  // cudaIpcOpenMemHandle mappings to close
-    uint32_t epoch = 0, mean_epoch = 0;
+    uint32_t epoch = 0, mean_epoch = 0, fast_epoch = 0;
     uint32_t cur = 0;  // P[cur] holds p_
     unsigned int* d_done = nullptr;
     uint32_t* d_error = nullptr;
@@ -282,6 +292,37 @@ int amcl3d_b200_device_info(int device, int* device_count, int* sm_count, int* c
     *l2_bytes = (uint64_t)p.l2CacheSize;
   if (mem_bytes)
     *mem_bytes = (uint64_t)p.totalGlobalMem;
+  return AMCL3D_B200_OK;
+}
+
+// page-locks a host buffer the caller keeps handing to set_particles / get_particles (cudaHostRegister), so that those
+// copies are single DMA transfers instead of staged pageable copies
+int amcl3d_b200_host_pin(void* ptr, size_t bytes)
+{
+  if (!ptr || !bytes)
+    return fail(AMCL3D_B200_ERR_ARG, "NULL buffer");
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered)
+  {
+    (void)cudaGetLastError();
+    cudaHostUnregister(ptr);
+    e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  }
+  if (e != cudaSuccess)
+    return fail_cuda(e, "cudaHostRegister");
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_host_unpin(void* ptr)
+{
+  if (!ptr)
+    return AMCL3D_B200_OK;
+  cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess)
+  {
+    (void)cudaGetLastError();
+    return fail_cuda(e, "cudaHostUnregister");
+  }
   return AMCL3D_B200_OK;
 }
 
@@ -588,6 +629,7 @@ int amcl3d_b200_grid_device_ptr(amcl3d_b200_grid_t g, void** d_prob)
 static int grid_build_impl(amcl3d_b200_grid_t g, const float* xyz, bool on_device, uint32_t stride, uint64_t n, double sensor_dev,
                            int mode, int sub, int keep_edt)
 {
+  NvtxRange nvtx_range("computeGrid");
   if (!g || !xyz || stride < 3)
     return fail(AMCL3D_B200_ERR_ARG, "bad cloud");
   if (!g->map.has_map)
@@ -1162,6 +1204,7 @@ static int fuse_range_async(amcl3d_b200_pf_t pf, const float* d_wr, float alpha)
 static int update_impl(amcl3d_b200_pf_t pf, const amcl3d_b200_beacon_t* beacons, uint32_t nb, float alpha, float sigma,
                        uint64_t* in_bounds, float* d_wr_ext)
 {
+  NvtxRange nvtx_range("Update");
   if (!pf || (nb && !beacons) || nb > (uint32_t)kMaxBeacons)
     return fail(AMCL3D_B200_ERR_ARG, "bad beacons");
   if (int rc = use_device(pf->grid->device))
@@ -1317,6 +1360,7 @@ static int normalize_async(amcl3d_b200_pf_t pf)
 
 int amcl3d_b200_pf_normalize(amcl3d_b200_pf_t pf, float* wtp)
 {
+  NvtxRange nvtx_range("particleNormalize");
   if (!pf)
     return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
   if (int rc = use_device(pf->grid->device))
@@ -1372,6 +1416,7 @@ static int adopt_alt(amcl3d_b200_pf_t pf, uint64_t count)
 
 int amcl3d_b200_pf_resample(amcl3d_b200_pf_t pf, float u01, uint64_t m0, uint64_t m1, void* d_out, int32_t* idx)
 {
+  NvtxRange nvtx_range("Resample");
   if (!pf)
     return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
   const uint64_t n = pf->n;
@@ -1422,6 +1467,7 @@ int amcl3d_b200_pf_resample(amcl3d_b200_pf_t pf, float u01, uint64_t m0, uint64_
 int amcl3d_b200_pf_uniform_sample(amcl3d_b200_pf_t pf, int sample_num, uint64_t k0, uint64_t k1, void* d_out,
                                   int32_t* idx, int* emitted)
 {
+  NvtxRange nvtx_range("uniformSample");
   if (!pf || sample_num < 0)
     return fail(AMCL3D_B200_ERR_ARG, "bad sample_num");
   const uint64_t S = (uint64_t)sample_num;
@@ -1476,6 +1522,7 @@ int amcl3d_b200_pf_uniform_sample(amcl3d_b200_pf_t pf, int sample_num, uint64_t 
 
 int amcl3d_b200_pf_mean(amcl3d_b200_pf_t pf, int exact, float out7[7])
 {
+  NvtxRange nvtx_range("getMean");
   if (!pf || !out7)
     return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
   if (int rc = use_device(pf->grid->device))
@@ -1528,6 +1575,7 @@ int amcl3d_b200_pf_best(amcl3d_b200_pf_t pf, float out7[7])
 
 int amcl3d_b200_pf_predict(amcl3d_b200_pf_t pf, const double delta[6], const float* noise6)
 {
+  NvtxRange nvtx_range("PFMove");
   if (!pf || !delta || (pf->n && !noise6))
     return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
   if (int rc = use_device(pf->grid->device))
@@ -1687,6 +1735,7 @@ int amcl3d_b200_pf_update_sample_height(amcl3d_b200_pf_t pf, const float* keypos
 int amcl3d_b200_pf_resample_step(amcl3d_b200_pf_t pf, int weight_multiply, int min_resamp, int max_resamp,
                                  const float* keyposes_xyz, uint64_t nkey, int* new_size)
 {
+  NvtxRange nvtx_range("Resample");
   if (!pf)
     return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
   int rc = AMCL3D_B200_OK;
@@ -1759,7 +1808,11 @@ int amcl3d_b200_pf_shard_init(amcl3d_b200_pf_t pf, uint64_t n_total, int rank, i
   P.off_mean = off;
   off += align256(2 * kMaxShardWorld * 8 * 4);
   P.off_flags = off;
-  off += align256(2 * kMaxShardWorld * 4);
+  off += align256(kShardFlagKinds * kMaxShardWorld * 4);
+  P.off_sums = off;
+  off += align256(2 * 2 * kMaxShardWorld * 4);
+  P.off_idx = off;
+  off += align256(S.n_max * 4);
   S.region_bytes = off;
   CU(cudaMalloc(&S.region, S.region_bytes));
   CU(cudaMemset(S.region, 0, S.region_bytes));
@@ -1889,6 +1942,7 @@ int shard_ready(amcl3d_b200_pf_t pf)
 
 int amcl3d_b200_pf_shard_normalize(amcl3d_b200_pf_t pf, float* wtp)
 {
+  NvtxRange nvtx_range("particleNormalize (sharded)");
   if (int rc = shard_ready(pf))
     return rc;
   amcl3d_b200_pf_s::Shard& S = pf->shard;
@@ -1918,6 +1972,7 @@ int amcl3d_b200_pf_shard_normalize(amcl3d_b200_pf_t pf, float* wtp)
 
 int amcl3d_b200_pf_shard_resample(amcl3d_b200_pf_t pf, float u01, int normalize, const void* d_wr_local, float alpha, int32_t* idx)
 {
+  NvtxRange nvtx_range("Resample (sharded)");
   if (int rc = shard_ready(pf))
     return rc;
   if (!normalize && d_wr_local)
@@ -1973,8 +2028,59 @@ int amcl3d_b200_pf_shard_resample(amcl3d_b200_pf_t pf, float u01, int normalize,
   return shard_check_error(pf);
 }
 
+// fast (non-exact) mode, see shard.cu: two scalar exchanges + source-side placement, no rank reads another rank's weights
+int amcl3d_b200_pf_shard_resample_fast(amcl3d_b200_pf_t pf, float u01, int32_t* idx)
+{
+  NvtxRange nvtx_range("Resample (sharded, fast)");
+  if (int rc = shard_ready(pf))
+    return rc;
+  amcl3d_b200_pf_s::Shard& S = pf->shard;
+  const uint64_t N = S.n_total, n = pf->n;
+  if (N < S.world)
+    return fail(AMCL3D_B200_ERR_ARG, "fewer particles than ranks");
+  CU(ensure(pf->d_prefix, pf->prefix_cap, std::max<uint64_t>(n, 1)));
+  CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(std::max<uint64_t>(n, 1))));
+  S.fast_epoch += 1;
+  const uint32_t e = S.fast_epoch, parity = e & 1u;
+  const uint32_t* flags = reinterpret_cast<const uint32_t*>(S.region + S.peers.off_flags);
+  const float* sums = reinterpret_cast<const float*>(S.region + S.peers.off_sums);
+  float* out = reinterpret_cast<float*>(S.region + S.peers.off_p + (size_t)(S.cur ^ 1u) * S.peers.p_bytes);
+  float* sc = pf->d_scalars;  // [0] local sum -> [4],[5] global sum / before; [1] local total -> [6],[7] total / base
+  {
+    Timed t(pf);
+    // 1. weight sum: local sequential chain, combined over the ranks in rank order
+    CU(launch_chain_prefix(pf->d_p, n, 1, nullptr, sc + 0, pf->d_dense, pf->chain_mode, pf->stream));
+    CU(launch_shard_publish_scalar(S.peers, sc + 0, 0, parity, e, S.rank, pf->stream));
+    CU(launch_shard_wait(flags, 2, S.world, e, S.d_error, pf->stream));
+    CU(launch_shard_combine_scalar(sums + ((size_t)0 * 2 + parity) * kMaxShardWorld, S.world, S.rank, sc + 4, pf->stream));
+    CU(launch_normalize(pf->grid->map, pf->d_p, n, sc + 4, pf->stream));  // ParticleFilter.cpp:180-195 with the global sum
+    // 2. local inclusive prefix of the normalised weights; its total places the rank's stretch in the global prefix
+    CU(launch_chain_prefix(pf->d_p, n, 0, pf->d_prefix, sc + 1, pf->d_dense, pf->chain_mode, pf->stream));
+    CU(launch_shard_publish_scalar(S.peers, sc + 1, 1, parity, e, S.rank, pf->stream));
+    CU(launch_shard_wait(flags, 3, S.world, e, S.d_error, pf->stream));
+    CU(launch_shard_combine_scalar(sums + ((size_t)1 * 2 + parity) * kMaxShardWorld, S.world, S.rank, sc + 6, pf->stream));
+    // 3. place this rank's offspring into the output blocks of their owners; wait until every rank has placed its own
+    CU(launch_shard_push(S.peers, pf->d_p, pf->d_prefix, (uint32_t)n, S.lo, N, sc + 6, u01, S.rank, S.cur ^ 1u, e, S.d_done,
+                         pf->stream));
+    CU(launch_shard_wait(flags, 4, S.world, e, S.d_error, pf->stream));
+    pf->launches += 11;
+    pf->launches += chain_extra_launches_take();
+  }
+  S.cur ^= 1u;
+  pf->d_p = out;
+  if (idx && n)
+  {
+    CU(cudaMemcpyAsync(idx, S.region + S.peers.off_idx, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, pf->stream));
+    return shard_check_error(pf);
+  }
+  if (pf->async_mode)
+    return AMCL3D_B200_OK;
+  return shard_check_error(pf);
+}
+
 int amcl3d_b200_pf_shard_mean(amcl3d_b200_pf_t pf, float out7[7], void* d_out7)
 {
+  NvtxRange nvtx_range("getMean (sharded)");
   if (!pf || (!out7 && !d_out7))
     return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
   amcl3d_b200_pf_s::Shard& S = pf->shard;

@@ -191,8 +191,11 @@ struct ShardPeers
   uint64_t off_w, off_wr;   // dense f32 [2][n_total]
   uint64_t off_inmap;       // u8 [2][n_total]
   uint64_t off_mean;        // f32 [2][kMaxShardWorld][8]
-  uint64_t off_flags;       // u32 [2 kinds][kMaxShardWorld]
+  uint64_t off_flags;       // u32 [kShardFlagKinds][kMaxShardWorld]
+  uint64_t off_sums;        // f32 [2 steps][2 parity][kMaxShardWorld]: per-rank partial sums of the fast mode
+  uint64_t off_idx;         // i32 [n_max]: global source index of every output of this rank (fast mode, pushed by the source)
 };
+constexpr uint32_t kShardFlagKinds = 8;  // 0 weights, 1 mean, 2 / 3 fast-mode sums, 4 fast-mode push done
 cudaError_t launch_shard_publish(const MapDev& map, const ShardPeers& peers, const float* particles, const float* wr_local,
                                  uint32_t n, uint32_t lo, uint32_t n_total, uint32_t parity, uint32_t epoch, uint32_t rank,
                                  unsigned int* done_counter, cudaStream_t stream);
@@ -203,6 +206,16 @@ cudaError_t launch_dense_fuse(float* w, const float* wr, uint64_t n, const float
                               cudaStream_t stream);
 cudaError_t launch_shard_search(const ShardPeers& peers, const float* prefix, uint64_t n, float u01, uint64_t m0, uint64_t m1,
                                 uint32_t src_buf, float* out, int32_t* idx, cudaStream_t stream);
+// fast (non-exact) mode: a per-rank scalar into every rank's sums[step][parity][rank], then flags[2 + step][rank] = epoch
+cudaError_t launch_shard_publish_scalar(const ShardPeers& peers, const float* value, uint32_t step, uint32_t parity, uint32_t epoch,
+                                        uint32_t rank, cudaStream_t stream);
+// out2[0] = sum over ranks in rank order (sequential f32), out2[1] = sum over the ranks before `rank`
+cudaError_t launch_shard_combine_scalar(const float* sums_all, uint32_t world, uint32_t rank, float* out2, cudaStream_t stream);
+// source-side resampling: every output m whose threshold falls into this rank's stretch (base, base + local total] of the
+// global prefix is found in the LOCAL prefix and the particle is STORED into the output block of the rank that owns m
+cudaError_t launch_shard_push(const ShardPeers& peers, const float* particles, const float* prefix_local, uint32_t n_local,
+                              uint64_t lo, uint64_t n_total, const float* base2 /* [1] = base */, float u01, uint32_t rank,
+                              uint32_t dst_buf, uint32_t epoch, unsigned int* done_counter, cudaStream_t stream);
 cudaError_t launch_shard_publish_mean(const ShardPeers& peers, const float* part7, uint32_t parity, uint32_t epoch, uint32_t rank,
                                       cudaStream_t stream);
 cudaError_t launch_shard_combine_mean(const float* mean_all, uint32_t world, float* out7, cudaStream_t stream);

@@ -720,6 +720,25 @@ __global__ void __launch_bounds__(256)
 // one sweep of the min-plus stencil for kFastPer consecutive outputs of one lane (two packed columns): rows[t] is the
 // candidate site row (first output - H + t); delta = output - site is a compile-time constant of every (t, k) pair, so
 // its squared offset is an immediate operand of VIADDMNMX
+// explicit global-space accesses for the walking pointers of the two passes (an opaque pointer would otherwise be
+// dereferenced through the generic address space)
+__device__ __forceinline__ uint32_t ldg_nc_u32(const void* p)
+{
+  uint32_t v;
+  asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_nc_u16(const void* p)
+{
+  uint16_t v;
+  asm volatile("ld.global.nc.b16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_f32x2(float* p, float a, float b)
+{
+  asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
 template <int SUB, int PAR, int H, typename RowFn>
 __device__ __forceinline__ void dpx_sweep(RowFn row, uint32_t best[kFastPer])
 {
@@ -757,26 +776,30 @@ __global__ void __launch_bounds__(256) ypass_dpx_kernel(const uint8_t* __restric
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const int i0 = (int)(it * kTI);
   const uint32_t cap = A.cap, cap2 = cap * 0x10001u;
-  const uint8_t* src = d1 + ((uint64_t)plane * A.w1) * A.px + ct * 64 + 2 * lane;
   {
-    // every load of the tile is issued before the first one is consumed (13 independent loads per thread at H = 20)
+    // warp w stages site rows r = w, w + 8, ...: one pointer walking down the plane by 8 rows a step, one unsigned
+    // compare per row (j < 0 wraps above w1); every load of the tile is issued before the first one is consumed
     constexpr int kLoads = (kRows + 7) / 8;
+    const int j0 = i0 - H + (int)warp;
+    const uint8_t* p = d1 + ((int64_t)plane * A.w1 + j0) * (int64_t)A.px + ct * 64 + 2 * lane;
+    const uint64_t step = 8ull * A.px;
     uint32_t raw[kLoads];
 #pragma unroll
     for (int q = 0; q < kLoads; ++q)
     {
-      const int r = (int)warp + 8 * q, j = i0 - H + r;
       raw[q] = 0xFFFFu;  // 255, 255: no site
-      if (r < kRows && j >= 0 && j < (int)A.w1)
-        raw[q] = *reinterpret_cast<const uint16_t*>(src + (uint64_t)j * A.px);
+      if ((int)warp + 8 * q < kRows && (uint32_t)(j0 + 8 * q) < A.w1)
+        raw[q] = ldg_nc_u16(p);
+      p += step;
+      asm volatile("" : "+l"(p));  // keep the walking pointer: one 64-bit add per row instead of a 64-bit multiply-add chain
     }
+    uint32_t* t = &tile[warp][lane];
 #pragma unroll
     for (int q = 0; q < kLoads; ++q)
     {
-      const int r = (int)warp + 8 * q;
       const uint32_t a = raw[q] & 0xFFu, c = raw[q] >> 8;
-      if (r < kRows)
-        tile[r][lane] = min(a * a, cap) | (min(c * c, cap) << 16);
+      if ((int)warp + 8 * q < kRows)
+        t[q * 8 * 32] = __vminu2(a * a | ((c * c) << 16), cap2);  // a, c <= 255: both squares fit their 16-bit half
     }
   }
   __syncthreads();
@@ -786,14 +809,14 @@ __global__ void __launch_bounds__(256) ypass_dpx_kernel(const uint8_t* __restric
     best[k] = cap2;
   const uint32_t base = warp * kFastPer;
   dpx_sweep<SUB, PAR, H>([&](int t) { return tile[base + t][lane]; }, best);
-  uint32_t* dst = reinterpret_cast<uint32_t*>(dxy + ((uint64_t)plane * A.sy) * A.px + ct * 64 + 2 * lane);
+  const uint32_t i_first = (uint32_t)i0 + base;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(dxy + ((uint64_t)plane * A.sy + i_first) * A.px + ct * 64 + 2 * lane);
+  const uint32_t left = A.sy > i_first ? A.sy - i_first : 0u;  // outputs of this thread that exist
+  const uint32_t pitch = A.px / 2;
 #pragma unroll
   for (int k = 0; k < kFastPer; ++k)
-  {
-    const uint32_t i = (uint32_t)i0 + base + k;
-    if (i < A.sy)
-      dst[(uint64_t)i * (A.px / 2)] = best[k];
-  }
+    if ((uint32_t)k < left)
+      dst[(uint64_t)k * pitch] = best[k];
 }
 
 // in: dxy [site row j = z][y][px] u16; out: prob [z][y][sx] f32 and the bricked u8 codes.
@@ -807,6 +830,7 @@ __global__ void __launch_bounds__(256)
                      uint32_t nbx, uint32_t nby)
 {
   constexpr int kRows = kZT + 2 * H;
+  static_assert(kRows % 2 == 0, "two site rows per staging step");
   extern __shared__ __align__(16) uint32_t zsm[];
   uint32_t(*tile)[4][32] = reinterpret_cast<uint32_t(*)[4][32]>(zsm);                          // [kRows][4][32]
   uint8_t* stage = reinterpret_cast<uint8_t*>(zsm + (size_t)kRows * 4 * 32);                  // 64 bricks x kBrickPitch
@@ -821,66 +845,96 @@ __global__ void __launch_bounds__(256)
   const int z0 = (int)(zt * kZT);
   const uint32_t cap = A.cap, cap2 = cap * 0x10001u;
   {
-    // (site row, y) pairs round-robin over the 8 warps, all loads issued before the first store (36 per thread at H = 20)
+    // warp w stages y row (w & 3) of the site rows r = (w >> 2), (w >> 2) + 2, ...: one pointer walking up by two site
+    // rows a step, one unsigned compare per row (a negative j wraps above the limit, a y row outside the grid has limit 0);
+    // loads in batches of 12, all issued before the first store
     const uint32_t warp = threadIdx.x >> 5;
-    constexpr int kLoads = (kRows * 4 + 7) / 8;
+    const uint32_t yy = warp & 3u, rb = warp >> 2;
+    const int j0 = z0 - H + (int)rb;
+    const uint32_t jlim = (y0 + yy < A.sy) ? A.w2 : 0u;
+    const uint64_t row = (uint64_t)A.sy * A.px;  // elements between site rows
+    const uint16_t* p = dxy + ((int64_t)j0 * (int64_t)A.sy + (int64_t)(y0 + yy)) * (int64_t)A.px + x0 + 2 * lane;
+    uint32_t* t = &tile[rb][yy][lane];
+    constexpr int kM = kRows / 2;  // staging steps of this warp
     constexpr int kBatch = 12;
-#pragma unroll 1
-    for (int q0 = 0; q0 < kLoads; q0 += kBatch)
+#pragma unroll
+    for (int m0 = 0; m0 < kM; m0 += kBatch)
     {
       uint32_t raw[kBatch];
 #pragma unroll
       for (int u = 0; u < kBatch; ++u)
       {
-        const int q = (int)warp + 8 * (q0 + u);
-        const int r = q >> 2, j = z0 - H + r;
-        const uint32_t yy = (uint32_t)q & 3u;
+        const int m = m0 + u;
         raw[u] = cap2;
-        if (q < kRows * 4 && j >= 0 && j < (int)A.w2 && y0 + yy < A.sy)
-          raw[u] = *reinterpret_cast<const uint32_t*>(dxy + ((uint64_t)j * A.sy + (y0 + yy)) * A.px + x0 + 2 * lane);
+        if (m < kM)
+        {
+          if ((uint32_t)(j0 + 2 * m) < jlim)
+            raw[u] = ldg_nc_u32(p);
+          p += 2 * row;
+          asm volatile("" : "+l"(p));  // walking pointer: one 64-bit add per staging step
+        }
       }
 #pragma unroll
       for (int u = 0; u < kBatch; ++u)
       {
-        const int q = (int)warp + 8 * (q0 + u);
-        if (q < kRows * 4)
-          tile[q >> 2][q & 3][lane] = raw[u];
+        const int m = m0 + u;
+        if (m < kM)
+          t[m * 2 * 4 * 32] = raw[u];
       }
     }
   }
   __syncthreads();
   const uint32_t x = x0 + 2 * lane, y = y0 + ty;
+  // how this thread's two x neighbours go out: 0 nothing, 1 first only, 2 both as one 8-byte store, 3 both as two stores
+  const uint32_t xmode = (y >= A.sy || x >= A.sx) ? 0u : (x + 1 >= A.sx ? 1u : ((A.sx & 1u) ? 3u : 2u));
+  const uint64_t zstride = (uint64_t)A.sy * A.sx;
+  const bool interior = (x0 + 64 <= A.sx) && (y0 + 4 <= A.sy) && !(A.sx & 1u);  // block-uniform
 #pragma unroll 1
   for (int s = 0; s < 2; ++s)
   {
-    const uint32_t zb = zg * 16 + s * 8;  // first output of this sweep, relative to the tile
+    const uint32_t zb = zg * 16 + s * 8;  // first output of this sweep, relative to the tile (a multiple of 8)
     uint32_t best[kFastPer];
 #pragma unroll
     for (int k = 0; k < kFastPer; ++k)
       best[k] = cap2;
     dpx_sweep<SUB, PAR, H>([&](int t) { return tile[zb + t][ty][lane]; }, best);
+    // staged brick (bz, bx) of the tile, voxel (z&3, y&3, x&7): two x neighbours = one 16-bit store; zb is a multiple of
+    // 8, so the brick row and the z-in-brick bits of output k are compile-time offsets from one base
+    uint8_t* st = stage + ((zb >> 2) * 8 + (lane >> 2)) * kBrickPitch + ((ty << 3) | ((2 * lane) & 7u));
+    float* dst = prob + ((uint64_t)((uint32_t)z0 + zb) * A.sy + y) * A.sx + x;
+    const uint32_t zleft = A.sz > (uint32_t)z0 + zb ? A.sz - ((uint32_t)z0 + zb) : 0u;  // outputs of this sweep inside the grid
+    if (interior && zleft >= (uint32_t)kFastPer)
+    {
+      // the whole tile lies inside the grid and rows are 8-byte aligned: no per-output tests, one 8-byte store each
+#pragma unroll
+      for (int k = 0; k < kFastPer; ++k)
+      {
+        const uint32_t ca = rank[best[k] & 0xFFFFu], cb = rank[best[k] >> 16];
+        *reinterpret_cast<uint16_t*>(st + (k >> 2) * 8 * kBrickPitch + ((k & 3) << 5)) = (uint16_t)(ca | (cb << 8));
+        stg_f32x2(dst, lut[ca], lut[cb]);
+        dst += zstride;
+        asm volatile("" : "+l"(dst));
+      }
+      continue;
+    }
 #pragma unroll
     for (int k = 0; k < kFastPer; ++k)
     {
-      const uint32_t zr = zb + k, z = (uint32_t)z0 + zr;
       const uint32_t ca = rank[best[k] & 0xFFFFu], cb = rank[best[k] >> 16];
-      // staged brick (bz, bx) of the tile, voxel (z&3, y&3, x&7): two x neighbours = one 16-bit store
-      const uint32_t so = ((zr >> 2) * 8 + (lane >> 2)) * kBrickPitch + (((zr & 3u) << 5) | (ty << 3) | ((2 * lane) & 7u));
-      *reinterpret_cast<uint16_t*>(stage + so) = (uint16_t)(ca | (cb << 8));
-      if (z < A.sz && y < A.sy)
+      *reinterpret_cast<uint16_t*>(st + (k >> 2) * 8 * kBrickPitch + ((k & 3) << 5)) = (uint16_t)(ca | (cb << 8));
+      if ((uint32_t)k < zleft && xmode != 0u)
       {
-        float* dst = prob + ((uint64_t)z * A.sy + y) * A.sx + x;
-        const float pa = lut[ca], pb = lut[cb];
-        if (!(A.sx & 1u) && x + 1 < A.sx)
-          *reinterpret_cast<float2*>(dst) = make_float2(pa, pb);
+        const float pa = lut[ca];
+        if (xmode == 2u)
+          *reinterpret_cast<float2*>(dst) = make_float2(pa, lut[cb]);
         else
         {
-          if (x < A.sx)
-            dst[0] = pa;
-          if (x + 1 < A.sx)
-            dst[1] = pb;
+          dst[0] = pa;
+          if (xmode == 3u)
+            dst[1] = lut[cb];
         }
       }
+      dst += zstride;
     }
   }
   __syncthreads();
@@ -970,8 +1024,14 @@ static cudaError_t launch_z_t(const FastArgs& A, const uint16_t* dxy, float* pro
 #define A3D_FOR_H(CALL)   \
   if (h <= 12)            \
     return CALL(12);      \
+  if (h <= 16)            \
+    return CALL(16);      \
+  if (h <= 18)            \
+    return CALL(18);      \
   if (h <= 20)            \
     return CALL(20);      \
+  if (h <= 24)            \
+    return CALL(24);      \
   if (h <= 28)            \
     return CALL(28);      \
   if (h <= 36)            \

@@ -22,6 +22,8 @@
 // only after it finished reading everything of epoch e).
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace a3d
 {
 namespace
@@ -183,6 +185,132 @@ __global__ void __launch_bounds__(256)
     idx[m - m0] = (int32_t)src;
 }
 
+// ---- fast (non-exact) mode --------------------------------------------------------------------------------------
+// north_star's "allreduce of the weight sum + allgather of prefix offsets": no rank ever sees another rank's weights.
+// Two scalar exchanges (local weight sum; local total of the normalised weights -> base offset of the rank's stretch of
+// the global prefix), then the SOURCE side places its particles: the thresholds u_m that fall into (base_r, base_r+1] are
+// searched in the rank's own prefix and the selected particle is stored straight into the output block of the rank that
+// owns slot m.  The sums are sequential f32 chains inside a rank but combined across ranks in rank order, so a threshold
+// sitting within an ulp of a prefix value can pick the neighbouring particle: indices are NOT guaranteed bit-identical
+// to one GPU (tests report the mismatch count); the exact mode above is the default.
+__global__ void publish_scalar_kernel(const __grid_constant__ ShardPeers peers, const float* __restrict__ value, uint32_t step,
+                                      uint32_t parity, uint32_t epoch, uint32_t rank)
+{
+  const uint32_t r = threadIdx.x;
+  if (r >= peers.world)
+    return;
+  float* dst = reinterpret_cast<float*>(peers.base[r] + peers.off_sums) + ((size_t)step * 2 + parity) * kMaxShardWorld + rank;
+  *dst = value[0];
+  __threadfence_system();
+  st_release_sys(reinterpret_cast<uint32_t*>(peers.base[r] + peers.off_flags) + (size_t)(2 + step) * kMaxShardWorld + rank, epoch);
+}
+__global__ void combine_scalar_kernel(const float* __restrict__ sums_all, uint32_t world, uint32_t rank, float* __restrict__ out2)
+{
+  if (threadIdx.x != 0)
+    return;
+  float total = 0.f, before = 0.f;
+  for (uint32_t r = 0; r < world; ++r)
+  {
+    if (r == rank)
+      before = total;
+    total = __fadd_rn(total, sums_all[r]);
+  }
+  out2[0] = total;
+  out2[1] = before;
+}
+
+__device__ __forceinline__ float threshold(float r, float factor, uint32_t m)
+{
+  return __fadd_rn(r, __fmul_rn(factor, __uint2float_rn(m)));  // ParticleFilter.cpp:241
+}
+// first m in [0, n] with u_m > c (n if none): u_m is non-decreasing in m
+__device__ __forceinline__ uint32_t first_above(float r, float factor, uint32_t n, float c)
+{
+  uint32_t lo = 0, hi = n;
+  while (lo < hi)
+  {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (threshold(r, factor, mid) > c)
+      hi = mid;
+    else
+      lo = mid + 1;
+  }
+  return lo;
+}
+__global__ void __launch_bounds__(256)
+    shard_push_kernel(const __grid_constant__ ShardPeers peers, const float* __restrict__ particles, const float* __restrict__ prefix,
+                      uint32_t n_local, uint64_t lo, uint64_t n_total, const float* __restrict__ base2, float u01, uint32_t rank,
+                      uint32_t dst_buf, uint32_t epoch, unsigned int* __restrict__ done_counter)
+{
+  const uint32_t N = (uint32_t)n_total;
+  const float factor = __fdiv_rn(1.f, __ull2float_rn(n_total));
+  const float r = __fmul_rn(factor, u01);
+  const float base = base2[1];
+  __shared__ uint32_t range[2];
+  if (threadIdx.x == 0)
+  {
+    // this rank's stretch of the global prefix is (base, base + local total]; rank 0 also takes u_m <= 0, the last rank
+    // everything above the global total (clamped to the last particle of the set like the exact path)
+    const float end = n_local ? __fadd_rn(base, prefix[n_local - 1]) : base;
+    const bool first = rank == 0, last = rank + 1 == peers.world;
+    range[0] = first ? 0u : first_above(r, factor, N, base);
+    range[1] = (n_local == 0) ? range[0] : (last ? N : first_above(r, factor, N, end));
+    if (n_local == 0)
+      range[1] = range[0];
+  }
+  __syncthreads();
+  const uint32_t m_a = range[0], m_b = range[1];
+  const uint64_t base_n = n_total / peers.world, rem = n_total % peers.world;
+  const uint64_t split = rem * (base_n + 1);
+  for (uint64_t m = (uint64_t)m_a + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; m < m_b; m += (uint64_t)gridDim.x * blockDim.x)
+  {
+    const float u = threshold(r, factor, (uint32_t)m);
+    uint32_t a = 0, b = n_local;
+    while (a < b)
+    {
+      const uint32_t mid = (a + b) >> 1;
+      if (u > __fadd_rn(base, prefix[mid]))
+        a = mid + 1;
+      else
+        b = mid;
+    }
+    const uint32_t src = (a >= n_local) ? n_local - 1 : a;
+    uint32_t owner;
+    uint64_t slot;
+    if (m < split)
+    {
+      owner = (uint32_t)(m / (base_n + 1));
+      slot = m - (uint64_t)owner * (base_n + 1);
+    }
+    else
+    {
+      owner = (uint32_t)(rem + (m - split) / base_n);
+      slot = (m - split) - (uint64_t)(owner - rem) * base_n;
+    }
+    const float* p = particles + (size_t)7 * src;
+    float* q = reinterpret_cast<float*>(peers.base[owner] + peers.off_p + (size_t)dst_buf * peers.p_bytes) + 7 * slot;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      q[k] = p[k];
+    q[6] = factor;
+    reinterpret_cast<int32_t*>(peers.base[owner] + peers.off_idx)[slot] = (int32_t)(lo + src);
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last_block;
+  if (threadIdx.x == 0)
+    last_block = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last_block)
+  {
+    __threadfence_system();
+    if (threadIdx.x < peers.world)
+      st_release_sys(reinterpret_cast<uint32_t*>(peers.base[threadIdx.x] + peers.off_flags) + (size_t)4 * kMaxShardWorld + rank, epoch);
+    if (threadIdx.x == 0)
+      *done_counter = 0;
+  }
+}
+
 // this rank's 7 partial floats (sums of w*x.., max w) into every rank's mean[parity][rank], then flags[1][rank] = epoch
 __global__ void publish_mean_kernel(const __grid_constant__ ShardPeers peers, const float* __restrict__ part7, uint32_t parity,
                                     uint32_t epoch, uint32_t rank)
@@ -259,6 +387,30 @@ cudaError_t launch_shard_search(const ShardPeers& peers, const float* prefix, ui
   if (m1 <= m0)
     return cudaSuccess;
   shard_search_kernel<<<(unsigned)((m1 - m0 + 255) / 256), 256, 0, stream>>>(peers, prefix, n, u01, m0, m1, src_buf, out, idx);
+  return cudaGetLastError();
+}
+cudaError_t launch_shard_publish_scalar(const ShardPeers& peers, const float* value, uint32_t step, uint32_t parity, uint32_t epoch,
+                                        uint32_t rank, cudaStream_t stream)
+{
+  publish_scalar_kernel<<<1, 32, 0, stream>>>(peers, value, step, parity, epoch, rank);
+  return cudaGetLastError();
+}
+cudaError_t launch_shard_combine_scalar(const float* sums_all, uint32_t world, uint32_t rank, float* out2, cudaStream_t stream)
+{
+  combine_scalar_kernel<<<1, 32, 0, stream>>>(sums_all, world, rank, out2);
+  return cudaGetLastError();
+}
+cudaError_t launch_shard_push(const ShardPeers& peers, const float* particles, const float* prefix_local, uint32_t n_local,
+                              uint64_t lo, uint64_t n_total, const float* base2, float u01, uint32_t rank, uint32_t dst_buf,
+                              uint32_t epoch, unsigned int* done_counter, cudaStream_t stream)
+{
+  // sized for a rank that places about twice its share; a rank holding most of the weight loops (grid-stride)
+  uint64_t want = 2 * (n_total / (peers.world ? peers.world : 1)) + 256;
+  uint32_t blocks = (uint32_t)std::min<uint64_t>((want + 255) / 256, 148 * 16);
+  if (blocks == 0)
+    blocks = 1;
+  shard_push_kernel<<<blocks, 256, 0, stream>>>(peers, particles, prefix_local, n_local, lo, n_total, base2, u01, rank, dst_buf, epoch,
+                                               done_counter);
   return cudaGetLastError();
 }
 cudaError_t launch_shard_publish_mean(const ShardPeers& peers, const float* part7, uint32_t parity, uint32_t epoch, uint32_t rank,

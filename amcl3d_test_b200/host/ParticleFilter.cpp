@@ -98,6 +98,7 @@ void ParticleFilter::pull(std::vector<Particle>& out) const
   if (!p_.dev_fresh_)
     throw std::logic_error("ParticleFilter: neither the host nor a device holds the current set");
   out.resize(p_.dev_n_);
+  p_.pin();
   if (where_ == kSingle)
   {
     uint64_t n = 0;
@@ -118,6 +119,7 @@ void ParticleFilter::syncDevice()
   if (p_.dev_fresh_ && where_ == kSingle)
     return;
   const std::vector<Particle>& h = p_.host();  // gathers from the shards if that is where the set is
+  p_.pin();
   check(amcl3d_b200_pf_set_particles(handle_, h.empty() ? nullptr : &h[0].x, h.size()), "upload p_");
   ++p_.uploads_;
   p_.dev_fresh_ = true;
@@ -192,6 +194,7 @@ void ParticleFilter::syncShards()
   const std::vector<Particle>& h = p_.host();
   if (h.empty())
     throw std::runtime_error("ParticleFilter: no particles to shard");
+  p_.pin();
   if (shard_.size() != world || shard_n_ != h.size())
   {
     dropShards();

@@ -245,6 +245,11 @@ class PeerShardedFilter:
             return self.pf.shard_resample(u01, self.wr_local.data_ptr(), self.alpha, want_idx=want_idx)
         return self.pf.shard_resample(u01, want_idx=want_idx)
 
+    def resample_fast(self, u01: float, want_idx=False):
+        """NON-exact mode: scalar exchanges + source-side placement (amcl3d_b200_pf_shard_resample_fast)."""
+        assert self.wr_local is None, "the fast mode has no range-beacon fusion"
+        return self.pf.shard_resample_fast(u01, want_idx=want_idx)
+
     def mean_device(self) -> torch.Tensor:
         self.pf.shard_mean(self._mean_buf.data_ptr(), fetch=False)
         return self._mean_buf[:7]

@@ -133,6 +133,33 @@ private:
     host_fresh_ = true;
     dev_fresh_ = false;
   }
+  ~ParticleMirror() { unpin(); }
+  ParticleMirror() {}
+  ParticleMirror(const ParticleMirror&) = delete;
+  // the vector's buffer is page-locked once it is large enough to matter (>= 256 KB) and re-registered when the vector
+  // reallocated: the set then crosses PCIe as one DMA transfer each way
+  void pin() const
+  {
+    const void* ptr = host_.data();
+    const size_t bytes = host_.capacity() * sizeof(Particle);
+    if (ptr == pinned_ptr_ && bytes == pinned_bytes_)
+      return;
+    unpin();
+    if (bytes >= (256u << 10) && amcl3d_b200_host_pin(const_cast<void*>(ptr), bytes) == AMCL3D_B200_OK)
+    {
+      pinned_ptr_ = ptr;
+      pinned_bytes_ = bytes;
+    }
+  }
+  void unpin() const
+  {
+    if (pinned_ptr_)
+      amcl3d_b200_host_unpin(const_cast<void*>(pinned_ptr_));
+    pinned_ptr_ = nullptr;
+    pinned_bytes_ = 0;
+  }
+  mutable const void* pinned_ptr_{ nullptr };
+  mutable size_t pinned_bytes_{ 0 };
   mutable std::vector<Particle> host_;
   mutable bool host_fresh_{ true };  // host_ holds the current set
   bool dev_fresh_{ false };          // the device(s) hold the current set

@@ -90,6 +90,11 @@ const char* amcl3d_b200_last_error(void);
 int amcl3d_b200_device_info(int device, int* device_count, int* sm_count, int* cc_major, int* cc_minor,
                             uint64_t* l2_bytes, uint64_t* mem_bytes);
 
+/* Page-locks / releases a host buffer that the caller keeps handing to set_particles / get_particles (the std::vector
+ * behind amcl3d::ParticleFilter::p_): the copies become single DMA transfers instead of staged pageable copies. */
+int amcl3d_b200_host_pin(void* ptr, size_t bytes);
+int amcl3d_b200_host_unpin(void* ptr);
+
 /* cudaLimitMaxL2FetchGranularity of the device (32, 64 or 128 bytes) -- a measurement knob.  The library never
  * changes this limit of the host application on its own (only when AMCL3D_B200_L2_FETCH is set in the
  * environment or through this call).  Measured on B200 (profiles/r2_gather_microbench.json): a scattered 1-byte
@@ -300,6 +305,13 @@ int amcl3d_b200_pf_shard_normalize(amcl3d_b200_pf_t pf, float* wtp);
  * d_wr_local (optional, DEVICE, hi - lo floats, needs normalize != 0): raw range-beacon weights of update_split, fused
  * with alpha over the global sums before normalising (row R).  idx (optional, HOST, hi - lo ints): global source indices. */
 int amcl3d_b200_pf_shard_resample(amcl3d_b200_pf_t pf, float u01, int normalize, const void* d_wr_local, float alpha, int32_t* idx);
+/* Fast (NON-exact) variant of the fused normalise + resample, north_star's "allreduce of the weight sum + allgather of
+ * prefix offsets": two scalar exchanges, every rank scans only its own block, and the source side stores each selected
+ * particle straight into the output block of the rank that owns the slot -- no rank reads another rank's weights.  The
+ * per-rank sums are combined in rank order instead of one sequential chain over all particles, so a threshold within an
+ * ulp of a prefix value may select the neighbouring particle: indices are not guaranteed identical to one GPU
+ * (tests/test_gpu_sharded.py reports the mismatch count).  No range-beacon fusion in this mode. */
+int amcl3d_b200_pf_shard_resample_fast(amcl3d_b200_pf_t pf, float u01, int32_t* idx);
 /* getMean over all ranks (partial sums exchanged through peer memory, combined in rank order in f64); out7 (HOST) and /
  * or d_out7 (DEVICE), at least one */
 int amcl3d_b200_pf_shard_mean(amcl3d_b200_pf_t pf, float out7[7], void* d_out7);

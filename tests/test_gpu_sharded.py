@@ -91,6 +91,27 @@ def test_world_of_one_equals_the_plain_handle(O, with_beacons):
         assert np.array_equal(ref[0][2], oidx)
 
 
+def test_fast_mode_in_a_world_of_one_is_the_exact_result():
+    """With one rank the fast mode's rank-order combination is the sequential chain itself: same indices, same bits."""
+    import torch
+
+    from amcl3d_test_b200 import synth
+    from amcl3d_test_b200.sharded import PeerShardedFilter
+
+    sm, g = _world(0)
+    cloud = synth.make_cloud(sm, 1500, 9.0)
+    P = synth.make_particles(sm, 30_011, "G")
+    ref = _one_gpu(g, P, [cloud, cloud], [0.37, 0.81])
+    f = PeerShardedFilter(g, P.shape[0], torch.device("cuda", 0))
+    f.set_particles(P)
+    for k, u01 in enumerate((0.37, 0.81)):
+        f.set_cloud(cloud)
+        f.update()
+        idx = f.resample_fast(u01, want_idx=True)
+        assert np.array_equal(idx, ref[k][2])
+        assert np.array_equal(bits(f.pf.p_), bits(ref[k][1]))
+
+
 def test_two_devices_in_one_process():
     """The ranks are handles of one process (attach_local + stream order): what amcl3d::ParticleFilter::setDevices uses."""
     if _device_count() < 2:

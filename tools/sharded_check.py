@@ -40,6 +40,14 @@ def one_gpu_frames(g, P, clouds, u01s, beacons=None):
     return out
 
 
+def exact_prefix(g, W):
+    """Inclusive sequential f32 prefix of the normalised weights of the one-GPU run (ParticleFilter.cpp:235-247)."""
+    pf = ParticleFilter(g)
+    pf.p_ = W
+    pf.particleNormalize()
+    return pf.prefix()
+
+
 def peer_frames(g, P, clouds, u01s, dev, beacons=None):
     n = P.shape[0]
     f = PeerShardedFilter(g, n, dev)
@@ -98,6 +106,45 @@ def main():
         ref_b = one_gpu_frames(g, P, clouds, u01s, beacons)
         f, got_b = peer_frames(g, P, clouds, u01s, dev, beacons)
         ok = compare(f"peer+beacons n={n} {kind}", rank, lo, hi, got_b, ref_b, weights_fused=True) and ok
+        del f
+    # fast (non-exact) mode: structurally valid resampled set, and how many indices differ from the exact result
+    for n, kind in ((40_000, "T"), (40_003, "G")):
+        P = synth.make_particles(sm, n, kind)
+        lo, hi = shard_bounds(n, world, rank)
+        ref = one_gpu_frames(g, P, clouds[:1], u01s[:1])
+        f = PeerShardedFilter(g, n, dev)
+        for rep in range(2):  # twice: the exchange slots ping-pong
+            f.set_particles(P[f.lo:f.hi])
+            f.set_cloud(clouds[0])
+            f.update()
+            idx = f.resample_fast(u01s[0], want_idx=True)
+            out = f.pf.p_
+            bad = int((idx != ref[0][2][lo:hi]).sum())
+            tot = torch.tensor([bad], device=dev)
+            dist.all_reduce(tot)
+            valid = bool(np.all(np.diff(idx) >= 0) and idx.min() >= 0 and idx.max() < n and
+                         np.array_equal(bits(out[:, :6]), bits(P[idx, :6])) and np.all(out[:, 6] == np.float32(1.0) / np.float32(n)))
+            if not valid:
+                print(f"rank {rank} fast n={n} {kind}: resampled slice is not a valid systematic resample")
+                ok = False
+            # a differing index must still be a defensible choice: the threshold lies within a few ulps of the EXACT
+            # prefix interval of the particle the fast mode picked (the two modes only differ in how partial sums round)
+            Wn = ref[0][0].copy()
+            pfx = exact_prefix(g, Wn)
+            um = np.float32(u01s[0]) * (np.float32(1.0) / np.float32(n)) + (np.float32(1.0) / np.float32(n)) * np.arange(lo, hi, dtype=np.float32)
+            eps = np.float32(4e-6)
+            upper_ok = um <= pfx[idx] + eps
+            lower_ok = (idx == 0) | (um > np.where(idx > 0, pfx[np.maximum(idx - 1, 0)], np.float32(0)) - eps)
+            tail = idx == n - 1
+            if not np.all((upper_ok | tail) & lower_ok):
+                print(f"rank {rank} fast n={n} {kind}: an index is not within {eps} of the exact prefix interval")
+                ok = False
+            if rank == 0 and rep == 0:
+                print(f"fast mode n={n} {kind} world={world}: {int(tot.item())} of {n} resampled indices differ from the exact mode")
+            mean = f.mean()
+            if not np.allclose(mean[:6], ref[0][3][:6], rtol=1e-3, atol=1e-3):
+                print(f"rank {rank} fast n={n} {kind}: mean {mean} vs {ref[0][3]}")
+                ok = False
         del f
     # the NCCL all-gather formulation (A/B baseline)
     n = 40_000

@@ -1212,53 +1212,113 @@ __global__ void count_emitted_kernel(const float* __restrict__ thr, int S, const
 
 // ---- mean ---------------------------------------------------------------------------------------
 // exact: lanes 0..5 of warp 0 each run one of the six sequential f32 chains mean.c += w * p.c
-// (ParticleFilter.cpp:204-209), lane 6 tracks w_max; the other warps stream particles through smem.
-constexpr int kMeanChunk = 512;  // particles per ring stage (7 floats each)
+// (ParticleFilter.cpp:204-209), lane 6 tracks w_max.  The particle records arrive in a two-stage shared-memory ring by
+// TMA bulk copies; the other seven warps turn every stage into component-major rows of the ROUNDED products w * p.c (the
+// reference rounds the product before the add: no FMA on baseline x86-64) one chunk ahead of the chain warp, whose step
+// is then a quarter of a conflict-free LDS.128 and one dependent FADD.
+constexpr int kMeanChunk = 384;        // particles per stage: 384 x 28 B = 10752 B (a multiple of 16, as TMA wants)
+constexpr int kMeanPitch = kMeanChunk + 4;  // floats between product rows: 16-byte aligned, 4 banks apart
 __global__ void __launch_bounds__(kChainThreads) mean_exact_kernel(const float* __restrict__ particles, uint64_t n,
                                                                    float* __restrict__ out7)
 {
-  __shared__ float ring[2][kMeanChunk * 7];
+  __shared__ __align__(128) float raw[2][kMeanChunk * 7];
+  __shared__ __align__(16) float prod[2][7][kMeanPitch];
+  __shared__ __align__(8) uint64_t full_bar[2];
   const uint32_t tid = threadIdx.x;
-  const uint64_t nchunks = (n + kMeanChunk - 1) / kMeanChunk;
+  // bulk copies move multiples of 16 bytes = 4 records; up to three records at the end are read directly
+  const bool tma_ok = (reinterpret_cast<uintptr_t>(particles) & 15u) == 0;
+  const uint64_t n4 = tma_ok ? (n & ~(uint64_t)3) : 0;
+  const uint64_t nchunks = (n4 + kMeanChunk - 1) / kMeanChunk;
+  if (tid == 0)
+  {
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto count_of = [&](uint64_t c) { return (uint32_t)((n4 - c * kMeanChunk) < (uint64_t)kMeanChunk ? (n4 - c * kMeanChunk) : (uint64_t)kMeanChunk); };
+  auto issue = [&](uint64_t c) {
+    const uint32_t s = (uint32_t)(c & 1u);
+    mbar_expect_tx(&full_bar[s], count_of(c) * 28u);
+    tma_bulk_g2s(&raw[s][0], particles + c * kMeanChunk * 7, count_of(c) * 28u, &full_bar[s]);
+  };
+  if (tid == 0)
+    for (uint64_t c = 0; c < nchunks && c < 2; ++c)
+      issue(c);
   float acc = 0.f;  // lanes 0..5: the sum; lane 6: the max
   for (uint64_t c = 0; c < nchunks + 1; ++c)
   {
     if (tid >= 32)
     {
-      if (c < nchunks)
+      if (c < nchunks)  // products of chunk c, one chunk ahead of the chain
       {
-        float* dst = ring[c & 1];
-        const uint64_t base = c * kMeanChunk * 7;
-        const uint64_t lim = n * 7;
-        for (uint32_t k = tid - 32; k < kMeanChunk * 7; k += kChainThreads - 32)
-          dst[k] = (base + k < lim) ? particles[base + k] : 0.f;
+        const uint32_t s = (uint32_t)(c & 1u), cnt = count_of(c);
+        mbar_wait(&full_bar[s], (uint32_t)((c >> 1) & 1u));
+        for (uint32_t k = tid - 32; k < cnt; k += kChainThreads - 32)
+        {
+          const float* p = &raw[s][k * 7];
+          const float w = p[6];
+#pragma unroll
+          for (int e = 0; e < 6; ++e)
+            prod[s][e][k] = __fmul_rn(w, p[e]);
+          prod[s][6][k] = w;
+        }
       }
     }
     else if (tid < 7 && c >= 1)
     {
-      const float* buf = ring[(c - 1) & 1];
-      const uint64_t base = (c - 1) * kMeanChunk;
-      const int cntc = (int)((n - base) < (uint64_t)kMeanChunk ? (n - base) : (uint64_t)kMeanChunk);
+      const uint32_t s = (uint32_t)((c - 1) & 1u);
+      const int cnt = (int)count_of(c - 1);
+      const float* row = prod[s][tid];
+      int k = 0;
       if (tid < 6)
       {
-#pragma unroll 4
-        for (int k = 0; k < cntc; ++k)
-          acc = __fadd_rn(acc, __fmul_rn(buf[k * 7 + 6], buf[k * 7 + tid]));
+        for (; k + 16 <= cnt; k += 16)
+        {
+          float4 t[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            t[u] = *reinterpret_cast<const float4*>(row + k + 4 * u);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+          {
+            acc = __fadd_rn(acc, t[u].x);
+            acc = __fadd_rn(acc, t[u].y);
+            acc = __fadd_rn(acc, t[u].z);
+            acc = __fadd_rn(acc, t[u].w);
+          }
+        }
+        for (; k < cnt; ++k)
+          acc = __fadd_rn(acc, row[k]);
       }
       else
       {
-        for (int k = 0; k < cntc; ++k)
+        for (; k + 4 <= cnt; k += 4)
         {
-          const float w = buf[k * 7 + 6];
-          if (w > acc)
-            acc = w;
+          const float4 t = *reinterpret_cast<const float4*>(row + k);
+          acc = fmaxf(fmaxf(acc, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));  // w_max starts at 0 and only grows (ParticleFilter.cpp:210-211)
         }
+        for (; k < cnt; ++k)
+          acc = fmaxf(acc, row[k]);
       }
     }
-    __syncthreads();
+    __syncthreads();  // products of chunk c are complete, raw[c & 1] and prod[(c - 1) & 1] are free
+    if (tid == 0 && c + 2 < nchunks)
+      issue(c + 2);
   }
   if (tid < 7)
+  {
+    const uint32_t col = tid < 6 ? tid : 6u;
+    for (uint64_t i = n4; i < n; ++i)
+    {
+      const float w = particles[i * 7 + 6];
+      if (tid < 6)
+        acc = __fadd_rn(acc, __fmul_rn(w, particles[i * 7 + col]));
+      else
+        acc = fmaxf(acc, w);
+    }
     out7[tid] = acc;
+  }
 }
 
 // fast: deterministic f64 tree reduction of the f32 products

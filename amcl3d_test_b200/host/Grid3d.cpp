@@ -2,8 +2,10 @@
 #include "amcl3d/Grid3d.h"
 
 #include <cmath>
+#include <cstddef>
 #include <fstream>
 #include <sstream>
+#include <vector>
 
 #include "map_io.h"
 
@@ -176,14 +178,59 @@ bool Grid3d::loadPCD(std::string file_path, pcl::PointCloud<PointType>::Ptr& inp
     g_log->warn("couldn't load pcd file under " + file_path);
     return false;
   }
-  // the reference buckets the three clouds by keyframe id and concatenates surf, outlier, corner per keyframe
-  // (Grid3d.cpp:88-121); the voxel filter that follows only sees the union, so the union is built directly
-  merged += surf;
-  merged += outlier;
-  merged += corner;
+  // Grid3d.cpp:88-121: the three clouds are bucketed by keyframe id (the intensity channel) and concatenated per
+  // keyframe as surf, outlier, corner -- the order the voxel filter then sees (it decides the f32 summation order inside
+  // a leaf).  A point whose id is not a valid keyframe index is undefined behaviour in the reference; it is dropped here.
+  const size_t nkey = keyposes_3d->points.size();
+  std::vector<std::vector<uint32_t>> bucket[3];
+  const pcl::PointCloud<PointType>* src[3] = { &surf, &outlier, &corner };
+  for (int c = 0; c < 3; ++c)
+  {
+    bucket[c].resize(nkey);
+    for (size_t i = 0; i < src[c]->points.size(); ++i)
+    {
+      const float id = src[c]->points[i].intensity;
+      if (id >= 0.f && static_cast<size_t>(static_cast<int>(id)) < nkey)
+        bucket[c][static_cast<size_t>(static_cast<int>(id))].push_back(static_cast<uint32_t>(i));
+    }
+  }
+  merged.points.reserve(surf.size() + outlier.size() + corner.size());
+  for (size_t k = 0; k < nkey; ++k)
+    for (int c = 0; c < 3; ++c)
+      for (uint32_t i : bucket[c][k])
+        merged.points.push_back(src[c]->points[i]);
   if (!input)
     input.reset(new pcl::PointCloud<PointType>());
-  io::voxelGridFilter(merged, 0.3f, *input);  // Grid3d.cpp:127-130
+  // Grid3d.cpp:127-130: pcl::VoxelGrid at 0.3 m -- the device filter of the input downsample (csrc/voxelfilter.cu: f32 sums in
+  // input order, non-finite points skipped like PCL does for a non-dense cloud)
+  input->points.clear();
+  if (!merged.points.empty())
+  {
+    amcl3d_b200_pf_t tmp = nullptr;
+    if (amcl3d_b200_pf_create(handle_, &tmp) != AMCL3D_B200_OK)
+      throw_last("loadPCD: pf_create");
+    uint32_t kept = 0;
+    const int ioff = static_cast<int>(offsetof(PointType, intensity) / sizeof(float));
+    int rc = amcl3d_b200_pf_set_cloud_downsampled(tmp, &merged.points[0].x, kStride, ioff, static_cast<uint32_t>(merged.points.size()),
+                                                  0.3f, /*skip_nonfinite=*/1, &kept);
+    std::vector<float> xyzi(static_cast<size_t>(kept) * 4);
+    if (rc == AMCL3D_B200_OK && kept)
+      rc = amcl3d_b200_pf_get_cloud(tmp, xyzi.data(), kept, &kept);
+    amcl3d_b200_pf_destroy(tmp);
+    if (rc != AMCL3D_B200_OK)
+      throw_last("loadPCD: voxel filter");
+    input->points.resize(kept);
+    for (uint32_t i = 0; i < kept; ++i)
+    {
+      PointType& q = input->points[i];
+      q.x = xyzi[4 * i];
+      q.y = xyzi[4 * i + 1];
+      q.z = xyzi[4 * i + 2];
+      q.intensity = xyzi[4 * i + 3];
+    }
+  }
+  input->width = static_cast<uint32_t>(input->points.size());
+  input->height = 1;
   return true;
 }
 

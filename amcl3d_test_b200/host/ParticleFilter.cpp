@@ -61,6 +61,9 @@ ParticleFilter::ParticleFilter(VSCOMMON::LoggerPtr& log, int device)
 {
   p_.owner_ = this;
   check(amcl3d_b200_pf_create(grid3d_->handle(), &handle_), "ParticleFilter");
+  // stream order: a step that hands nothing back to the host (update, particleNormalize, resample ...) returns once it is
+  // launched; the host waits where it receives something (getMean, getBestParticle, reading p_)
+  check(amcl3d_b200_pf_set_async(handle_, 1), "set_async");
   devices_ = devices_from_env(device);
 }
 
@@ -68,6 +71,9 @@ ParticleFilter::ParticleFilter(int device) : grid3d_(new Grid3d(device)), genera
 {
   p_.owner_ = this;
   check(amcl3d_b200_pf_create(grid3d_->handle(), &handle_), "ParticleFilter");
+  // stream order: a step that hands nothing back to the host (update, particleNormalize, resample ...) returns once it is
+  // launched; the host waits where it receives something (getMean, getBestParticle, reading p_)
+  check(amcl3d_b200_pf_set_async(handle_, 1), "set_async");
   devices_ = devices_from_env(device);
 }
 
@@ -76,6 +82,9 @@ ParticleFilter::ParticleFilter(amcl3d_b200_grid_t borrowed_grid)
 {
   p_.owner_ = this;
   check(amcl3d_b200_pf_create(grid3d_->handle(), &handle_), "ParticleFilter");
+  // stream order: a step that hands nothing back to the host (update, particleNormalize, resample ...) returns once it is
+  // launched; the host waits where it receives something (getMean, getBestParticle, reading p_)
+  check(amcl3d_b200_pf_set_async(handle_, 1), "set_async");
   amcl3d_b200_grid_info_t info;
   check(amcl3d_b200_grid_get_info(borrowed_grid, &info), "grid_get_info");
   devices_ = devices_from_env(info.device);
@@ -461,7 +470,7 @@ extern "C" __attribute__((visibility("default"))) int amcl3d_host_bench_frames(a
                                                                                 uint64_t n, const float* cloud_xyz, uint32_t npts,
                                                                                 int steps, int warmup, double* ms_per_frame,
                                                                                 float mean7[7], const int* devices, int n_devices,
-                                                                                uint64_t* transfers2)
+                                                                                uint64_t* transfers2, double* phase_ms6)
 {
   try
   {
@@ -484,6 +493,7 @@ extern "C" __attribute__((visibility("default"))) int amcl3d_host_bench_frames(a
     std::vector<Particle> fresh(src, src + n);
     Particle m;
     double checksum = 0;
+    double phase[6] = { 0, 0, 0, 0, 0, 0 };
     uint64_t up0 = 0, down0 = 0;
     std::chrono::steady_clock::time_point t0;
     for (int s = 0; s < warmup + steps; ++s)
@@ -494,14 +504,31 @@ extern "C" __attribute__((visibility("default"))) int amcl3d_host_bench_frames(a
         up0 = pf.p_.uploads();
         down0 = pf.p_.downloads();
       }
+      typedef std::chrono::steady_clock clk;
+      const clk::time_point a0 = clk::now();
       pf.p_ = fresh;  // the host hands over this frame's particles
+      const clk::time_point a1 = clk::now();
       pf.update(cloud);
+      const clk::time_point a2 = clk::now();
       pf.particleNormalize();
+      const clk::time_point a3 = clk::now();
       pf.resample();
+      const clk::time_point a4 = clk::now();
       m = pf.getMean();
+      const clk::time_point a5 = clk::now();
       const std::vector<Particle>& out = pf.p_;  // the host looks at the resampled set
       checksum += out[out.size() / 2].x;
+      const clk::time_point a6 = clk::now();
+      if (s >= warmup)
+      {
+        const clk::time_point t[7] = { a0, a1, a2, a3, a4, a5, a6 };
+        for (int k = 0; k < 6; ++k)
+          phase[k] += std::chrono::duration<double, std::milli>(t[k + 1] - t[k]).count();
+      }
     }
+    if (phase_ms6)
+      for (int k = 0; k < 6; ++k)
+        phase_ms6[k] = phase[k] / (steps > 0 ? steps : 1);
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (ms_per_frame)
       *ms_per_frame = ms / (steps > 0 ? steps : 1);

@@ -74,6 +74,12 @@ int loadPCDFile(const std::string& path, pcl::PointCloud<PointType>& cloud)
   }
   if (npoints == 0)
     npoints = width * height;
+  // a malformed header (SIZE / COUNT of 0 or below, absurd sizes) is rejected like a missing file
+  for (const auto& fd : fields)
+    if (fd.size <= 0 || fd.size > 8 || fd.count <= 0 || fd.count > (1 << 20))
+      return -1;
+  if (npoints > (size_t(1) << 33))
+    return -1;
   size_t step = 0;
   int fx = -1, fy = -1, fz = -1, fi = -1;
   for (size_t i = 0; i < fields.size(); ++i)
@@ -158,61 +164,5 @@ int savePCDFile(const std::string& path, const pcl::PointCloud<PointType>& cloud
   return f ? 0 : -1;
 }
 
-void voxelGridFilter(const pcl::PointCloud<PointType>& in, float leaf, pcl::PointCloud<PointType>& out)
-{
-  out.points.clear();
-  if (in.points.empty() || !(leaf > 0))
-    return;
-  float lo[3] = { std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max() };
-  float hi[3] = { -lo[0], -lo[1], -lo[2] };
-  for (const auto& p : in.points)
-  {
-    const float v[3] = { p.x, p.y, p.z };
-    for (int a = 0; a < 3; ++a)
-    {
-      lo[a] = std::min(lo[a], v[a]);
-      hi[a] = std::max(hi[a], v[a]);
-    }
-  }
-  long mn[3], dv[3];
-  for (int a = 0; a < 3; ++a)
-  {
-    mn[a] = static_cast<long>(std::floor(lo[a] / leaf));
-    dv[a] = static_cast<long>(std::floor(hi[a] / leaf)) - mn[a] + 1;
-  }
-  std::vector<std::pair<long, uint32_t>> keyed(in.points.size());
-  for (size_t i = 0; i < in.points.size(); ++i)
-  {
-    const auto& p = in.points[i];
-    const long ix = static_cast<long>(std::floor(p.x / leaf)) - mn[0];
-    const long iy = static_cast<long>(std::floor(p.y / leaf)) - mn[1];
-    const long iz = static_cast<long>(std::floor(p.z / leaf)) - mn[2];
-    keyed[i] = { ix + iy * dv[0] + iz * dv[0] * dv[1], static_cast<uint32_t>(i) };
-  }
-  std::sort(keyed.begin(), keyed.end());
-  for (size_t i = 0; i < keyed.size();)
-  {
-    size_t j = i;
-    double s[4] = { 0, 0, 0, 0 };
-    for (; j < keyed.size() && keyed[j].first == keyed[i].first; ++j)
-    {
-      const auto& p = in.points[keyed[j].second];
-      s[0] += p.x;
-      s[1] += p.y;
-      s[2] += p.z;
-      s[3] += p.intensity;
-    }
-    const double n = static_cast<double>(j - i);
-    PointType c;
-    c.x = static_cast<float>(s[0] / n);
-    c.y = static_cast<float>(s[1] / n);
-    c.z = static_cast<float>(s[2] / n);
-    c.intensity = static_cast<float>(s[3] / n);
-    out.points.push_back(c);
-    i = j;
-  }
-  out.width = static_cast<uint32_t>(out.points.size());
-  out.height = 1;
-}
 }  // namespace io
 }  // namespace amcl3d

@@ -53,13 +53,31 @@ STRONG = {"C4", "C5s", "C5"}
 BEACONS = {"C5s", "C5"}
 
 
+def config_for(workload, kind, world):
+    """The `config` object of the line: names the workload and nothing run-specific, so the B200 arm and the reference
+    arm (which times a bounded sample of the same workload on the host cores) print the identical object."""
+    extent, resol, n_per_gpu, n_pts, _ = WORKLOADS[workload]
+    strong = workload in STRONG
+    n_total = n_per_gpu if strong else n_per_gpu * world
+    size = [int(round(e / resol)) for e in extent]
+    cells = size[0] * size[1] * size[2]
+    return {
+        "workload": f"{workload}: {n_total // world} particles/GPU x {n_pts}-point cloud, map {extent[0]:g}x{extent[1]:g}x{extent[2]:g} m "
+                    f"at {resol} m = {size[0]}x{size[1]}x{size[2]} voxels ({cells*4/1e9:.2f} GB float grid replica per GPU), "
+                    "step = update + normalise + resample + mean"
+                    + (" with 8 UWB range beacons fused" if workload in BEACONS else ""),
+        "particles_kind": kind, "particles_total": n_total, "points": n_pts,
+        "l2": "inputs larger than L2 (grid replica >> 126 MB), no flush",
+    }
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS) + ["C2"])
     ap.add_argument("--particles", default="T", choices=["T", "G"], help="tracking cluster / global uniform")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the config-4 strong-scaling section of the default run")
@@ -270,9 +288,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {n_sample}-particle bounded sample of the per-GPU block x {n_pts} points, "
-                               f"{args.particles} particles, map cropped to the cloud radius at {resol} m",
-                   "particles_kind": args.particles},
+        "config": config_for(args.workload, args.particles, max(1, args.gpus)),
+        "sample": f"{n_sample}-particle bounded sample of the per-GPU block x {n_pts} points per step, map cropped to the cloud radius "
+                  f"at {resol} m (identical voxels where the cloud lands)",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": r["kind"],
                          "sample": f"{n_sample} particles x {n_pts} points per step, {threads} host threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -779,16 +797,10 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {
-            "workload": f"{args.workload}: {n_local} particles/GPU x {n_pts}-point cloud, map {extent[0]:g}x{extent[1]:g}x{extent[2]:g} m "
-                        f"at {resol} m = {info['size'][0]}x{info['size'][1]}x{info['size'][2]} voxels "
-                        f"({info['n_cells']*4/1e9:.2f} GB float grid, {info['coded_bytes']/1e9:.2f} GB coded replica per GPU), "
-                        "step = update + normalise + resample + mean"
-                        + (" with 8 UWB range beacons fused" if beacons is not None else ""),
-            "particles_kind": args.particles, "particles_total": n_total, "points": n_pts,
-            "l2": "inputs larger than L2 (grid replica >> 126 MB), no flush",
-            "in_bounds_fraction": n_in / (n_local * n_pts),
-            "grid_build_s_incl_h2d": grid_build_s,
+        "config": config_for(args.workload, args.particles, world),
+        "details": {
+            "coded_grid_bytes_per_gpu": info["coded_bytes"], "grid_size": list(info["size"]),
+            "in_bounds_fraction": n_in / (n_local * n_pts), "grid_build_s_incl_h2d": grid_build_s,
             "exchange": "none (1 GPU)" if world == 1 else "peer-memory stores/loads over NVLink in the library's own kernels (csrc/shard.cu), no NCCL on the data path",
         },
         "update_ms": upd, "resample_mean_ms": ms_step - upd,
@@ -844,22 +856,69 @@ def cpp_class_e2e(grid, P, cloud, steps):
     fn = lib.amcl3d_host_bench_frames
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p,
-                   C.c_void_p, C.c_int, C.c_void_p]
+                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     Pc = np.ascontiguousarray(P, np.float32)
     cl = np.ascontiguousarray(cloud[:, :3], np.float32)
     ms = C.c_double(0)
     mean = np.zeros(7, np.float32)
     moved = np.zeros(2, np.uint64)
+    phase = np.zeros(6, np.float64)
     rc = fn(grid._h, Pc.ctypes.data, Pc.shape[0], cl.ctypes.data, cl.shape[0], steps, 2, C.byref(ms), mean.ctypes.data, None, 0,
-            moved.ctypes.data)
+            moved.ctypes.data, phase.ctypes.data)
     if rc != 0:
         raise RuntimeError(f"amcl3d_host_bench_frames rc={rc}")
     n = Pc.shape[0] * cl.shape[0]
     return {"value": n / (ms.value * 1e-3), "unit": UNIT, "ms_per_step": ms.value,
             "h2d_bytes_per_step": int(Pc.nbytes + cl.shape[0] * 16), "d2h_bytes_per_step": int(Pc.nbytes + 28),
             "set_uploads_per_step": float(moved[0]) / steps, "set_downloads_per_step": float(moved[1]) / steps,
-            "what": "amcl3d::ParticleFilter (C++ class, pageable std::vector p_): p_ = particles; update(cloud); particleNormalize(); "
+            "host_ms_per_call": dict(zip(["p_ = particles", "update (launch only)", "particleNormalize (launch only)",
+                                          "resample (launch only)", "getMean (waits for the step)", "read p_ (D2H)"],
+                                         [float(v) for v in phase])),
+            "what": "amcl3d::ParticleFilter (C++ class, std::vector p_ page-locked by the mirror, bit-exact getMean): p_ = particles; update(cloud); particleNormalize(); "
                     "resample(); getMean(); read p_ -- lazily synced host mirror: one H2D and one D2H of the set per frame"}
+
+
+def run_c2(args):
+    """python bench.py --workload C2: BASELINE config 2 on its own -- the probability-grid build at 100 x 100 x 20 m, 0.05 m.
+    value = voxels per second of the build kernels (CUDA events on the build stream, best of the timed builds)."""
+    import torch
+
+    from amcl3d_test_b200 import Grid3d, synth
+
+    cfg = synth.CONFIGS["C2"]
+    sm = synth.make_map(cfg["extent"], cfg["resol"])
+    grid = Grid3d(0)
+    grid.computePointCloud(sm.points, cfg["resol"])
+    sampler = None
+    ms, wall = [], []
+    for k in range(args.warmup + args.steps):
+        if k == args.warmup:
+            sampler = ClockSampler(0)
+            sampler.start()
+        t0 = time.time()
+        grid.computeGrid(sm.points, 0.05, sub=2)
+        if k >= args.warmup:
+            wall.append(time.time() - t0)
+            ms.append(grid.last_build_ms())
+    clocks = sampler.stop()
+    info = grid.info()
+    hbm_peak, hbm_src = measured_peaks()
+    sec = c2_section(grid, info, int(sm.points.shape[0]), ms, float(np.min(wall)), hbm_peak, not args.no_cpu_baseline)
+    best = sec["kernels_ms"]
+    line = {"metric": "grid_build_voxels_per_sec", "value": sec["voxels_per_sec"], "unit": "voxels/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": best, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
+            "data": "synthetic", "config": {"workload": sec["workload"], "l2": "inputs larger than L2 (5 GB of intermediates), no flush"},
+            "roofline": dict(sec["roofline"], traffic=None, peak_source=hbm_src),
+            "e2e": {"value": info["n_cells"] / float(np.min(wall)), "unit": "voxels/s", "h2d_bytes_per_step": int(sm.points.nbytes),
+                    "d2h_bytes_per_step": 0, "ms_per_step": float(np.min(wall)) * 1e3,
+                    "what": "Grid3d.computeGrid from HOST map points: H2D of the points, workspace allocation, the build, free"},
+            "kernels_ms_all_builds": sec["kernels_ms_all_builds"], "clocks": clocks, "gpu_launches": 9 * args.steps}
+    if "cpu_reference_1core" in sec:
+        c = sec["cpu_reference_1core"]
+        if "voxels_per_sec" in c:
+            line["cpu_baseline"] = {"value": c["voxels_per_sec"], "unit": "voxels/s", "cores": 1, "kind": c["kind"], "sample": c["sample"]}
+    del torch
+    print(json.dumps(line))
 
 
 def main():
@@ -869,7 +928,13 @@ def main():
     real_out = os.dup(1)
     os.dup2(2, 1)
     sys.stdout = os.fdopen(real_out, "w", buffering=1)
-    if args.impl == "reference":
+    if args.workload == "C2":
+        if args.impl == "reference":
+            raise SystemExit("--workload C2 has no reference arm of its own: its line carries cpu_baseline (computeGrid on a crop)")
+        if args.steps == 100:
+            args.steps = 5  # a build is tens of ms plus 0.7 GB of H2D: the default of the update loop is too many
+        run_c2(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

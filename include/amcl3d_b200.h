@@ -97,7 +97,7 @@ int amcl3d_b200_host_unpin(void* ptr);
 
 /* cudaLimitMaxL2FetchGranularity of the device (32, 64 or 128 bytes) -- a measurement knob.  The library never
  * changes this limit of the host application on its own (only when AMCL3D_B200_L2_FETCH is set in the
- * environment or through this call).  Measured on B200 (profiles/r2_gather_microbench.json): a scattered 1-byte
+ * environment or through this call).  Measured on B200 (profiles/r2_gather_probe_ncu.txt): a scattered 1-byte
  * gather that misses L2 costs a full 128-byte line of DRAM traffic at every setting, 32, 64 and 128 alike. */
 int amcl3d_b200_set_l2_fetch_granularity(int device, int bytes);
 int amcl3d_b200_get_l2_fetch_granularity(int device, int* bytes);

@@ -109,6 +109,15 @@ def test_cpp_classes_match_the_oracle(O, tmp_path):
     assert d["open_missing_dir"][0, 0] == 0 and d["open_ok"][0, 0] == 1 and d["open_cached_ok"][0, 0] == 1
     fc = d["open_filtered_cloud"]
     assert 10 < fc.shape[0] < sm.points.shape[0]
+    # loadPCD (Grid3d.cpp:88-130): points bucketed by keyframe id (intensity = i % 5), concatenated per keyframe as surf,
+    # outlier, corner, then pcl::VoxelGrid at 0.3 m -- the oracle's restatement of that filter on the same order
+    n_map = sm.points.shape[0]
+    ids = np.arange(n_map)
+    kind = ids % 3  # the driver deals the map points out as corner (0), surf (1), outlier (2)
+    order = np.concatenate([ids[(ids % 5 == k) & (kind == c)] for k in range(5) for c in (1, 2, 0)])
+    merged = np.concatenate([sm.points[order], (order % 5).astype(np.float32)[:, None]], 1)
+    ref_fc = O.voxel_filter(merged, 0.3, ioff=3)
+    assert np.array_equal(bits(fc), bits(ref_fc[:, :3]))
     fmn, fmx = O.compute_bounds(fc)
     fm = O.Map(fmn, fmx, 0.3, 0.05)
     assert list(d["open_size"][0]) == list(fm.size)

@@ -132,12 +132,13 @@ def main():
             Wn = ref[0][0].copy()
             pfx = exact_prefix(g, Wn)
             um = np.float32(u01s[0]) * (np.float32(1.0) / np.float32(n)) + (np.float32(1.0) / np.float32(n)) * np.arange(lo, hi, dtype=np.float32)
-            eps = np.float32(4e-6)
+            # accumulated rounding of a sequential f32 sum of n terms below 1 is a random walk of ~sqrt(n) half-ulps
+            eps = np.float32(8.0 * np.sqrt(n) * 2.0 ** -24)
             upper_ok = um <= pfx[idx] + eps
             lower_ok = (idx == 0) | (um > np.where(idx > 0, pfx[np.maximum(idx - 1, 0)], np.float32(0)) - eps)
             tail = idx == n - 1
             if not np.all((upper_ok | tail) & lower_ok):
-                print(f"rank {rank} fast n={n} {kind}: an index is not within {eps} of the exact prefix interval")
+                print(f"rank {rank} fast n={n} {kind}: an index is not within {eps} (f32 summation noise) of the exact prefix interval")
                 ok = False
             if rank == 0 and rep == 0:
                 print(f"fast mode n={n} {kind} world={world}: {int(tot.item())} of {n} resampled indices differ from the exact mode")

@@ -153,3 +153,67 @@ def test_two_ranks_one_process_per_gpu():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "OK bit-identical to 1 GPU" in r.stdout
+
+
+def test_grid_clone_gives_the_same_weights(O):
+    """amcl3d_b200_grid_clone: a replica (coded cells only, and with the float cells) drives update() to the same bits; a
+    codes-only replica refuses to hand out float cells it does not hold."""
+    from amcl3d_test_b200 import ParticleFilter, synth
+    from amcl3d_test_b200.capi import check  # noqa: F401
+
+    sm, g = _world(0)
+    cloud = synth.make_cloud(sm, 1500, 9.0)
+    P = synth.make_particles(sm, 9000, "T")
+    pf = ParticleFilter(g)
+    pf.p_ = P
+    pf.update(cloud)
+    want = pf.p_
+    dev = 1 if _device_count() >= 2 else 0
+    for with_float in (False, True):
+        r = g.clone(dev, with_float=with_float)
+        assert r.info()["size"] == g.info()["size"] and r.info()["lut_n"] == g.info()["lut_n"] and r.info()["device"] == dev
+        q = ParticleFilter(r)
+        q.p_ = P
+        q.update(cloud)
+        assert np.array_equal(bits(q.p_), bits(want))
+        if with_float:
+            assert np.array_equal(bits(r.downloadGrid()), bits(g.downloadGrid()))
+        else:
+            with pytest.raises(RuntimeError):
+                r.downloadGrid()
+
+
+def test_shard_calls_fail_loudly_when_misused():
+    """Bad geometry, calls before the peers are attached, a block that does not match the partition."""
+    import ctypes as C
+
+    from amcl3d_test_b200 import ParticleFilter, capi, synth
+
+    sm, g = _world(0)
+    L = capi.load()
+    pf = ParticleFilter(g)
+    assert L.amcl3d_b200_pf_shard_init(pf._h, 0, 0, 1) == capi.ERR_ARG          # no particles
+    assert L.amcl3d_b200_pf_shard_init(pf._h, 100, 3, 2) == capi.ERR_ARG        # rank outside the world
+    assert L.amcl3d_b200_pf_shard_init(pf._h, 100, 0, 17) == capi.ERR_ARG       # more ranks than the exchange region holds
+    assert L.amcl3d_b200_pf_shard_resample(pf._h, C.c_float(0.5), 1, None, C.c_float(1.0), None) == capi.ERR_STATE  # not sharded
+    assert L.amcl3d_b200_pf_shard_init(pf._h, 1000, 0, 2) == capi.OK
+    assert L.amcl3d_b200_pf_shard_init(pf._h, 1000, 0, 2) == capi.ERR_STATE     # twice
+    assert L.amcl3d_b200_pf_shard_resample(pf._h, C.c_float(0.5), 1, None, C.c_float(1.0), None) == capi.ERR_STATE  # peers not attached
+    assert L.amcl3d_b200_pf_shard_mean(pf._h, None, None) == capi.ERR_ARG
+    lo, hi, nbytes = pf.shard_info()
+    assert (lo, hi) == (0, 500) and nbytes > 2 * 500 * 28 + 2 * 1000 * 4
+    assert len(pf.shard_ipc_handle()) == 64
+
+
+def test_host_pin_roundtrip():
+    import ctypes as C
+
+    from amcl3d_test_b200 import capi
+
+    L = capi.load()
+    buf = np.zeros(1 << 20, np.uint8)
+    assert L.amcl3d_b200_host_pin(C.c_void_p(buf.ctypes.data), buf.nbytes) == capi.OK
+    assert L.amcl3d_b200_host_pin(C.c_void_p(buf.ctypes.data), buf.nbytes) == capi.OK   # registering again re-registers
+    assert L.amcl3d_b200_host_unpin(C.c_void_p(buf.ctypes.data)) == capi.OK
+    assert L.amcl3d_b200_host_unpin(C.c_void_p(buf.ctypes.data)) != capi.OK             # nothing left to release
+    assert L.amcl3d_b200_host_pin(None, 16) == capi.ERR_ARG

@@ -51,6 +51,10 @@ class ParticleFilter;
 class ParticleMirror
 {
 public:
+  ParticleMirror() {}
+  ~ParticleMirror() { unpin(); }
+  ParticleMirror(const ParticleMirror&) = delete;
+  ParticleMirror& operator=(const ParticleMirror& o) { return *this = o.host(); }  // pf.p_ = other.p_ copies the set
   typedef Particle value_type;
   typedef std::vector<Particle>::iterator iterator;
   typedef std::vector<Particle>::const_iterator const_iterator;
@@ -133,9 +137,6 @@ private:
     host_fresh_ = true;
     dev_fresh_ = false;
   }
-  ~ParticleMirror() { unpin(); }
-  ParticleMirror() {}
-  ParticleMirror(const ParticleMirror&) = delete;
   // the vector's buffer is page-locked once it is large enough to matter (>= 256 KB) and re-registered when the vector
   // reallocated: the set then crosses PCIe as one DMA transfer each way
   void pin() const

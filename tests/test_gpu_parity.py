@@ -729,3 +729,40 @@ def test_stream_ordered_calls_give_the_same_bits(O, world_c1, gpu_c1):
     b.mean_device(buf.data_ptr())
     b.sync()
     assert np.allclose(buf.cpu().numpy(), O.mean(out), rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 383, 384, 385, 771, 1155, 100_003])
+def test_exact_mean_ring_edges(O, gpu_c1, n):
+    """mean_exact_kernel streams the records through a TMA ring in chunks of 384 and reads up to three tail records
+    directly: every chunk / tail boundary against the oracle's sequential chains (ParticleFilter.cpp:198-216), with signed
+    coordinates so that the six chains cancel and re-grow."""
+    from amcl3d_test_b200 import ParticleFilter
+
+    rng = np.random.RandomState(1000 + n)
+    P = np.zeros((n, 7), np.float32)
+    P[:, :6] = rng.normal(0, 30, (n, 6)).astype(np.float32)
+    P[:, 6] = (rng.uniform(0, 1, n) ** 4 / n).astype(np.float32)
+    P[rng.randint(0, n, max(1, n // 7)), 6] = 0
+    pf = ParticleFilter(gpu_c1)
+    pf.p_ = P
+    assert np.array_equal(bits(pf.getMean(exact=True)), bits(O.mean(O.particles(P))))
+
+
+def test_exact_mean_on_a_buffer_that_is_not_16_byte_aligned(O, gpu_c1):
+    """A bound device buffer 4 bytes off a 16-byte boundary: the bulk copies cannot be used, the records are read directly."""
+    import torch
+
+    from amcl3d_test_b200 import ParticleFilter
+
+    n = 2050
+    rng = np.random.RandomState(5)
+    P = np.zeros((n, 7), np.float32)
+    P[:, :6] = rng.normal(0, 10, (n, 6)).astype(np.float32)
+    P[:, 6] = (rng.uniform(0, 1, n) / n).astype(np.float32)
+    buf = torch.zeros(7 * n + 1, dtype=torch.float32, device="cuda:0")
+    view = buf[1:]
+    assert view.data_ptr() % 16 == 4
+    view.copy_(torch.from_numpy(P.reshape(-1)))
+    pf = ParticleFilter(gpu_c1)
+    pf.bind_device(view.data_ptr(), n, n, keep=buf)
+    assert np.array_equal(bits(pf.getMean(exact=True)), bits(O.mean(O.particles(P))))

@@ -106,6 +106,7 @@ void ParticleFilter::pull(std::vector<Particle>& out) const
 {
   if (!p_.dev_fresh_)
     throw std::logic_error("ParticleFilter: neither the host nor a device holds the current set");
+  p_.will_hold(p_.dev_n_);
   out.resize(p_.dev_n_);
   p_.pin();
   if (where_ == kSingle)

@@ -82,24 +82,28 @@ public:
   // whole-set replacement: nothing is pulled from the device first
   ParticleMirror& operator=(const std::vector<Particle>& v)
   {
+    will_hold(v.size());
     host_ = v;
     replaced();
     return *this;
   }
   ParticleMirror& operator=(std::vector<Particle>&& v)
   {
+    unpin();  // the buffer itself is replaced
     host_ = std::move(v);
     replaced();
     return *this;
   }
   void assign(size_t n, const Particle& v)
   {
+    will_hold(n);
     host_.assign(n, v);
     replaced();
   }
   template <class It>
   void assign(It first, It last)
   {
+    unpin();
     host_.assign(first, last);
     replaced();
   }
@@ -110,12 +114,29 @@ public:
   }
   void swap(std::vector<Particle>& v)
   {
+    unpin();
     edit().swap(v);
   }
-  void resize(size_t n) { edit().resize(n); }
-  void resize(size_t n, const Particle& v) { edit().resize(n, v); }
-  void reserve(size_t n) { host_.reserve(n); }
-  void push_back(const Particle& v) { edit().push_back(v); }
+  void resize(size_t n)
+  {
+    will_hold(n);
+    edit().resize(n);
+  }
+  void resize(size_t n, const Particle& v)
+  {
+    will_hold(n);
+    edit().resize(n, v);
+  }
+  void reserve(size_t n)
+  {
+    will_hold(n);
+    host_.reserve(n);
+  }
+  void push_back(const Particle& v)
+  {
+    will_hold(size() + 1);
+    edit().push_back(v);
+  }
 
   /*! Read-only view, pulled from the device if a device step changed the set since the last look. */
   const std::vector<Particle>& host() const;
@@ -151,6 +172,12 @@ private:
       pinned_ptr_ = ptr;
       pinned_bytes_ = bytes;
     }
+  }
+  // a page-locked buffer is released BEFORE the vector may reallocate it away
+  void will_hold(size_t n) const
+  {
+    if (n > host_.capacity())
+      unpin();
   }
   void unpin() const
   {

@@ -256,7 +256,18 @@ def cpu_baseline(workload, kind, target_seconds):
     n_sample = int(max(64 * threads, min(200_000, target_seconds * rate / n_pts)))
     r = run_cpu_sample(workload, kind, n_sample, threads, setup=setup)
     t = r["t_update"] + r["t_resample"]
+    one = None
+    try:
+        n1 = int(max(64, min(4000, 3.0 * rate / threads / n_pts)))
+        r1 = run_cpu_sample(workload, kind, n1, 1, reps=2, setup=setup)
+        t1 = r1["t_update"] + r1["t_resample"]
+        one = {"value": r1["evals"] / t1, "unit": UNIT, "cores": 1,
+               "sample": f"{n1} particles x {n_pts} points on one host thread (the reference is single-threaded, "
+                         "amcl3d/CMakeLists.txt:9), best of 2; scales linearly in particles"}
+    except Exception as e:
+        one = {"error": repr(e)}
     return {
+        "one_core": one,
         "value": r["evals"] / t, "unit": UNIT, "cores": threads, "kind": r["kind"],
         "sample": f"{n_sample} particles x {n_pts} points of the {workload} workload ({kind} particles), "
                   f"update {r['t_update']*1e3:.0f} ms + normalise/resample/mean {r['t_resample']*1e3:.0f} ms, "
@@ -742,6 +753,17 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         wall = float(t.item())
     e2e_value = evals_step * args.steps / wall   # evals_step counts all ranks; wall is the max over ranks
+    # SURVEY 8(d) metric (ii): update + resample ms "H2D of the cloud included": the per-frame cloud preparation (H2D from the
+    # pinned host buffer, packing, Morton sort) timed on its own with CUDA events, added to the resident step
+    ec0, ec1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cloud_ms = []
+    for _ in range(10):
+        ec0.record(stream)
+        filt.set_cloud(pin_c.numpy())
+        ec1.record(stream)
+        torch.cuda.synchronize()
+        cloud_ms.append(ec0.elapsed_time(ec1))
+    cloud_ms = float(np.median(cloud_ms))
     h2d = int(pin_p.numel() * 4 + pin_c.numel() * 4)
     d2h = int(pin_out.numel() * 4 + 28)
 
@@ -804,6 +826,7 @@ def run_b200(args):
             "exchange": "none (1 GPU)" if world == 1 else "peer-memory stores/loads over NVLink in the library's own kernels (csrc/shard.cu), no NCCL on the data path",
         },
         "update_ms": upd, "resample_mean_ms": ms_step - upd,
+        "update_resample_ms_incl_cloud_h2d": ms_step + cloud_ms, "cloud_h2d_pack_sort_ms": cloud_ms,
         "update_evals_per_sec": n_local * n_pts / (upd * 1e-3) * world,
         "roofline": roof,
         "gather_peaks_loads_per_sec": peaks,

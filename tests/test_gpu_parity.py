@@ -766,3 +766,33 @@ def test_exact_mean_on_a_buffer_that_is_not_16_byte_aligned(O, gpu_c1):
     pf = ParticleFilter(gpu_c1)
     pf.bind_device(view.data_ptr(), n, n, keep=buf)
     assert np.array_equal(bits(pf.getMean(exact=True)), bits(O.mean(O.particles(P))))
+
+
+@pytest.mark.parametrize("n,npts", [(1, 256), (7, 300), (255, 2000), (256, 257), (257, 2000), (600, 2000), (600, 255)])
+def test_small_sets_take_the_sweep_path_bit_exactly(O, n, npts):
+    """The pose + Morton sweep + ordered-sum path is used from ONE particle on (it parallelises over cloud chunks, which is
+    what a small set needs): ragged particle tiles and clouds of barely two chunks against the oracle, and a cloud below
+    two chunks (255 points) through the single kernel."""
+    from amcl3d_test_b200 import Grid3d, ParticleFilter, synth
+
+    sm = synth.make_map((20.0, 20.0, 5.0), 0.1)
+    g = Grid3d(0)
+    mn, mx = g.computePointCloud(sm.points, 0.1)
+    g.computeGrid(sm.points, 0.05, sub=2)
+    assert g.info()["rep"] == 1  # u8 dictionary codes
+    m = O.Map(mn, mx, 0.1, 0.05)
+    m.set_prob(g.downloadGrid())
+    cloud = synth.make_cloud(sm, npts, 12.0)
+    P = synth.make_particles(sm, max(n, 2), "T")[:n]
+    P[::5, :3] += 30.0  # some particles outside the map
+    pf = ParticleFilter(g)
+    pf.p_ = P
+    n_in = pf.update(cloud, count=True)
+    swept = pf.last_phase_ms()[1] > 0
+    assert swept == (npts >= 256)
+    ref = O.update(m, O.particles(P), cloud)
+    assert np.array_equal(bits(pf.p_), bits(ref))
+    assert n_in == O.count_in_bounds(m, O.particles(P), cloud)
+    # the single pose of Grid3d::computeCloudWeight goes the same way (Grid3d.cpp:234-301)
+    w = g.computeCloudWeight(cloud, *P[0, :6])
+    assert bits(w) == bits(O.cloud_weight(m, cloud, P[0, :6]))

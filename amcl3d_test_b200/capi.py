@@ -3,6 +3,7 @@ if libamcl3d_b200.so is missing it is built with nvcc; if that fails the import 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 from . import build as _build
@@ -74,6 +75,8 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB
+    if os.environ.get("AMCL3D_B200_LIB"):  # tuning sweeps: a variant of the library built with other kernel parameters
+        path = Path(os.environ["AMCL3D_B200_LIB"])
     if not path.exists():
         _build.build_native()
     L = C.CDLL(str(path))

@@ -1053,6 +1053,8 @@ int amcl3d_b200_pf_bind_device(amcl3d_b200_pf_t pf, void* d_aos7, uint64_t n, ui
 {
   if (!pf || !d_aos7 || n > capacity || capacity >= (1ull << 31))
     return fail(AMCL3D_B200_ERR_ARG, "bad device buffer");
+  if (pf->shard.on)
+    return fail(AMCL3D_B200_ERR_STATE, "a sharded handle keeps p_ inside its exchange region");
   if (!pf->external)
     cudaFree(pf->d_p);
   pf->d_p = reinterpret_cast<float*>(d_aos7);
@@ -1864,6 +1866,8 @@ int amcl3d_b200_pf_shard_attach_ipc(amcl3d_b200_pf_t pf, const void* handles, si
   if (int rc = use_device(pf->grid->device))
     return rc;
   amcl3d_b200_pf_s::Shard& S = pf->shard;
+  if (S.attached && S.world > 1)
+    return fail(AMCL3D_B200_ERR_STATE, "peers are already attached");
   for (uint32_t r = 0; r < S.world; ++r)
   {
     if (r == S.rank)

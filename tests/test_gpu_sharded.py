@@ -202,6 +202,7 @@ def test_shard_calls_fail_loudly_when_misused():
     assert L.amcl3d_b200_pf_shard_mean(pf._h, None, None) == capi.ERR_ARG
     lo, hi, nbytes = pf.shard_info()
     assert (lo, hi) == (0, 500) and nbytes > 2 * 500 * 28 + 2 * 1000 * 4
+    assert L.amcl3d_b200_pf_bind_device(pf._h, C.c_void_p(256), 1, 1) == capi.ERR_STATE  # p_ lives in the exchange region
     assert len(pf.shard_ipc_handle()) == 64
 
 

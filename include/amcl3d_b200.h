@@ -181,8 +181,11 @@ int amcl3d_b200_pf_set_async(amcl3d_b200_pf_t pf, int enable);
 int amcl3d_b200_pf_sync(amcl3d_b200_pf_t pf);
 /* enable (default) / disable the two-phase update: phase 1 sweeps the cloud in Morton order (so that all
  * particles work in the same neighbourhood of the map at the same time) and parks 1-byte codes, phase 2 adds
- * them in the original cloud order -- bit-identical weights, ~1.4x faster on large grids.  Takes effect at
- * the next set_cloud.  Environment AMCL3D_B200_TWO_PHASE=0 sets the default for new handles. */
+ * them in the original cloud order -- bit-identical weights.  Used for u8-coded (device-built) grids and clouds of at
+ * least 256 points, from ONE particle on: it parallelises over (particle tile, cloud chunk) pairs, which is what a
+ * small set needs too (600 x 2 000: 0.34 -> 0.07 ms; 100 k x 10 k: 27.9 -> 4.1 ms against the one-launch path on the
+ * float grid).  Takes effect at the next update (the Morton order is built lazily).  Environment
+ * AMCL3D_B200_TWO_PHASE=0 sets the default for new handles. */
 int amcl3d_b200_pf_set_two_phase(amcl3d_b200_pf_t pf, int enable);
 /* run this handle's kernels on a caller-owned cudaStream_t (NULL = the handle's own non-blocking stream; pass
  * cudaStreamLegacy / cudaStreamPerThread explicitly to order with the default stream) */

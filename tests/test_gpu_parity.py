@@ -483,7 +483,7 @@ def test_resample_one_million_bit_exact(O, world_c1, pf):
 
 @pytest.mark.parametrize("kind", ["T", "G"])
 def test_two_phase_update_is_bit_identical(O, world_c1, kind):
-    """>= 4096 particles on a device-built (u8-coded) grid take the two-phase path (Morton sweep + ordered sum):
+    """A device-built (u8-coded) grid and a cloud of two chunks or more take the two-phase path (Morton sweep + ordered sum):
     same bits as the single-kernel path and as the oracle, same in-bounds count."""
     from amcl3d_test_b200 import Grid3d, ParticleFilter, synth
 

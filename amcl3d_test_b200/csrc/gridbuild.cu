@@ -834,6 +834,12 @@ __global__ void __launch_bounds__(256)
   extern __shared__ __align__(16) uint32_t zsm[];
   uint32_t(*tile)[4][32] = reinterpret_cast<uint32_t(*)[4][32]>(zsm);                          // [kRows][4][32]
   uint8_t* stage = reinterpret_cast<uint8_t*>(zsm + (size_t)kRows * 4 * 32);                  // 64 bricks x kBrickPitch
+  // the two tables of the epilogue in shared memory: 32-bit addresses and no L1 tag lookups in the hot loop
+  float* lut_s = reinterpret_cast<float*>(stage + 64 * kBrickPitch);                          // 256 dictionary values
+  uint8_t* rank_s = reinterpret_cast<uint8_t*>(lut_s + 256);                                  // code of every d2 <= cap
+  for (uint32_t w = threadIdx.x; w < (A.cap + 4u) / 4u; w += 256)
+    reinterpret_cast<uint32_t*>(rank_s)[w] = reinterpret_cast<const uint32_t*>(rank)[w];
+  lut_s[threadIdx.x] = lut[threadIdx.x];
   const uint32_t ztiles = (A.sz + kZT - 1) / kZT, ctiles = A.px / 64;
   uint32_t b = blockIdx.x;
   const uint32_t zt = b % ztiles;  // z fastest: neighbouring blocks share their halo rows in L2
@@ -909,9 +915,9 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
       for (int k = 0; k < kFastPer; ++k)
       {
-        const uint32_t ca = rank[best[k] & 0xFFFFu], cb = rank[best[k] >> 16];
+        const uint32_t ca = rank_s[best[k] & 0xFFFFu], cb = rank_s[best[k] >> 16];
         *reinterpret_cast<uint16_t*>(st + (k >> 2) * 8 * kBrickPitch + ((k & 3) << 5)) = (uint16_t)(ca | (cb << 8));
-        stg_f32x2(dst, lut[ca], lut[cb]);
+        stg_f32x2(dst, lut_s[ca], lut_s[cb]);
         dst += zstride;
         asm volatile("" : "+l"(dst));
       }
@@ -920,18 +926,18 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int k = 0; k < kFastPer; ++k)
     {
-      const uint32_t ca = rank[best[k] & 0xFFFFu], cb = rank[best[k] >> 16];
+      const uint32_t ca = rank_s[best[k] & 0xFFFFu], cb = rank_s[best[k] >> 16];
       *reinterpret_cast<uint16_t*>(st + (k >> 2) * 8 * kBrickPitch + ((k & 3) << 5)) = (uint16_t)(ca | (cb << 8));
       if ((uint32_t)k < zleft && xmode != 0u)
       {
-        const float pa = lut[ca];
+        const float pa = lut_s[ca];
         if (xmode == 2u)
-          *reinterpret_cast<float2*>(dst) = make_float2(pa, lut[cb]);
+          *reinterpret_cast<float2*>(dst) = make_float2(pa, lut_s[cb]);
         else
         {
           dst[0] = pa;
           if (xmode == 3u)
-            dst[1] = lut[cb];
+            dst[1] = lut_s[cb];
         }
       }
       dst += zstride;
@@ -1011,7 +1017,7 @@ template <int SUB, int PAR, int H>
 static cudaError_t launch_z_t(const FastArgs& A, const uint16_t* dxy, float* prob, uint8_t* codes, const uint8_t* rank,
                               const float* lut, uint32_t nbx, uint32_t nby, unsigned blocks, cudaStream_t stream)
 {
-  const size_t smem = (size_t)(kZT + 2 * H) * 4 * 32 * 4 + 64 * kBrickPitch;
+  const size_t smem = (size_t)(kZT + 2 * H) * 4 * 32 * 4 + 64 * kBrickPitch + 256 * sizeof(float) + (((size_t)A.cap + 4) & ~(size_t)3);
   // per-device attribute of the function: set on every launch (cheap), never cached process-wide
   cudaError_t e = cudaFuncSetAttribute(zpass_dpx_kernel<SUB, PAR, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess)
@@ -1232,7 +1238,7 @@ static cudaError_t build_fast(const MapDev& map, const Lattice& L, const float* 
     CK(cudaMalloc(&d_bits, sizeof(uint32_t) * bits_words));
     CK(cudaMalloc(&d_d1, rows * A.px));
     CK(cudaMalloc(&d_dxy, sizeof(uint16_t) * (uint64_t)A.w2 * sy * A.px));
-    CK(cudaMalloc(&d_rank, cap + 1));
+    CK(cudaMalloc(&d_rank, ((size_t)cap + 4) & ~(size_t)3));  // the z pass copies it to shared memory in whole words
     CK(cudaMalloc(&d_needed, cap + 1));
     CK(cudaMalloc(&d_values, sizeof(int32_t) * 256));
     CK(cudaMalloc(&d_lut, sizeof(float) * 256));

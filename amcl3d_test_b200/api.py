@@ -410,6 +410,28 @@ class ParticleFilter:
         check(self._L.amcl3d_b200_pf_shard_init(self._h, int(n_total), int(rank), int(world)))
         return self.shard_info()[:2]
 
+    def shard_init_capacity(self, n_total: int, n_capacity: int, rank: int, world: int):
+        """shard_init with an exchange region sized for n_capacity particles in total: the set may be resized up to that."""
+        check(self._L.amcl3d_b200_pf_shard_init_capacity(self._h, int(n_total), int(n_capacity), int(rank), int(world)))
+        return self.shard_info()[:2]
+
+    def shard_resize(self, n_total: int):
+        """Collective: new total particle count (<= capacity), the block partition is re-drawn; p_ is to be filled again."""
+        check(self._L.amcl3d_b200_pf_shard_resize(self._h, int(n_total)))
+        return self.shard_info()[:2]
+
+    @staticmethod
+    def shard_gather_local(pfs, dst):
+        """The blocks of all ranks (handles of this process) into p_ of the plain handle dst, device to device."""
+        arr = (C.c_void_p * len(pfs))(*[p._h.value for p in pfs])
+        check(capi.load().amcl3d_b200_pf_shard_gather_local(arr, len(pfs), dst._h))
+
+    @staticmethod
+    def shard_scatter_local(src, pfs):
+        """p_ of the plain handle src over the ranks (resized to its count), device to device."""
+        arr = (C.c_void_p * len(pfs))(*[p._h.value for p in pfs])
+        check(capi.load().amcl3d_b200_pf_shard_scatter_local(src._h, arr, len(pfs)))
+
     def shard_info(self):
         lo, hi, nb = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         check(self._L.amcl3d_b200_pf_shard_info(self._h, C.byref(lo), C.byref(hi), C.byref(nb)))

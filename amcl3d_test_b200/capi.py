@@ -18,7 +18,8 @@ SYMBOLS = [
     "amcl3d_b200_set_l2_fetch_granularity", "amcl3d_b200_get_l2_fetch_granularity", "amcl3d_b200_pf_set_chain_mode",
     "amcl3d_b200_grid_set_edt_fast", "amcl3d_b200_grid_build_device", "amcl3d_b200_grid_last_build_ms",
     "amcl3d_b200_pf_last_phase_ms",
-    "amcl3d_b200_pf_shard_init", "amcl3d_b200_pf_shard_info", "amcl3d_b200_pf_shard_ipc_handle",
+    "amcl3d_b200_pf_shard_init", "amcl3d_b200_pf_shard_init_capacity", "amcl3d_b200_pf_shard_resize",
+    "amcl3d_b200_pf_shard_gather_local", "amcl3d_b200_pf_shard_scatter_local", "amcl3d_b200_pf_shard_info", "amcl3d_b200_pf_shard_ipc_handle",
     "amcl3d_b200_pf_shard_attach_ipc", "amcl3d_b200_pf_shard_attach_local", "amcl3d_b200_pf_shard_resample",
     "amcl3d_b200_pf_shard_mean", "amcl3d_b200_pf_shard_resample_local", "amcl3d_b200_pf_shard_mean_local",
     "amcl3d_b200_pf_shard_normalize", "amcl3d_b200_pf_shard_normalize_local", "amcl3d_b200_grid_clone",
@@ -93,6 +94,10 @@ def load():
         "amcl3d_b200_grid_last_build_ms": (i, [vp, P(f32)]),
         "amcl3d_b200_pf_last_phase_ms": (i, [vp, P(f32)]),
         "amcl3d_b200_pf_shard_init": (i, [vp, u64, i, i]),
+        "amcl3d_b200_pf_shard_init_capacity": (i, [vp, u64, u64, i, i]),
+        "amcl3d_b200_pf_shard_resize": (i, [vp, u64]),
+        "amcl3d_b200_pf_shard_gather_local": (i, [P(vp), i, vp]),
+        "amcl3d_b200_pf_shard_scatter_local": (i, [vp, P(vp), i]),
         "amcl3d_b200_pf_shard_info": (i, [vp, P(u64), P(u64), P(u64)]),
         "amcl3d_b200_pf_shard_ipc_handle": (i, [vp, vp, C.c_size_t]),
         "amcl3d_b200_pf_shard_attach_ipc": (i, [vp, vp, C.c_size_t]),

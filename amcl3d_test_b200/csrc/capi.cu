@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <new>
 #include <string>
 #include <vector>
@@ -153,6 +154,7 @@ struct amcl3d_b200_pf_s
   BeaconSet* d_beacons = nullptr;
   void* d_scratch = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_sync = nullptr;  // orders this handle's stream against another handle's (shard gather / scatter)
   cudaEvent_t ev_phase[4] = { nullptr, nullptr, nullptr, nullptr };  // pose | sweep | ordered sum of the last large-set update
   bool phase_timed = false;
   bool timed = false;
@@ -163,7 +165,7 @@ struct amcl3d_b200_pf_s
   {
     bool on = false, attached = false;
     uint32_t rank = 0, world = 1;
-    uint64_t n_total = 0, n_max = 0, lo = 0, hi = 0;
+    uint64_t n_total = 0, n_cap = 0, n_max = 0, lo = 0, hi = 0;  // n_cap: the total the region is sized for (n_total <= n_cap)
     char* region = nullptr;
     size_t region_bytes = 0;
     ShardPeers peers{};
@@ -877,6 +879,8 @@ int amcl3d_b200_pf_create(amcl3d_b200_grid_t g, amcl3d_b200_pf_t* out)
     e = cudaEventCreate(&pf->ev0);
   if (e == cudaSuccess)
     e = cudaEventCreate(&pf->ev1);
+  if (e == cudaSuccess)
+    e = cudaEventCreateWithFlags(&pf->ev_sync, cudaEventDisableTiming);
   for (int k = 0; k < 4 && e == cudaSuccess; ++k)
     e = cudaEventCreate(&pf->ev_phase[k]);
   if (e == cudaSuccess)
@@ -945,6 +949,8 @@ int amcl3d_b200_pf_destroy(amcl3d_b200_pf_t pf)
     cudaEventDestroy(pf->ev0);
   if (pf->ev1)
     cudaEventDestroy(pf->ev1);
+  if (pf->ev_sync)
+    cudaEventDestroy(pf->ev_sync);
   for (int k = 0; k < 4; ++k)
     if (pf->ev_phase[k])
       cudaEventDestroy(pf->ev_phase[k]);
@@ -1787,7 +1793,13 @@ int shard_check_error(amcl3d_b200_pf_t pf)
 
 int amcl3d_b200_pf_shard_init(amcl3d_b200_pf_t pf, uint64_t n_total, int rank, int world)
 {
-  if (!pf || world < 1 || world > (int)kMaxShardWorld || rank < 0 || rank >= world || n_total == 0 || n_total >= (1ull << 31))
+  return amcl3d_b200_pf_shard_init_capacity(pf, n_total, n_total, rank, world);
+}
+
+int amcl3d_b200_pf_shard_init_capacity(amcl3d_b200_pf_t pf, uint64_t n_total, uint64_t n_capacity, int rank, int world)
+{
+  if (!pf || world < 1 || world > (int)kMaxShardWorld || rank < 0 || rank >= world || n_total == 0 || n_capacity < n_total ||
+      n_capacity >= (1ull << 31))
     return fail(AMCL3D_B200_ERR_ARG, "bad shard geometry");
   if (pf->shard.on)
     return fail(AMCL3D_B200_ERR_STATE, "already sharded");
@@ -1797,7 +1809,8 @@ int amcl3d_b200_pf_shard_init(amcl3d_b200_pf_t pf, uint64_t n_total, int rank, i
   S.rank = (uint32_t)rank;
   S.world = (uint32_t)world;
   S.n_total = n_total;
-  S.n_max = (n_total + world - 1) / world;
+  S.n_cap = n_capacity;
+  S.n_max = (n_capacity + world - 1) / world;
   shard_bounds(n_total, S.world, S.rank, &S.lo, &S.hi);
   ShardPeers& P = S.peers;
   P.world = S.world;
@@ -1806,11 +1819,11 @@ int amcl3d_b200_pf_shard_init(amcl3d_b200_pf_t pf, uint64_t n_total, int rank, i
   P.p_bytes = align256(S.n_max * 28);
   off += 2 * P.p_bytes;
   P.off_w = off;
-  off += align256(2 * n_total * 4);
+  off += align256(2 * n_capacity * 4);
   P.off_wr = off;
-  off += align256(2 * n_total * 4);
+  off += align256(2 * n_capacity * 4);
   P.off_inmap = off;
-  off += align256(2 * n_total);
+  off += align256(2 * n_capacity);
   P.off_mean = off;
   off += align256(2 * kMaxShardWorld * 8 * 4);
   P.off_flags = off;
@@ -1837,6 +1850,10 @@ int amcl3d_b200_pf_shard_init(amcl3d_b200_pf_t pf, uint64_t n_total, int rank, i
   pf->external = true;
   pf->cap = S.n_max;
   pf->n = S.hi - S.lo;
+  // the scratch of the replicated chains, sized for the capacity NOW: a cudaFree / cudaMalloc inside a collective call would
+  // synchronise the device while another rank of this process spins in wait_kernel for a publish that is not launched yet
+  CU(ensure(pf->d_prefix, pf->prefix_cap, n_capacity));
+  CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(n_capacity)));
   S.cur = 0;
   S.on = true;
   S.attached = (world == 1);
@@ -1889,7 +1906,7 @@ int amcl3d_b200_pf_shard_attach_local(amcl3d_b200_pf_t* pfs, int world)
     return fail(AMCL3D_B200_ERR_ARG, "bad handle array");
   for (int r = 0; r < world; ++r)
     if (!pfs[r] || !pfs[r]->shard.on || pfs[r]->shard.world != (uint32_t)world || pfs[r]->shard.rank != (uint32_t)r ||
-        pfs[r]->shard.n_total != pfs[0]->shard.n_total)
+        pfs[r]->shard.n_total != pfs[0]->shard.n_total || pfs[r]->shard.n_cap != pfs[0]->shard.n_cap)
       return fail(AMCL3D_B200_ERR_ARG, "handles must be shard_init'ed as ranks 0..world-1 of the same set");
   for (int a = 0; a < world; ++a)
   {
@@ -1920,19 +1937,29 @@ int amcl3d_b200_pf_shard_attach_local(amcl3d_b200_pf_t* pfs, int world)
 
 namespace
 {
-// one exchange: this rank's weights (+ raw range weights, isIntoMap flags) into every rank's dense copy, then wait for
-// everybody else's.  Returns the parity of the dense copies that now hold the epoch.
-int shard_exchange(amcl3d_b200_pf_t pf, const void* d_wr_local, uint32_t* parity_out)
+// A collective call runs in two halves: PUBLISH (this rank's contribution stored into every rank's region, flag raised)
+// and REST (everything that reads what the other ranks published).  One process per GPU (CUDA IPC): one call does both
+// and a spinning wait_kernel orders them across processes (kSpin).  Ranks that are handles of ONE process: the group call
+// issues the first half on every rank, orders the streams with CUDA events, then issues the second half -- no kernel ever
+// spins on something the host has not launched yet (a spinning kernel deadlocks against anything that synchronises the
+// device in between: a lazily loaded module at a kernel's first launch, a cudaFree, or two streams sharing a hardware queue).
+enum : int { kPublish = 1, kRest = 2, kSpin = 4, kWhole = kPublish | kRest | kSpin };
+
+// this rank's weights (+ raw range weights, isIntoMap flags) into every rank's dense copy
+int shard_publish(amcl3d_b200_pf_t pf, const void* d_wr_local)
 {
   amcl3d_b200_pf_s::Shard& S = pf->shard;
   S.epoch += 1;
-  const uint32_t parity = S.epoch & 1u;
-  const uint32_t* flags = reinterpret_cast<const uint32_t*>(S.region + S.peers.off_flags);
   CU(launch_shard_publish(pf->grid->map, S.peers, pf->d_p, reinterpret_cast<const float*>(d_wr_local), (uint32_t)pf->n,
-                          (uint32_t)S.lo, (uint32_t)S.n_total, parity, S.epoch, S.rank, S.d_done, pf->stream));
-  CU(launch_shard_wait(flags, 0, S.world, S.epoch, S.d_error, pf->stream));
-  pf->launches += 2;
-  *parity_out = parity;
+                          (uint32_t)S.lo, (uint32_t)S.n_cap, S.epoch & 1u, S.epoch, S.rank, S.d_done, pf->stream));
+  pf->launches += 1;
+  return AMCL3D_B200_OK;
+}
+int shard_spin(amcl3d_b200_pf_t pf, uint32_t kind, uint32_t epoch)
+{
+  amcl3d_b200_pf_s::Shard& S = pf->shard;
+  CU(launch_shard_wait(reinterpret_cast<const uint32_t*>(S.region + S.peers.off_flags), kind, S.world, epoch, S.d_error, pf->stream));
+  pf->launches += 1;
   return AMCL3D_B200_OK;
 }
 int shard_ready(amcl3d_b200_pf_t pf)
@@ -1946,28 +1973,147 @@ int shard_ready(amcl3d_b200_pf_t pf)
     return fail(AMCL3D_B200_ERR_STATE, "p_ must hold this rank's block of the partition");
   return use_device(pf->grid->device);
 }
+
+int shard_normalize_impl(amcl3d_b200_pf_t pf, int phases)
+{
+  if (int rc = shard_ready(pf))
+    return rc;
+  amcl3d_b200_pf_s::Shard& S = pf->shard;
+  const uint64_t N = S.n_total;
+  CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(S.n_cap)));  // sized at shard_init: no-op
+  Timed t(pf);
+  if (phases & kPublish)
+    if (int rc = shard_publish(pf, nullptr))
+      return rc;
+  if (!(phases & kRest))
+    return AMCL3D_B200_OK;
+  if (phases & kSpin)
+    if (int rc = shard_spin(pf, 0, S.epoch))
+      return rc;
+  const float* w = reinterpret_cast<const float*>(S.region + S.peers.off_w) + (size_t)(S.epoch & 1u) * S.n_cap;
+  // ParticleFilter.cpp:171-178 over ALL particles (same chain on every rank), :180-195 on the rank's own block
+  CU(launch_chain_dense(w, N, 1, nullptr, pf->d_scalars + 0, pf->d_dense, pf->chain_mode, pf->stream));
+  CU(launch_normalize(pf->grid->map, pf->d_p, pf->n, pf->d_scalars + 0, pf->stream));
+  pf->launches += 2;
+  pf->launches += chain_extra_launches_take();
+  return AMCL3D_B200_OK;
+}
+
+int shard_resample_impl(amcl3d_b200_pf_t pf, float u01, int normalize, const void* d_wr_local, float alpha, bool want_idx, int phases)
+{
+  if (int rc = shard_ready(pf))
+    return rc;
+  if (!normalize && d_wr_local)
+    return fail(AMCL3D_B200_ERR_ARG, "the range fusion is part of the normalising call");
+  amcl3d_b200_pf_s::Shard& S = pf->shard;
+  const uint64_t N = S.n_total, n = pf->n;
+  CU(ensure(pf->d_prefix, pf->prefix_cap, S.n_cap));  // sized at shard_init: no-ops
+  CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(S.n_cap)));
+  int32_t* d_idx = nullptr;
+  if (want_idx)
+  {
+    CU(ensure(pf->d_idx, pf->idx_cap, n));
+    d_idx = pf->d_idx;
+  }
+  Timed t(pf);
+  if (phases & kPublish)
+    if (int rc = shard_publish(pf, d_wr_local))
+      return rc;
+  if (!(phases & kRest))
+    return AMCL3D_B200_OK;
+  if (phases & kSpin)
+    if (int rc = shard_spin(pf, 0, S.epoch))
+      return rc;
+  const uint32_t parity = S.epoch & 1u;
+  float* out = reinterpret_cast<float*>(S.region + S.peers.off_p + (size_t)(S.cur ^ 1u) * S.peers.p_bytes);
+  float* w = reinterpret_cast<float*>(S.region + S.peers.off_w) + (size_t)parity * S.n_cap;
+  float* wr = reinterpret_cast<float*>(S.region + S.peers.off_wr) + (size_t)parity * S.n_cap;
+  const uint8_t* inmap = reinterpret_cast<const uint8_t*>(S.region + S.peers.off_inmap) + (size_t)parity * S.n_cap;
+  // the reference's sequential chains over ALL particles, replicated on every rank: same bits as one GPU
+  if (d_wr_local)
+  {
+    CU(launch_chain_dense(w, N, 0, nullptr, pf->d_scalars + 0, pf->d_dense, pf->chain_mode, pf->stream));
+    CU(launch_chain_dense(wr, N, 0, nullptr, pf->d_scalars + 1, pf->d_dense, pf->chain_mode, pf->stream));
+    CU(launch_dense_fuse(w, wr, N, pf->d_scalars + 0, pf->d_scalars + 1, alpha, pf->stream));
+    pf->launches += 3;
+  }
+  if (normalize)
+  {
+    CU(launch_chain_dense(w, N, 1, nullptr, pf->d_scalars + 0, pf->d_dense, pf->chain_mode, pf->stream));  // ParticleFilter.cpp:171-178
+    CU(launch_dense_normalize(w, inmap, N, pf->d_scalars + 0, pf->stream));                                // :180-195
+    pf->launches += 2;
+  }
+  CU(launch_chain_dense(w, N, 0, pf->d_prefix, nullptr, pf->d_dense, pf->chain_mode, pf->stream));  // :235-247
+  // this rank's output slice; the selected particles are read from their owners over NVLink
+  CU(launch_shard_search(S.peers, pf->d_prefix, N, u01, S.lo, S.hi, S.cur, out, d_idx, pf->stream));
+  pf->launches += 2;
+  pf->launches += chain_extra_launches_take();
+  S.cur ^= 1u;
+  pf->d_p = out;
+  return AMCL3D_B200_OK;
+}
+
+int shard_mean_impl(amcl3d_b200_pf_t pf, float* dst, int phases)
+{
+  amcl3d_b200_pf_s::Shard& S = pf->shard;
+  if (!S.on || !S.attached)
+    return fail(AMCL3D_B200_ERR_STATE, "shard not attached to its peers");
+  if (int rc = use_device(pf->grid->device))
+    return rc;
+  Timed t(pf);
+  if (phases & kPublish)
+  {
+    S.mean_epoch += 1;
+    CU(launch_mean(pf->d_p, pf->n, 0, S.d_part7, pf->d_scratch, pf->stream));
+    CU(launch_shard_publish_mean(S.peers, S.d_part7, S.mean_epoch & 1u, S.mean_epoch, S.rank, pf->stream));
+    pf->launches += 3;
+  }
+  if (!(phases & kRest))
+    return AMCL3D_B200_OK;
+  if (phases & kSpin)
+    if (int rc = shard_spin(pf, 1, S.mean_epoch))
+      return rc;
+  CU(launch_shard_combine_mean(reinterpret_cast<const float*>(S.region + S.peers.off_mean) + (size_t)(S.mean_epoch & 1u) * kMaxShardWorld * 8,
+                               S.world, dst, pf->stream));
+  pf->launches += 1;
+  return AMCL3D_B200_OK;
+}
+
+// the group form for ranks that are handles of one process: first half on every rank, events, second half on every rank
+int local_collective(amcl3d_b200_pf_t* pfs, int world, const std::function<int(int, int)>& half)
+{
+  if (!pfs || world < 1 || world > (int)kMaxShardWorld)
+    return fail(AMCL3D_B200_ERR_ARG, "bad handle array");
+  for (int r = 0; r < world; ++r)
+    if (!pfs[r])
+      return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+  for (int r = 0; r < world; ++r)
+  {
+    if (int rc = half(r, kPublish))
+      return rc;
+    if (int rc = use_device(pfs[r]->grid->device))
+      return rc;
+    CU(cudaEventRecord(pfs[r]->ev_sync, pfs[r]->stream));
+  }
+  for (int r = 0; r < world; ++r)
+  {
+    if (int rc = use_device(pfs[r]->grid->device))
+      return rc;
+    for (int q = 0; q < world; ++q)
+      if (q != r)
+        CU(cudaStreamWaitEvent(pfs[r]->stream, pfs[q]->ev_sync, 0));
+    if (int rc = half(r, kRest))
+      return rc;
+  }
+  return AMCL3D_B200_OK;
+}
 }  // namespace
 
 int amcl3d_b200_pf_shard_normalize(amcl3d_b200_pf_t pf, float* wtp)
 {
   NvtxRange nvtx_range("particleNormalize (sharded)");
-  if (int rc = shard_ready(pf))
+  if (int rc = shard_normalize_impl(pf, kWhole))
     return rc;
-  amcl3d_b200_pf_s::Shard& S = pf->shard;
-  const uint64_t N = S.n_total;
-  CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(N)));
-  {
-    Timed t(pf);
-    uint32_t parity = 0;
-    if (int rc = shard_exchange(pf, nullptr, &parity))
-      return rc;
-    const float* w = reinterpret_cast<const float*>(S.region + S.peers.off_w) + (size_t)parity * N;
-    // ParticleFilter.cpp:171-178 over ALL particles (same chain on every rank), :180-195 on the rank's own block
-    CU(launch_chain_dense(w, N, 1, nullptr, pf->d_scalars + 0, pf->d_dense, pf->chain_mode, pf->stream));
-    CU(launch_normalize(pf->grid->map, pf->d_p, pf->n, pf->d_scalars + 0, pf->stream));
-    pf->launches += 2;
-    pf->launches += chain_extra_launches_take();
-  }
   if (!wtp)
   {
     if (pf->async_mode)
@@ -1981,54 +2127,11 @@ int amcl3d_b200_pf_shard_normalize(amcl3d_b200_pf_t pf, float* wtp)
 int amcl3d_b200_pf_shard_resample(amcl3d_b200_pf_t pf, float u01, int normalize, const void* d_wr_local, float alpha, int32_t* idx)
 {
   NvtxRange nvtx_range("Resample (sharded)");
-  if (int rc = shard_ready(pf))
+  if (int rc = shard_resample_impl(pf, u01, normalize, d_wr_local, alpha, idx != nullptr, kWhole))
     return rc;
-  if (!normalize && d_wr_local)
-    return fail(AMCL3D_B200_ERR_ARG, "the range fusion is part of the normalising call");
-  amcl3d_b200_pf_s::Shard& S = pf->shard;
-  const uint64_t N = S.n_total, n = pf->n;
-  CU(ensure(pf->d_prefix, pf->prefix_cap, N));
-  CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(N)));
-  int32_t* d_idx = nullptr;
-  if (idx)
+  if (idx && pf->n)
   {
-    CU(ensure(pf->d_idx, pf->idx_cap, n));
-    d_idx = pf->d_idx;
-  }
-  float* out = reinterpret_cast<float*>(S.region + S.peers.off_p + (size_t)(S.cur ^ 1u) * S.peers.p_bytes);
-  {
-    Timed t(pf);
-    uint32_t parity = 0;
-    if (int rc = shard_exchange(pf, d_wr_local, &parity))
-      return rc;
-    float* w = reinterpret_cast<float*>(S.region + S.peers.off_w) + (size_t)parity * N;
-    float* wr = reinterpret_cast<float*>(S.region + S.peers.off_wr) + (size_t)parity * N;
-    const uint8_t* inmap = reinterpret_cast<const uint8_t*>(S.region + S.peers.off_inmap) + (size_t)parity * N;
-    // the reference's sequential chains over ALL particles, replicated on every rank: same bits as one GPU
-    if (d_wr_local)
-    {
-      CU(launch_chain_dense(w, N, 0, nullptr, pf->d_scalars + 0, pf->d_dense, pf->chain_mode, pf->stream));
-      CU(launch_chain_dense(wr, N, 0, nullptr, pf->d_scalars + 1, pf->d_dense, pf->chain_mode, pf->stream));
-      CU(launch_dense_fuse(w, wr, N, pf->d_scalars + 0, pf->d_scalars + 1, alpha, pf->stream));
-      pf->launches += 3;
-    }
-    if (normalize)
-    {
-      CU(launch_chain_dense(w, N, 1, nullptr, pf->d_scalars + 0, pf->d_dense, pf->chain_mode, pf->stream));  // ParticleFilter.cpp:171-178
-      CU(launch_dense_normalize(w, inmap, N, pf->d_scalars + 0, pf->stream));                                // :180-195
-      pf->launches += 2;
-    }
-    CU(launch_chain_dense(w, N, 0, pf->d_prefix, nullptr, pf->d_dense, pf->chain_mode, pf->stream));  // :235-247
-    // this rank's output slice; the selected particles are read from their owners over NVLink
-    CU(launch_shard_search(S.peers, pf->d_prefix, N, u01, S.lo, S.hi, S.cur, out, d_idx, pf->stream));
-    pf->launches += 2;
-    pf->launches += chain_extra_launches_take();
-  }
-  S.cur ^= 1u;
-  pf->d_p = out;
-  if (idx && n)
-  {
-    CU(cudaMemcpyAsync(idx, d_idx, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, pf->stream));
+    CU(cudaMemcpyAsync(idx, pf->d_idx, sizeof(int32_t) * pf->n, cudaMemcpyDeviceToHost, pf->stream));
     return shard_check_error(pf);
   }
   if (pf->async_mode)
@@ -2046,8 +2149,8 @@ int amcl3d_b200_pf_shard_resample_fast(amcl3d_b200_pf_t pf, float u01, int32_t* 
   const uint64_t N = S.n_total, n = pf->n;
   if (N < S.world)
     return fail(AMCL3D_B200_ERR_ARG, "fewer particles than ranks");
-  CU(ensure(pf->d_prefix, pf->prefix_cap, std::max<uint64_t>(n, 1)));
-  CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(std::max<uint64_t>(n, 1))));
+  CU(ensure(pf->d_prefix, pf->prefix_cap, S.n_cap));  // sized at shard_init: no-ops
+  CU(ensure(pf->d_dense, pf->dense_cap, chain_scratch_floats(S.n_cap)));
   S.fast_epoch += 1;
   const uint32_t e = S.fast_epoch, parity = e & 1u;
   const uint32_t* flags = reinterpret_cast<const uint32_t*>(S.region + S.peers.off_flags);
@@ -2091,52 +2194,24 @@ int amcl3d_b200_pf_shard_mean(amcl3d_b200_pf_t pf, float out7[7], void* d_out7)
   NvtxRange nvtx_range("getMean (sharded)");
   if (!pf || (!out7 && !d_out7))
     return fail(AMCL3D_B200_ERR_ARG, "NULL argument");
-  amcl3d_b200_pf_s::Shard& S = pf->shard;
-  if (!S.on || !S.attached)
-    return fail(AMCL3D_B200_ERR_STATE, "shard not attached to its peers");
-  if (int rc = use_device(pf->grid->device))
-    return rc;
-  S.mean_epoch += 1;
-  const uint32_t parity = S.mean_epoch & 1u;
   float* dst = d_out7 ? reinterpret_cast<float*>(d_out7) : pf->d_scalars + 8;
-  {
-    Timed t(pf);
-    CU(launch_mean(pf->d_p, pf->n, 0, S.d_part7, pf->d_scratch, pf->stream));
-    CU(launch_shard_publish_mean(S.peers, S.d_part7, parity, S.mean_epoch, S.rank, pf->stream));
-    CU(launch_shard_wait(reinterpret_cast<const uint32_t*>(S.region + S.peers.off_flags), 1, S.world, S.mean_epoch, S.d_error,
-                         pf->stream));
-    CU(launch_shard_combine_mean(reinterpret_cast<const float*>(S.region + S.peers.off_mean) + (size_t)parity * kMaxShardWorld * 8,
-                                 S.world, dst, pf->stream));
-    pf->launches += 5;
-  }
+  if (int rc = shard_mean_impl(pf, dst, kWhole))
+    return rc;
   if (out7)
   {
-    if (d_out7)
-      CU(cudaMemcpyAsync(out7, d_out7, 7 * sizeof(float), cudaMemcpyDeviceToHost, pf->stream));
-    else
-      CU(cudaMemcpyAsync(out7, pf->d_scalars + 8, 7 * sizeof(float), cudaMemcpyDeviceToHost, pf->stream));
+    CU(cudaMemcpyAsync(out7, dst, 7 * sizeof(float), cudaMemcpyDeviceToHost, pf->stream));
     return shard_check_error(pf);
   }
   return finish_call(pf);
 }
 
-// ranks = handles of ONE process: the collective calls are issued on every handle in stream order first and waited for
-// afterwards (a synchronous call on rank 0 alone would wait for a publish rank 1 has not launched yet)
+// ranks = handles of ONE process: both halves of the collective call are issued on every handle in stream order, with CUDA
+// events between them instead of a spinning kernel (see kPublish / kRest above), then waited for
 int amcl3d_b200_pf_shard_normalize_local(amcl3d_b200_pf_t* pfs, int world)
 {
-  if (!pfs || world < 1 || world > (int)kMaxShardWorld)
-    return fail(AMCL3D_B200_ERR_ARG, "bad handle array");
-  for (int r = 0; r < world; ++r)
-  {
-    if (!pfs[r])
-      return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
-    const bool was = pfs[r]->async_mode;
-    pfs[r]->async_mode = true;
-    const int rc = amcl3d_b200_pf_shard_normalize(pfs[r], nullptr);
-    pfs[r]->async_mode = was;
-    if (rc != AMCL3D_B200_OK)
-      return rc;
-  }
+  NvtxRange nvtx_range("particleNormalize (sharded, one process)");
+  if (int rc = local_collective(pfs, world, [&](int r, int phases) { return shard_normalize_impl(pfs[r], phases); }))
+    return rc;
   for (int r = 0; r < world; ++r)
     if (!pfs[r]->async_mode)
       if (int rc = amcl3d_b200_pf_sync(pfs[r]))
@@ -2147,19 +2222,11 @@ int amcl3d_b200_pf_shard_normalize_local(amcl3d_b200_pf_t* pfs, int world)
 int amcl3d_b200_pf_shard_resample_local(amcl3d_b200_pf_t* pfs, int world, float u01, int normalize, const void* const* d_wr_local,
                                         float alpha)
 {
-  if (!pfs || world < 1 || world > (int)kMaxShardWorld)
-    return fail(AMCL3D_B200_ERR_ARG, "bad handle array");
-  for (int r = 0; r < world; ++r)
-  {
-    if (!pfs[r])
-      return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
-    const bool was = pfs[r]->async_mode;
-    pfs[r]->async_mode = true;
-    const int rc = amcl3d_b200_pf_shard_resample(pfs[r], u01, normalize, d_wr_local ? d_wr_local[r] : nullptr, alpha, nullptr);
-    pfs[r]->async_mode = was;
-    if (rc != AMCL3D_B200_OK)
-      return rc;
-  }
+  NvtxRange nvtx_range("Resample (sharded, one process)");
+  if (int rc = local_collective(pfs, world, [&](int r, int phases) {
+        return shard_resample_impl(pfs[r], u01, normalize, d_wr_local ? d_wr_local[r] : nullptr, alpha, false, phases);
+      }))
+    return rc;
   for (int r = 0; r < world; ++r)
     if (!pfs[r]->async_mode)
       if (int rc = amcl3d_b200_pf_sync(pfs[r]))
@@ -2169,25 +2236,138 @@ int amcl3d_b200_pf_shard_resample_local(amcl3d_b200_pf_t* pfs, int world, float 
 
 int amcl3d_b200_pf_shard_mean_local(amcl3d_b200_pf_t* pfs, int world, float out7[7])
 {
-  if (!pfs || !out7 || world < 1 || world > (int)kMaxShardWorld)
+  NvtxRange nvtx_range("getMean (sharded, one process)");
+  if (!out7)
     return fail(AMCL3D_B200_ERR_ARG, "bad argument");
-  for (int r = 0; r < world; ++r)
-  {
-    if (!pfs[r])
-      return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
-    const bool was = pfs[r]->async_mode;
-    pfs[r]->async_mode = true;
-    const int rc = amcl3d_b200_pf_shard_mean(pfs[r], nullptr, pfs[r]->d_scalars + 8);
-    pfs[r]->async_mode = was;
-    if (rc != AMCL3D_B200_OK)
-      return rc;
-  }
+  if (int rc = local_collective(pfs, world, [&](int r, int phases) { return shard_mean_impl(pfs[r], pfs[r]->d_scalars + 8, phases); }))
+    return rc;
   for (int r = 0; r < world; ++r)
     if (int rc = amcl3d_b200_pf_sync(pfs[r]))
       return rc;
   if (int rc = use_device(pfs[0]->grid->device))
     return rc;
   CU(cudaMemcpy(out7, pfs[0]->d_scalars + 8, 7 * sizeof(float), cudaMemcpyDeviceToHost));
+  return AMCL3D_B200_OK;
+}
+
+int amcl3d_b200_pf_shard_resize(amcl3d_b200_pf_t pf, uint64_t n_total)
+{
+  if (!pf || !pf->shard.on)
+    return fail(AMCL3D_B200_ERR_STATE, "not sharded");
+  amcl3d_b200_pf_s::Shard& S = pf->shard;
+  if (n_total == 0 || n_total > S.n_cap)
+    return fail(AMCL3D_B200_ERR_ARG, "particle count outside the capacity of the exchange region");
+  S.n_total = n_total;
+  shard_bounds(n_total, S.world, S.rank, &S.lo, &S.hi);
+  pf->n = S.hi - S.lo;
+  return AMCL3D_B200_OK;
+}
+
+namespace
+{
+cudaError_t copy_between(void* dst, int dst_device, const void* src, int src_device, size_t bytes, cudaStream_t stream)
+{
+  if (dst_device == src_device)
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream);
+  return cudaMemcpyPeerAsync(dst, dst_device, src, src_device, bytes, stream);
+}
+int local_group_ok(amcl3d_b200_pf_t* pfs, int world, amcl3d_b200_pf_t other)
+{
+  if (!pfs || !other || world < 1 || world > (int)kMaxShardWorld)
+    return fail(AMCL3D_B200_ERR_ARG, "bad handle array");
+  if (other->shard.on)
+    return fail(AMCL3D_B200_ERR_ARG, "the handle outside the group must be a plain (unsharded) one");
+  for (int r = 0; r < world; ++r)
+  {
+    if (!pfs[r])
+      return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+    const amcl3d_b200_pf_s::Shard& S = pfs[r]->shard;
+    if (!S.on || !S.attached || S.world != (uint32_t)world || S.rank != (uint32_t)r || S.n_total != pfs[0]->shard.n_total)
+      return fail(AMCL3D_B200_ERR_STATE, "handles must be the attached ranks 0..world-1 of one set");
+  }
+  return AMCL3D_B200_OK;
+}
+}  // namespace
+
+int amcl3d_b200_pf_shard_gather_local(amcl3d_b200_pf_t* pfs, int world, amcl3d_b200_pf_t dst)
+{
+  if (int rc = local_group_ok(pfs, world, dst))
+    return rc;
+  const uint64_t N = pfs[0]->shard.n_total;
+  for (int r = 0; r < world; ++r)
+    if (pfs[r]->n != pfs[r]->shard.hi - pfs[r]->shard.lo)
+      return fail(AMCL3D_B200_ERR_STATE, "p_ must hold this rank's block of the partition");
+  const int ddev = dst->grid->device;
+  if (int rc = use_device(ddev))
+    return rc;
+  if (dst->external)
+  {
+    if (N > dst->cap)
+      return fail(AMCL3D_B200_ERR_ARG, "bound device buffer too small for the gathered set");
+  }
+  else if (N > dst->cap)
+  {
+    CU(cudaStreamSynchronize(dst->stream));  // the old buffer may still be in use by launched work
+    CU(ensure_particles(dst->d_p, dst->cap, N));
+  }
+  for (int r = 0; r < world; ++r)
+  {
+    amcl3d_b200_pf_t s = pfs[r];
+    if (int rc = use_device(s->grid->device))
+      return rc;
+    CU(cudaEventRecord(s->ev_sync, s->stream));
+    if (int rc = use_device(ddev))
+      return rc;
+    CU(cudaStreamWaitEvent(dst->stream, s->ev_sync, 0));
+    if (s->n)
+      CU(copy_between(dst->d_p + 7 * s->shard.lo, ddev, s->d_p, s->grid->device, sizeof(float) * 7 * s->n, dst->stream));
+  }
+  dst->n = N;
+  // the shards must not overwrite their blocks before the copies have read them
+  CU(cudaEventRecord(dst->ev_sync, dst->stream));
+  for (int r = 0; r < world; ++r)
+  {
+    if (int rc = use_device(pfs[r]->grid->device))
+      return rc;
+    CU(cudaStreamWaitEvent(pfs[r]->stream, dst->ev_sync, 0));
+  }
+  if (int rc = use_device(ddev))
+    return rc;
+  return finish_call(dst);
+}
+
+int amcl3d_b200_pf_shard_scatter_local(amcl3d_b200_pf_t src, amcl3d_b200_pf_t* pfs, int world)
+{
+  if (int rc = local_group_ok(pfs, world, src))
+    return rc;
+  const uint64_t N = src->n;
+  if (N < (uint64_t)world || N > pfs[0]->shard.n_cap)
+    return fail(AMCL3D_B200_ERR_ARG, "particle count outside [world, capacity of the exchange regions]");
+  const int sdev = src->grid->device;
+  if (int rc = use_device(sdev))
+    return rc;
+  CU(cudaEventRecord(src->ev_sync, src->stream));
+  for (int r = 0; r < world; ++r)
+  {
+    amcl3d_b200_pf_t d = pfs[r];
+    if (int rc = amcl3d_b200_pf_shard_resize(d, N))
+      return rc;
+    if (int rc = use_device(d->grid->device))
+      return rc;
+    CU(cudaStreamWaitEvent(d->stream, src->ev_sync, 0));
+    if (d->n)
+      CU(copy_between(d->d_p, d->grid->device, src->d_p + 7 * d->shard.lo, sdev, sizeof(float) * 7 * d->n, d->stream));
+    CU(cudaEventRecord(d->ev_sync, d->stream));
+  }
+  // src must not change its set before the copies have read it
+  if (int rc = use_device(sdev))
+    return rc;
+  for (int r = 0; r < world; ++r)
+    CU(cudaStreamWaitEvent(src->stream, pfs[r]->ev_sync, 0));
+  for (int r = 0; r < world; ++r)
+    if (!pfs[r]->async_mode)
+      if (int rc = amcl3d_b200_pf_sync(pfs[r]))
+        return rc;
   return AMCL3D_B200_OK;
 }
 

@@ -226,8 +226,8 @@ struct ShardPeers
   char* base[kMaxShardWorld];
   uint32_t world;
   uint64_t off_p, p_bytes;  // particle blocks P[2], p_bytes each
-  uint64_t off_w, off_wr;   // dense f32 [2][n_total]
-  uint64_t off_inmap;       // u8 [2][n_total]
+  uint64_t off_w, off_wr;   // dense f32 [2][n_capacity]
+  uint64_t off_inmap;       // u8 [2][n_capacity]
   uint64_t off_mean;        // f32 [2][kMaxShardWorld][8]
   uint64_t off_flags;       // u32 [kShardFlagKinds][kMaxShardWorld]
   uint64_t off_sums;        // f32 [2 steps][2 parity][kMaxShardWorld]: per-rank partial sums of the fast mode
@@ -235,7 +235,7 @@ struct ShardPeers
 };
 constexpr uint32_t kShardFlagKinds = 8;  // 0 weights, 1 mean, 2 / 3 fast-mode sums, 4 fast-mode push done
 cudaError_t launch_shard_publish(const MapDev& map, const ShardPeers& peers, const float* particles, const float* wr_local,
-                                 uint32_t n, uint32_t lo, uint32_t n_total, uint32_t parity, uint32_t epoch, uint32_t rank,
+                                 uint32_t n, uint32_t lo, uint32_t dense_stride, uint32_t parity, uint32_t epoch, uint32_t rank,
                                  unsigned int* done_counter, cudaStream_t stream);
 cudaError_t launch_shard_wait(const uint32_t* flags, uint32_t kind, uint32_t world, uint32_t epoch, uint32_t* error,
                               cudaStream_t stream);

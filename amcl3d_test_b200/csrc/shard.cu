@@ -5,7 +5,7 @@
 // Every rank owns one exchange region (one cudaMalloc, mapped into the peers through CUDA IPC handles or, inside one
 // process, through peer access):
 //     P[2][n_max]        the rank's particle block, ping-pong (resample reads the peers' P[cur] and writes its own P[cur^1])
-//     w[2][N]            dense weights of ALL particles, ping-pong by epoch: every rank STORES its own slice into every
+//     w[2][C]            (C = the capacity the region was sized for, N <= C) dense weights of ALL particles, ping-pong by epoch: every rank STORES its own slice into every
 //                        peer's copy over NVLink (4 B per particle instead of 28)
 //     wr[2][N]           raw range-beacon weights (row R), same
 //     inmap[2][N]        isIntoMap of every particle (particleNormalize zeroes the weight outside the map, ParticleFilter.cpp:187-191)
@@ -56,7 +56,7 @@ __device__ __forceinline__ bool into_map(const MapDev& map, float x, float y, fl
 // block to finish raises flags[rank] = epoch on every peer.
 __global__ void __launch_bounds__(256)
     publish_kernel(const __grid_constant__ MapDev map, const __grid_constant__ ShardPeers peers, const float* __restrict__ particles,
-                   const float* __restrict__ wr_local, uint32_t n, uint32_t lo, uint32_t n_total, uint32_t parity, uint32_t epoch,
+                   const float* __restrict__ wr_local, uint32_t n, uint32_t lo, uint32_t dense_stride, uint32_t parity, uint32_t epoch,
                    uint32_t rank, unsigned int* __restrict__ done_counter)
 {
   const uint32_t world = peers.world;
@@ -69,10 +69,10 @@ __global__ void __launch_bounds__(256)
     for (uint32_t r = 0; r < world; ++r)
     {
       char* base = peers.base[r];
-      reinterpret_cast<float*>(base + peers.off_w)[(size_t)parity * n_total + lo + i] = w;
-      reinterpret_cast<uint8_t*>(base + peers.off_inmap)[(size_t)parity * n_total + lo + i] = in;
+      reinterpret_cast<float*>(base + peers.off_w)[(size_t)parity * dense_stride + lo + i] = w;
+      reinterpret_cast<uint8_t*>(base + peers.off_inmap)[(size_t)parity * dense_stride + lo + i] = in;
       if (wr_local)
-        reinterpret_cast<float*>(base + peers.off_wr)[(size_t)parity * n_total + lo + i] = wr;
+        reinterpret_cast<float*>(base + peers.off_wr)[(size_t)parity * dense_stride + lo + i] = wr;
     }
   }
   __threadfence_system();
@@ -349,7 +349,7 @@ __global__ void combine_mean_kernel(const float* __restrict__ mean_all, uint32_t
 }  // namespace
 
 cudaError_t launch_shard_publish(const MapDev& map, const ShardPeers& peers, const float* particles, const float* wr_local,
-                                 uint32_t n, uint32_t lo, uint32_t n_total, uint32_t parity, uint32_t epoch, uint32_t rank,
+                                 uint32_t n, uint32_t lo, uint32_t dense_stride, uint32_t parity, uint32_t epoch, uint32_t rank,
                                  unsigned int* done_counter, cudaStream_t stream)
 {
   uint32_t blocks = (n + 255) / 256;
@@ -357,7 +357,7 @@ cudaError_t launch_shard_publish(const MapDev& map, const ShardPeers& peers, con
     blocks = 148 * 4;
   if (blocks == 0)
     blocks = 1;
-  publish_kernel<<<blocks, 256, 0, stream>>>(map, peers, particles, wr_local, n, lo, n_total, parity, epoch, rank, done_counter);
+  publish_kernel<<<blocks, 256, 0, stream>>>(map, peers, particles, wr_local, n, lo, dense_stride, parity, epoch, rank, done_counter);
   return cudaGetLastError();
 }
 cudaError_t launch_shard_wait(const uint32_t* flags, uint32_t kind, uint32_t world, uint32_t epoch, uint32_t* error,

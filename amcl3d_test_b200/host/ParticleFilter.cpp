@@ -1,6 +1,7 @@
 // ParticleFilter.cpp -- host shim of the B200 particle filter over the C-ABI.
 #include "amcl3d/ParticleFilter.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -128,7 +129,15 @@ void ParticleFilter::syncDevice()
 {
   if (p_.dev_fresh_ && where_ == kSingle)
     return;
-  const std::vector<Particle>& h = p_.host();  // gathers from the shards if that is where the set is
+  if (p_.dev_fresh_ && where_ == kSharded && !shard_.empty())
+  {
+    // the blocks of the shards into the first device's handle, device to device over NVLink: no host copy
+    check(amcl3d_b200_pf_shard_gather_local(shard_.data(), static_cast<int>(shard_.size()), handle_), "gather the shards");
+    ++gathers_;
+    where_ = kSingle;  // the host copy, if current, stays current: the set did not change
+    return;
+  }
+  const std::vector<Particle>& h = p_.host();
   p_.pin();
   check(amcl3d_b200_pf_set_particles(handle_, h.empty() ? nullptr : &h[0].x, h.size()), "upload p_");
   ++p_.uploads_;
@@ -159,6 +168,7 @@ void ParticleFilter::dropShards()
     amcl3d_b200_pf_destroy(h);
   shard_.clear();
   shard_n_ = 0;
+  shard_cap_ = 0;
 }
 
 void ParticleFilter::setDevices(const std::vector<int>& devices)
@@ -201,21 +211,40 @@ void ParticleFilter::syncShards()
   }
   if (p_.dev_fresh_ && where_ == kSharded && shard_n_ == p_.dev_n_)
     return;
-  const std::vector<Particle>& h = p_.host();
-  if (h.empty())
-    throw std::runtime_error("ParticleFilter: no particles to shard");
-  p_.pin();
-  if (shard_.size() != world || shard_n_ != h.size())
+  const uint64_t n_now = p_.size();
+  if (n_now < world)
+    throw std::runtime_error("ParticleFilter: fewer particles than devices");
+  if (shard_.size() != world || n_now > shard_cap_)
   {
+    // exchange regions with room for the largest set the resampling policy can ask for (setParticleNum)
     dropShards();
+    const uint64_t cap = std::max<uint64_t>(n_now, static_cast<uint64_t>(std::max(max_resamp_num_, 0)));
     shard_.assign(world, nullptr);
     for (size_t r = 0; r < world; ++r)
     {
       check(amcl3d_b200_pf_create(r == 0 ? grid3d_->handle() : replicas_[r], &shard_[r]), "pf_create (shard)");
-      check(amcl3d_b200_pf_shard_init(shard_[r], h.size(), static_cast<int>(r), static_cast<int>(world)), "shard_init");
+      check(amcl3d_b200_pf_shard_init_capacity(shard_[r], n_now, cap, static_cast<int>(r), static_cast<int>(world)), "shard_init");
     }
     check(amcl3d_b200_pf_shard_attach_local(shard_.data(), static_cast<int>(world)), "shard_attach_local");
-    shard_n_ = h.size();
+    shard_n_ = n_now;
+    shard_cap_ = cap;
+  }
+  if (p_.dev_fresh_ && where_ == kSingle)
+  {
+    // the set is on the first device's handle (a step without a sharded form ran there): device to device over NVLink
+    check(amcl3d_b200_pf_shard_scatter_local(handle_, shard_.data(), static_cast<int>(world)), "scatter to the shards");
+    ++scatters_;
+    shard_n_ = n_now;
+    where_ = kSharded;
+    return;
+  }
+  const std::vector<Particle>& h = p_.host();
+  p_.pin();
+  if (shard_n_ != n_now)
+  {
+    for (size_t r = 0; r < world; ++r)
+      check(amcl3d_b200_pf_shard_resize(shard_[r], n_now), "shard_resize");
+    shard_n_ = n_now;
   }
   for (size_t r = 0; r < world; ++r)
   {
@@ -310,7 +339,7 @@ void ParticleFilter::predict(const double delta_x, const double delta_y, const d
     for (int k = 0; k < 6; ++k)
       noise[6 * i + k] = ranGaussian(0, dev[k]);
   const double delta[6] = { delta_x, delta_y, delta_z, delta_roll, delta_pitch, delta_yaw };
-  if (sharded() && n)
+  if (sharded())
   {
     syncShards();
     for (size_t r = 0; r < shard_.size(); ++r)
@@ -336,7 +365,7 @@ void ParticleFilter::setCloudAll(const pcl::PointCloud<PointType>::Ptr& cloud)
 
 void ParticleFilter::update(const pcl::PointCloud<PointType>::Ptr& cloud)
 {
-  if (sharded() && !p_.empty())
+  if (sharded())
   {
     syncShards();
     setCloudAll(cloud);
@@ -372,7 +401,7 @@ void ParticleFilter::update(const pcl::PointCloud<PointType>::Ptr& cloud, const 
 
 void ParticleFilter::particleNormalize()
 {
-  if (sharded() && !p_.empty())
+  if (sharded())
   {
     syncShards();
     check(amcl3d_b200_pf_shard_normalize_local(shard_.data(), static_cast<int>(shard_.size())), "particleNormalize (sharded)");
@@ -394,7 +423,7 @@ void ParticleFilter::addParticleWeight()
 Particle ParticleFilter::getMean()
 {
   Particle m;
-  if (sharded() && !p_.empty())
+  if (sharded())
   {
     // partial sums per device, combined in rank order in f64 (the one step of the sharded path that is not the
     // reference's sequential f32 chain: differs from one GPU in the last ulps)

@@ -12,8 +12,11 @@
 // Callers may keep reading and editing p_ between calls exactly as they do with the reference.
 // setDevices({0,1,...}) (or AMCL3D_B200_DEVICES=0,1,...) shards the particles over several GPUs of one NVLink box:
 // the grid is replicated, predict / update / particleNormalize / resample / getMean run sharded with the exchange in
-// the library's own peer-memory kernels (csrc/shard.cu), bit-identical to one GPU; every other step runs on the
-// first device.  Host RNG (std::mt19937) as in the reference; setSeed() makes runs reproducible (the reference seeds
+// the library's own peer-memory kernels (csrc/shard.cu), bit-identical to one GPU; every other step (uniformSample,
+// addParticleWeight, getBestParticle, the MonteCarloLocalization steps) runs on the first device, and the set moves there
+// and back DEVICE TO DEVICE over NVLink (amcl3d_b200_pf_shard_gather_local / _scatter_local), never through the host; the
+// shards are sized for max(max_resamp_num_, the current count), so a changing particle count re-draws the partition
+// without remaking them.  Host RNG (std::mt19937) as in the reference; setSeed() makes runs reproducible (the reference seeds
 // from std::random_device).
 #pragma once
 
@@ -275,6 +278,9 @@ public:
    *  the plain path.  Also read from AMCL3D_B200_DEVICES at construction.  The first device must be grid3d_'s. */
   void setDevices(const std::vector<int>& devices);
   const std::vector<int>& devices() const { return devices_; }
+  /*! Device-to-device moves of the whole set between the shards and the first device's handle so far (tests). */
+  uint64_t deviceGathers() const { return gathers_; }
+  uint64_t deviceScatters() const { return scatters_; }
 
 public:
   ParticleMirror p_;
@@ -295,7 +301,7 @@ private:
   float ranGaussian(const double mean, const double sigma);
   float rngUniform(const float range_from, const float range_to);
   void pull(std::vector<Particle>& out) const;  // device(s) -> host
-  bool sharded() const { return devices_.size() > 1; }
+  bool sharded() const { return devices_.size() > 1 && p_.size() >= devices_.size(); }
   void syncShards();     // the current set is spread over the shard handles
   void shardsChanged();  // a sharded device step changed the set
   void dropShards();
@@ -311,7 +317,8 @@ private:
   std::vector<int> devices_;
   std::vector<amcl3d_b200_pf_t> shard_;
   std::vector<amcl3d_b200_grid_t> replicas_;
-  uint64_t shard_n_{ 0 }, replica_generation_{ 0 };
+  uint64_t shard_n_{ 0 }, shard_cap_{ 0 }, replica_generation_{ 0 };
+  uint64_t gathers_{ 0 }, scatters_{ 0 };
   enum Where { kNowhere, kSingle, kSharded };
   Where where_{ kNowhere };  // which device-side home holds the set when p_.dev_fresh_
 };

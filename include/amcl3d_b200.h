@@ -293,6 +293,12 @@ int amcl3d_b200_pf_resample_step(amcl3d_b200_pf_t pf, int weight_multiply, int m
  * exchange region; fill it with set_particles / get it with get_particles as usual */
 int amcl3d_b200_pf_shard_init(amcl3d_b200_pf_t pf, uint64_t n_total, int rank, int world);
 int amcl3d_b200_pf_shard_info(amcl3d_b200_pf_t pf, uint64_t* lo, uint64_t* hi, uint64_t* region_bytes);
+/* the same with room to grow: the region is sized for n_capacity particles in total (n_total <= n_capacity), so that steps
+ * which change the particle count every frame (uniformSample, PFResample: amcl3d.cpp:192-203, ParticleFilter.cpp:256-280)
+ * do not remake the region.  shard_resize (collective, every rank with the same value, no exchange in flight) re-draws the
+ * block partition for a new total <= n_capacity; the contents of p_ are unspecified until it is filled again. */
+int amcl3d_b200_pf_shard_init_capacity(amcl3d_b200_pf_t pf, uint64_t n_total, uint64_t n_capacity, int rank, int world);
+int amcl3d_b200_pf_shard_resize(amcl3d_b200_pf_t pf, uint64_t n_total);
 /* CUDA IPC handle (64 bytes) of this rank's region / open the regions of all ranks (`world` handles, `stride` bytes apart,
  * indexed by rank; the own entry is ignored) */
 int amcl3d_b200_pf_shard_ipc_handle(amcl3d_b200_pf_t pf, void* handle64, size_t cap);
@@ -326,6 +332,14 @@ int amcl3d_b200_pf_shard_normalize_local(amcl3d_b200_pf_t* pfs, int world);
 int amcl3d_b200_pf_shard_resample_local(amcl3d_b200_pf_t* pfs, int world, float u01, int normalize, const void* const* d_wr_local,
                                         float alpha);
 int amcl3d_b200_pf_shard_mean_local(amcl3d_b200_pf_t* pfs, int world, float out7[7]);
+/* Steps of the reference that have no sharded form (uniformSample, addParticleWeight, computeSampleNum, updateSampleHeight,
+ * getBestParticle: their exact f32 chains run over the whole set anyway) on a set that lives in shards, without the host:
+ * gather_local copies the blocks of all ranks into p_ of the plain handle `dst` (any device of the box) device to device
+ * over NVLink, in stream order (dst's stream waits for the shards' streams and the other way round); scatter_local is
+ * the way back: it resizes the shards to the count `src` holds now (<= their capacity, >= world) and copies every rank
+ * its block of the new partition. */
+int amcl3d_b200_pf_shard_gather_local(amcl3d_b200_pf_t* pfs, int world, amcl3d_b200_pf_t dst);
+int amcl3d_b200_pf_shard_scatter_local(amcl3d_b200_pf_t src, amcl3d_b200_pf_t* pfs, int world);
 
 /* sequential f32 inclusive prefix of the current weights (ParticleFilter.cpp:259-264), for tests and
  * for multi-GPU callers: DEVICE pointer valid until the next call on the handle */

@@ -324,31 +324,55 @@ int main(int argc, char** argv)
     const float after_edit[2] = { (float)(pf.p_.uploads() - up0), (float)(pf.p_.downloads() - down0) };
     dump("lazy_after_edit", after_edit, 1, 2);
   }
-  // particles sharded over two devices behind the same class (skipped on a one-GPU box)
+  // a frame that changes the particle count between two sharded steps (the PFResample pattern, amcl3d.cpp:192-203):
+  // update, addParticleWeight, uniformSample, update, particleNormalize, resample.  Transfers counted before the host looks.
+  auto frame2 = [&](const std::string& tag) {
+    pf.p_ = P;
+    const uint64_t up0 = pf.p_.uploads(), down0 = pf.p_.downloads(), g0 = pf.deviceGathers(), s0 = pf.deviceScatters();
+    pf.update(cloud);
+    pf.addParticleWeight();
+    int S3 = sample_num;
+    pf.uniformSample(S3);
+    pf.update(cloud);
+    pf.particleNormalize();
+    pf.setSeed(seed);
+    pf.resample();
+    const float moves[4] = { (float)(pf.p_.uploads() - up0), (float)(pf.p_.downloads() - down0), (float)(pf.deviceGathers() - g0),
+                             (float)(pf.deviceScatters() - s0) };
+    dump((tag + "_frame2_moves").c_str(), moves, 1, 4);
+    dump_particles((tag + "_frame2").c_str(), pf.p_);
+  };
+  frame2("sd");
+  // particles sharded behind the same class: two and three ranks on device 0 (runs on a one-GPU box: the exchange protocol
+  // is the same, the "peers" are regions of the same device), and two devices when the box has them
   {
     int ndev = 0;
     amcl3d_b200_device_info(0, &ndev, nullptr, nullptr, nullptr, nullptr, nullptr);
     dump_scalar("md_devices", (float)ndev);
-    if (ndev >= 2)
-    {
-      pf.setDevices({ 0, 1 });
+    auto run_md = [&](const std::vector<int>& devs, const std::string& tag) {
+      pf.setDevices(devs);
       pf.p_ = P;
       pf.update(cloud);
-      dump_particles("md_after_update", pf.p_);
+      dump_particles((tag + "_after_update").c_str(), pf.p_);
       pf.particleNormalize();
-      dump_particles("md_after_normalize", pf.p_);
+      dump_particles((tag + "_after_normalize").c_str(), pf.p_);
       Particle mm = pf.getMean();
-      dump("md_mean", &mm.x, 1, 7);
+      dump((tag + "_mean").c_str(), &mm.x, 1, 7);
       pf.setSeed(seed);
       pf.resample();
-      dump_particles("md_after_resample", pf.p_);
-      // a step that only exists on one device brings the set home and carries on
+      dump_particles((tag + "_after_resample").c_str(), pf.p_);
+      // a step that only exists on one device: the set goes to the first device and carries on there
       pf.p_ = weighted;
       int S2 = sample_num;
       pf.uniformSample(S2);
-      dump_particles("md_after_uniform_sample", pf.p_);
+      dump_particles((tag + "_after_uniform_sample").c_str(), pf.p_);
+      frame2(tag);
       pf.setDevices({ 0 });
-    }
+    };
+    run_md({ 0, 0 }, "r2");
+    run_md({ 0, 0, 0 }, "r3");
+    if (ndev >= 2)
+      run_md({ 0, 1 }, "md");
   }
   g_out.close();
   std::printf("host_api_test ok\n");

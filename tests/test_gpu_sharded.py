@@ -3,7 +3,8 @@ must equal the one-GPU result bit for bit -- weights, resampled indices and part
 230-254), several frames in a row (the exchange region ping-pongs by epoch).
 
   * world 1 through the sharded entry points: runs on any box with one GPU;
-  * two devices inside ONE process (amcl3d_b200_pf_shard_attach_local, the path the C++ classes use): needs 2 GPUs;
+  * several ranks inside ONE process (amcl3d_b200_pf_shard_attach_local, the path the C++ classes use): two and three
+    ranks on device 0 (any box) and two devices (needs 2 GPUs);
   * one process per GPU under torch.distributed.run at 2 ranks (CUDA IPC): needs 2 GPUs; tools/sharded_check.py.
 """
 import os
@@ -112,25 +113,38 @@ def test_fast_mode_in_a_world_of_one_is_the_exact_result():
         assert np.array_equal(bits(f.pf.p_), bits(ref[k][1]))
 
 
-def test_two_devices_in_one_process():
+# rank layouts of the in-process tests: device ordinal of every rank.  Ranks that share a device run the very same exchange
+# protocol (stores into, flags on and loads from the other rank's region) -- so the protocol is covered on a one-GPU box too.
+LAYOUTS = {"2 ranks on device 0": [0, 0], "3 ranks on device 0": [0, 0, 0], "2 devices": [0, 1]}
+
+
+def _layout(name):
+    devs = LAYOUTS[name]
+    if max(devs) + 1 > _device_count():
+        pytest.skip(f"needs {max(devs) + 1} GPUs")
+    return devs
+
+
+@pytest.mark.parametrize("layout", list(LAYOUTS))
+def test_ranks_in_one_process(layout):
     """The ranks are handles of one process (attach_local + stream order): what amcl3d::ParticleFilter::setDevices uses."""
-    if _device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    devs = _layout(layout)
     from amcl3d_test_b200 import ParticleFilter, synth
     from amcl3d_test_b200.sharded import shard_bounds
 
-    sm, g0 = _world(0)
-    _, g1 = _world(1)
-    grids = [g0, g1]
+    world = len(devs)
+    by_dev = {}
+    for dv in sorted(set(devs)):
+        sm, by_dev[dv] = _world(dv)
     clouds = [synth.make_cloud(sm, 1500, 9.0, seed=synth.SEED_CLOUD + k) for k in range(3)]
     u01s = [0.37, 0.0, 0.93]
     n = 20_001
     P = synth.make_particles(sm, n, "T")
-    ref = _one_gpu(g0, P, clouds, u01s)
-    pfs = [ParticleFilter(g) for g in grids]
+    ref = _one_gpu(by_dev[0], P, clouds, u01s)
+    pfs = [ParticleFilter(by_dev[dv]) for dv in devs]
     for r, pf in enumerate(pfs):
-        lo, hi = pf.shard_init(n, r, 2)
-        assert (lo, hi) == shard_bounds(n, 2, r)
+        lo, hi = pf.shard_init(n, r, world)
+        assert (lo, hi) == shard_bounds(n, world, r)
         pf.p_ = P[lo:hi]
     ParticleFilter.shard_attach_local(pfs)
     for k, (cloud, u01) in enumerate(zip(clouds, u01s)):
@@ -141,6 +155,71 @@ def test_two_devices_in_one_process():
         assert np.array_equal(bits(out), bits(ref[k][1]))
         mean = ParticleFilter.shard_mean_local(pfs)
         assert np.allclose(mean[:6], ref[k][3][:6], rtol=1e-5, atol=1e-6) and mean[6] == ref[k][3][6]
+
+
+@pytest.mark.parametrize("layout", list(LAYOUTS))
+def test_particle_count_changes_between_sharded_steps(layout):
+    """uniformSample changes the particle count every frame (amcl3d.cpp:192-203, ParticleFilter.cpp:256-280) and has no
+    sharded form: the set is gathered into a plain handle device to device, resampled there, and scattered back over a
+    re-drawn partition (shards with capacity) -- shrinking, then growing.  Bit-identical to one GPU throughout."""
+    devs = _layout(layout)
+    from amcl3d_test_b200 import ParticleFilter, synth
+    from amcl3d_test_b200.sharded import shard_bounds
+
+    world = len(devs)
+    by_dev = {}
+    for dv in sorted(set(devs)):
+        sm, by_dev[dv] = _world(dv)
+    clouds = [synth.make_cloud(sm, 1200, 9.0, seed=synth.SEED_CLOUD + k) for k in range(3)]
+    n, cap = 6_001, 9_000
+    counts = [4_099, 8_999]  # shrink, then grow to just below the capacity
+    u01s = [0.11, 0.77]
+    P = synth.make_particles(sm, n, "T")
+
+    one = ParticleFilter(by_dev[0])
+    one.p_ = P
+    one.update(clouds[0])
+    ref = []
+    for S, cloud, u01 in zip(counts, clouds[1:], u01s):
+        one.uniformSample(S)
+        after_sample = one.p_
+        one.update(cloud)
+        one.particleNormalize()
+        one.resample(u01)
+        ref.append((after_sample, one.p_))
+
+    home = ParticleFilter(by_dev[0])  # the plain handle the set visits
+    pfs = [ParticleFilter(by_dev[dv]) for dv in devs]
+    for r, pf in enumerate(pfs):
+        lo, hi = pf.shard_init_capacity(n, cap, r, world)
+        assert (lo, hi) == shard_bounds(n, world, r)
+        pf.p_ = P[lo:hi]
+    ParticleFilter.shard_attach_local(pfs)
+    for pf in pfs:
+        pf.update(clouds[0])
+    for k, (S, cloud, u01) in enumerate(zip(counts, clouds[1:], u01s)):
+        ParticleFilter.shard_gather_local(pfs, home)
+        home.uniformSample(S)
+        assert np.array_equal(bits(home.p_), bits(ref[k][0]))
+        ParticleFilter.shard_scatter_local(home, pfs)
+        for r, pf in enumerate(pfs):
+            assert pf.shard_info()[:2] == shard_bounds(S, world, r) and pf.size() == shard_bounds(S, world, r)[1] - shard_bounds(S, world, r)[0]
+        assert np.array_equal(bits(np.concatenate([pf.p_ for pf in pfs])), bits(ref[k][0]))
+        for pf in pfs:
+            pf.update(cloud)
+        ParticleFilter.shard_resample_local(pfs, u01)
+        assert np.array_equal(bits(np.concatenate([pf.p_ for pf in pfs])), bits(ref[k][1]))
+    # misuse: beyond the capacity, fewer particles than ranks, a sharded handle as the plain one
+    home.p_ = synth.make_particles(sm, cap + 1, "T")
+    with pytest.raises(RuntimeError):
+        ParticleFilter.shard_scatter_local(home, pfs)
+    home.p_ = P[:world - 1]
+    with pytest.raises(RuntimeError):
+        ParticleFilter.shard_scatter_local(home, pfs)
+    with pytest.raises(RuntimeError):
+        ParticleFilter.shard_gather_local(pfs, pfs[0])
+    with pytest.raises(RuntimeError):
+        pfs[0].shard_resize(cap + 1)
 
 
 def test_two_ranks_one_process_per_gpu():

@@ -154,13 +154,25 @@ def test_cpp_classes_match_the_oracle(O, tmp_path):
     assert list(d["lazy_after_read"][0]) == [1, 1]
     assert list(d["lazy_after_edit"][0]) == [2, 1]
     assert np.array_equal(bits(d["lazy_after_frame"]), bits(d["after_resample"]))
-    # the same class sharded over two devices (amcl3d::ParticleFilter::setDevices): bit-identical to one device
-    if d["md_devices"][0, 0] >= 2:
-        assert np.array_equal(bits(d["md_after_update"]), bits(d["after_update"]))
-        assert np.array_equal(bits(d["md_after_normalize"]), bits(d["after_normalize"]))
-        assert np.array_equal(bits(d["md_after_resample"]), bits(d["after_resample"]))
-        assert np.array_equal(bits(d["md_after_uniform_sample"]), bits(d["after_uniform_sample"]))
-        assert np.allclose(d["md_mean"][0, :6], d["mean"][0, :6], rtol=1e-5, atol=1e-6)
+    # the same class sharded (amcl3d::ParticleFilter::setDevices): two and three ranks on device 0 -- the exchange protocol
+    # of csrc/shard.cu with regions of one device as "peers", so this runs on a one-GPU box -- and two devices when the
+    # box has them: bit-identical to one device.  frame2 changes the particle count between two sharded steps; the set
+    # moves to the first device and back device to device (one gather, one scatter, no host copy).
+    assert list(d["sd_frame2_moves"][0]) == [1, 0, 0, 0]
+    F, _, _ = O.uniform_sample(m, O.scale_by_max(W.copy()), S)
+    F = O.update(m, O.particles(F), cloud)
+    O.normalize(m, F)
+    F, _ = O.resample(F, d["resample_u01"][0, 0])
+    assert F.shape[0] == S != P.shape[0]
+    assert np.array_equal(bits(d["sd_frame2"]), bits(F))
+    for tag in ["r2", "r3"] + (["md"] if d["md_devices"][0, 0] >= 2 else []):
+        assert np.array_equal(bits(d[tag + "_after_update"]), bits(d["after_update"])), tag
+        assert np.array_equal(bits(d[tag + "_after_normalize"]), bits(d["after_normalize"])), tag
+        assert np.array_equal(bits(d[tag + "_after_resample"]), bits(d["after_resample"])), tag
+        assert np.array_equal(bits(d[tag + "_after_uniform_sample"]), bits(d["after_uniform_sample"])), tag
+        assert np.allclose(d[tag + "_mean"][0, :6], d["mean"][0, :6], rtol=1e-5, atol=1e-6), tag
+        assert list(d[tag + "_frame2_moves"][0]) == [1, 0, 1, 1], tag
+        assert np.array_equal(bits(d[tag + "_frame2"]), bits(d["sd_frame2"])), tag
     # free-function builders
     ref2 = O.compute_grid2(m, sm.points)
     assert np.allclose(d["free_compute_grid2"].reshape(-1), ref2, rtol=1e-6, atol=1e-30)

@@ -241,6 +241,21 @@ int main(int argc, char** argv)
     mcl.p_ = weighted;
     mcl.PFResample(true);
     dump_particles("mcl_after_pfresample", mcl.p_);
+    // the frame of the localisation loop (update, then PFResample: amcl3d.cpp:125,160,192-203) on one device and with the
+    // particles sharded over two ranks: PFResample has no sharded form, the set visits the first device and comes back
+    for (int pass = 0; pass < 2; ++pass)
+    {
+      if (pass == 1)
+        mcl.setDevices({ 0, 0 });
+      mcl.p_ = P;
+      const uint64_t down0 = mcl.p_.downloads();
+      mcl.update(cloud);
+      mcl.PFResample(true);
+      mcl.update(cloud);
+      dump_scalar(pass ? "mcl_md_frame_downloads" : "mcl_sd_frame_downloads", (float)(mcl.p_.downloads() - down0));
+      dump_particles(pass ? "mcl_md_after_frame" : "mcl_sd_after_frame", mcl.p_);
+    }
+    mcl.setDevices({ 0 });
     PointType h = mcl.getMapHeight(P[0].x, P[0].y);
     const float hv[3] = { h.x, h.y, h.z };
     dump("mcl_map_height", hv, 1, 3);

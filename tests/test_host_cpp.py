@@ -135,6 +135,12 @@ def test_cpp_classes_match_the_oracle(O, tmp_path):
     O.update_sample_height(Z, kp)
     assert np.array_equal(bits(d["mcl_after_height"]), bits(Z))
     assert np.array_equal(bits(d["mcl_after_pfresample"]), bits(O.pf_resample_step(m, W.copy(), 1, 150, 400, kp)))
+    # update -> PFResample -> update, on one device (against the oracle) and sharded over two ranks (same bits, no download)
+    G = O.pf_resample_step(m, O.update(m, O.particles(P), cloud), 1, 150, 400, kp)
+    G = O.update(m, O.particles(G), cloud)
+    assert np.array_equal(bits(d["mcl_sd_after_frame"]), bits(G))
+    assert np.array_equal(bits(d["mcl_md_after_frame"]), bits(G))
+    assert d["mcl_sd_frame_downloads"][0, 0] == 0 and d["mcl_md_frame_downloads"][0, 0] == 0
     # RelocPose: z of the nearest keypose replaces the given z (amcl3d.cpp:169-174), then ParticleFilter::relocPose
     q = np.array([P[0, 0], P[0, 1], 0.0], np.float32)
     nearest = kp[np.argmin(((kp - q) ** 2).astype(np.float32).sum(1))]

@@ -325,8 +325,10 @@ int amcl3d_b200_pf_shard_resample_fast(amcl3d_b200_pf_t pf, float u01, int32_t* 
  * or d_out7 (DEVICE), at least one */
 int amcl3d_b200_pf_shard_mean(amcl3d_b200_pf_t pf, float out7[7], void* d_out7);
 
-/* the two collective calls for ranks that are handles of ONE process (attach_local): issued on every handle in stream
- * order, then waited for (a synchronous call on one handle would wait for peers that were not launched yet).
+/* the collective calls for ranks that are handles of ONE process (attach_local; ranks may share a device): the publishing
+ * half of the exchange is issued on every handle, the streams are ordered with CUDA events, then the reading half is
+ * issued -- no kernel spins on work of this process that is not launched yet (the per-handle calls above, whose wait_kernel
+ * spins on the peers' flags, are for one process per rank; called rank after rank from one thread they would time out).
  * d_wr_local: NULL or `world` DEVICE pointers (rank r's raw range weights). */
 int amcl3d_b200_pf_shard_normalize_local(amcl3d_b200_pf_t* pfs, int world);
 int amcl3d_b200_pf_shard_resample_local(amcl3d_b200_pf_t* pfs, int world, float u01, int normalize, const void* const* d_wr_local,

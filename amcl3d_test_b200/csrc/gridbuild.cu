@@ -38,21 +38,48 @@ __device__ __forceinline__ uint32_t f2key(float f)
   const uint32_t b = __float_as_uint(f);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
+// the point passes keep four points per thread in flight: a batch of coalesced loads, then the work (the passes are
+// latency-bound otherwise: one point, three f64 divides and one atomic per loop trip).  A slot beyond n reads as NaN, which
+// every pass skips like any other non-finite point.
+constexpr int kPointsInFlight = 4;
+__device__ __forceinline__ void load_points(const float* __restrict__ xyz, uint32_t stride, uint64_t n, uint64_t i0, uint64_t T,
+                                            float (&q)[kPointsInFlight][3])
+{
+#pragma unroll
+  for (int u = 0; u < kPointsInFlight; ++u)
+  {
+    const uint64_t i = i0 + (uint64_t)u * T;
+    if (i < n)
+    {
+      const float* p = xyz + i * stride;
+      q[u][0] = p[0];
+      q[u][1] = p[1];
+      q[u][2] = p[2];
+    }
+    else
+      q[u][0] = q[u][1] = q[u][2] = __int_as_float(0x7FC00000);
+  }
+}
 __global__ void bounds_kernel(const float* __restrict__ xyz, uint32_t stride, uint64_t n, uint32_t* __restrict__ keys)
 {
   uint32_t lo[3] = { 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu }, hi[3] = { 0, 0, 0 };
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+  const uint64_t T = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += kPointsInFlight * T)
   {
-    const float* p = xyz + i * stride;
-    const float x = p[0], y = p[1], z = p[2];
-    if (!isfinite(x) || !isfinite(y) || !isfinite(z))
-      continue;
-    const uint32_t k[3] = { f2key(x), f2key(y), f2key(z) };
+    float q[kPointsInFlight][3];
+    load_points(xyz, stride, n, i0, T, q);  // all loads of the batch before the first use
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+    for (int u = 0; u < kPointsInFlight; ++u)
     {
-      lo[a] = min(lo[a], k[a]);
-      hi[a] = max(hi[a], k[a]);
+      if (!isfinite(q[u][0]) || !isfinite(q[u][1]) || !isfinite(q[u][2]))
+        continue;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+      {
+        const uint32_t k = f2key(q[u][a]);
+        lo[a] = min(lo[a], k);
+        hi[a] = max(hi[a], k);
+      }
     }
   }
 #pragma unroll
@@ -77,6 +104,7 @@ struct Lattice
 {
   double min[3];
   double pitch;  // resol / sub
+  double rinv;   // fl64(1 / pitch)
   int sub;
   int w[3];      // site nodes per axis = size + 1
   uint32_t words_per_row;
@@ -89,7 +117,15 @@ __device__ __forceinline__ bool snap_point(const Lattice& L, const float* p, lon
   {
     if (!isfinite(p[a]))
       return false;
-    h[a] = __double2ll_rn(__ddiv_rn(__dsub_rn((double)p[a], L.min[a]), L.pitch));
+    // lrint((p - min) / pitch): the product with the rounded reciprocal is within |q| * 2^-51 of the quotient, so both
+    // round to the same integer unless the quotient sits that close to a tie -- only then is the real divide needed
+    const double t = __dsub_rn((double)p[a], L.min[a]);
+    const double q = __dmul_rn(t, L.rinv);
+    const double r = rint(q);
+    if (0.5 - fabs(__dsub_rn(q, r)) <= fabs(q) * 1e-15)
+      h[a] = __double2ll_rn(__ddiv_rn(t, L.pitch));
+    else
+      h[a] = __double2ll_rn(r);
   }
   return true;
 }
@@ -107,12 +143,19 @@ __global__ void class_count_kernel(const __grid_constant__ Lattice L, const floa
   if (threadIdx.x < 8)
     sh[threadIdx.x] = 0;
   __syncthreads();
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+  const uint64_t T = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += kPointsInFlight * T)
   {
-    long long h[3];
-    if (!snap_point(L, xyz + i * stride, h))
-      continue;
-    atomicAdd(&sh[class_of(L, h)], 1u);
+    float q[kPointsInFlight][3];
+    load_points(xyz, stride, n, i0, T, q);
+#pragma unroll
+    for (int u = 0; u < kPointsInFlight; ++u)
+    {
+      long long h[3];
+      if (!snap_point(L, q[u], h))
+        continue;
+      atomicAdd(&sh[class_of(L, h)], 1u);
+    }
   }
   __syncthreads();
   if (threadIdx.x < 8 && sh[threadIdx.x])
@@ -124,10 +167,16 @@ __global__ void voxelize_kernel(const __grid_constant__ Lattice L, const float* 
                                 uint64_t n, int cls, uint32_t* __restrict__ bits, uint32_t sparse_mask,
                                 int4* __restrict__ sparse, unsigned int* __restrict__ sparse_count)
 {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+  const uint64_t T = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += kPointsInFlight * T)
   {
+   float q[kPointsInFlight][3];
+   load_points(xyz, stride, n, i0, T, q);
+#pragma unroll
+   for (int u = 0; u < kPointsInFlight; ++u)
+   {
     long long h[3];
-    if (!snap_point(L, xyz + i * stride, h))
+    if (!snap_point(L, q[u], h))
       continue;
     const int c = class_of(L, h);
     const bool is_sparse = sparse != nullptr && ((sparse_mask >> c) & 1u);
@@ -149,6 +198,7 @@ __global__ void voxelize_kernel(const __grid_constant__ Lattice L, const float* 
     }
     const uint64_t row = (uint64_t)j[2] * L.w[1] + (uint64_t)j[1];
     atomicOr(&bits[row * L.words_per_row + (uint32_t)(j[0] >> 5)], 1u << (j[0] & 31));
+   }
   }
 }
 
@@ -1449,6 +1499,7 @@ cudaError_t build_grid_edt(const MapDev& map, const float* d_xyz, uint32_t strid
     L.w[a] = (int)map.size[a] + 1;
   }
   L.pitch = map.resol / sub;
+  L.rinv = 1.0 / L.pitch;
   L.sub = sub;
   L.words_per_row = (uint32_t)((L.w[0] + 31) / 32);
   const uint64_t rows = (uint64_t)L.w[1] * L.w[2];

@@ -41,6 +41,34 @@ def test_edt_bit_exact_small(O, lattice, sub):
     assert np.array_equal(prob == 0, ref_prob == 0)
 
 
+@pytest.mark.parametrize("sub", [1, 2])
+def test_snap_to_the_lattice_at_and_around_ties(O, sub):
+    """Map points half-way between two lattice nodes and a few float steps either side of it: the device snaps with a
+    reciprocal product and falls back to the real f64 divide near a tie -- same node as lrint((p - min) / pitch) always."""
+    from amcl3d_test_b200 import Grid3d
+
+    rng = np.random.RandomState(11)
+    resol, extent = 0.1, (5.0, 4.0, 2.0)
+    pitch = resol / sub
+    size = np.round(np.array(extent) / resol).astype(int)
+    k = np.stack([rng.randint(0, size[a] * sub, 1500) for a in range(3)], 1)
+    pts = ((k + 0.5) * pitch).astype(np.float32)  # ties up to the float rounding of the coordinate
+    for step in range(1, 4):  # ... and up to three float steps above / below on random axes
+        up = np.nextafter(pts, np.float32(np.inf)) if step % 2 else np.nextafter(pts, np.float32(-np.inf))
+        pts = np.where(rng.randint(0, 2, pts.shape).astype(bool), up, pts).astype(np.float32)
+    pts = np.concatenate([[[0, 0, 0], list(extent)], pts]).astype(np.float32)
+    mn, mx = O.compute_bounds(pts)
+    m = O.Map(mn, mx, resol, 0.05)
+    ref = O.edt_exact(m, pts, sub=sub)
+    g = Grid3d(0)
+    g.computePointCloud(pts, resol)
+    g.computeGrid(pts, 0.05, sub=sub, keep_edt=True)
+    assert np.array_equal(g.edt(), ref)
+    exact_field = g.downloadGrid()
+    g.computeGrid(pts, 0.05, sub=sub)  # the fused fast build snaps through the same function
+    assert np.array_equal(bits(g.downloadGrid()), bits(exact_field))
+
+
 def test_edt_c1_map(O, world_c1):
     from amcl3d_test_b200 import Grid3d
 

@@ -163,6 +163,33 @@ __global__ void class_count_kernel(const __grid_constant__ Lattice L, const floa
 }
 
 // dense class `cls`: set occupancy bits; sparse classes (mask bit set): append lattice coordinates
+__device__ __forceinline__ void voxelize_point(const Lattice& L, const float* p, int cls, uint32_t* __restrict__ bits,
+                                               uint32_t sparse_mask, int4* __restrict__ sparse, unsigned int* __restrict__ sparse_count)
+{
+  long long h[3];
+  if (!snap_point(L, p, h))
+    return;
+  const int c = class_of(L, h);
+  const bool is_sparse = sparse != nullptr && ((sparse_mask >> c) & 1u);
+  if (!is_sparse && (bits == nullptr || c != cls))
+    return;
+  // site node index along each axis; nodes outside [0, size] are dropped
+  long long j[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    j[a] = (L.sub == 2) ? ((h[a] - ((c >> a) & 1)) >> 1) : h[a];
+  if (j[0] < 0 || j[0] >= L.w[0] || j[1] < 0 || j[1] >= L.w[1] || j[2] < 0 || j[2] >= L.w[2])
+    return;
+  if (is_sparse)
+  {
+    const unsigned int slot = atomicAdd(sparse_count, 1u);
+    if (slot < 8u * kSparseMax)
+      sparse[slot] = make_int4((int)h[0], (int)h[1], (int)h[2], 0);
+    return;
+  }
+  const uint64_t row = (uint64_t)j[2] * L.w[1] + (uint64_t)j[1];
+  atomicOr(&bits[row * L.words_per_row + (uint32_t)(j[0] >> 5)], 1u << (j[0] & 31));
+}
 __global__ void voxelize_kernel(const __grid_constant__ Lattice L, const float* __restrict__ xyz, uint32_t stride,
                                 uint64_t n, int cls, uint32_t* __restrict__ bits, uint32_t sparse_mask,
                                 int4* __restrict__ sparse, unsigned int* __restrict__ sparse_count)
@@ -170,35 +197,11 @@ __global__ void voxelize_kernel(const __grid_constant__ Lattice L, const float* 
   const uint64_t T = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += kPointsInFlight * T)
   {
-   float q[kPointsInFlight][3];
-   load_points(xyz, stride, n, i0, T, q);
+    float q[kPointsInFlight][3];
+    load_points(xyz, stride, n, i0, T, q);
 #pragma unroll
-   for (int u = 0; u < kPointsInFlight; ++u)
-   {
-    long long h[3];
-    if (!snap_point(L, q[u], h))
-      continue;
-    const int c = class_of(L, h);
-    const bool is_sparse = sparse != nullptr && ((sparse_mask >> c) & 1u);
-    if (!is_sparse && (bits == nullptr || c != cls))
-      continue;
-    // site node index along each axis; nodes outside [0, size] are dropped
-    long long j[3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-      j[a] = (L.sub == 2) ? ((h[a] - ((c >> a) & 1)) >> 1) : h[a];
-    if (j[0] < 0 || j[0] >= L.w[0] || j[1] < 0 || j[1] >= L.w[1] || j[2] < 0 || j[2] >= L.w[2])
-      continue;
-    if (is_sparse)
-    {
-      const unsigned int slot = atomicAdd(sparse_count, 1u);
-      if (slot < 8u * kSparseMax)
-        sparse[slot] = make_int4((int)h[0], (int)h[1], (int)h[2], 0);
-      continue;
-    }
-    const uint64_t row = (uint64_t)j[2] * L.w[1] + (uint64_t)j[1];
-    atomicOr(&bits[row * L.words_per_row + (uint32_t)(j[0] >> 5)], 1u << (j[0] & 31));
-   }
+    for (int u = 0; u < kPointsInFlight; ++u)
+      voxelize_point(L, q[u], cls, bits, sparse_mask, sparse, sparse_count);
   }
 }
 

@@ -128,7 +128,8 @@ __device__ __forceinline__ uint64_t voxel_address(const MapDev& map, uint32_t ix
 
 // The gathers use one useful element of every line they touch.  AMCL3D_LOAD_MODE selects the cache
 // operator: 0 ld.global.nc (L1-allocating), 1 ld.global.cg (L2 only), 2 ld.global.nc.L1::no_allocate,
-// 3 ld.global.L1::no_allocate.L2::evict_first.
+// 3 ld.global.L1::no_allocate.L2::evict_first, 4 ld.global.nc.L2::64B (the L2 fetches 64 instead of 128 bytes from DRAM
+// on a miss: profiles/r2_l2_prefetch_size_probe.txt).
 #ifndef AMCL3D_LOAD_MODE
 #define AMCL3D_LOAD_MODE 0
 #endif
@@ -138,6 +139,8 @@ __device__ __forceinline__ uint64_t voxel_address(const MapDev& map, uint32_t ix
 #define A3D_LD(suffix) "ld.global.nc.L1::no_allocate." suffix
 #elif AMCL3D_LOAD_MODE == 3
 #define A3D_LD(suffix) "ld.global.L1::no_allocate." suffix
+#elif AMCL3D_LOAD_MODE == 4
+#define A3D_LD(suffix) "ld.global.nc.L2::64B." suffix
 #else
 #define A3D_LD(suffix) "ld.global.nc." suffix
 #endif
@@ -672,6 +675,10 @@ __global__ void __launch_bounds__(256)
         case 5: asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(v[u]) : "l"(a)); break;
         case 6: asm volatile("ld.global.L1::evict_first.f32 %0, [%1];" : "=f"(v[u]) : "l"(a)); break;
         case 7: asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v[u]) : "l"(a)); break;
+        case 8: asm volatile("ld.global.L2::64B.f32 %0, [%1];" : "=f"(v[u]) : "l"(a)); break;   // L2 prefetch-size hints
+        case 9: asm volatile("ld.global.L2::128B.f32 %0, [%1];" : "=f"(v[u]) : "l"(a)); break;
+        case 10: asm volatile("ld.global.L2::256B.f32 %0, [%1];" : "=f"(v[u]) : "l"(a)); break;
+        case 11: asm volatile("ld.global.nc.L1::no_allocate.L2::64B.f32 %0, [%1];" : "=f"(v[u]) : "l"(a)); break;
         default: v[u] = __ldg(a); break;
       }
     }

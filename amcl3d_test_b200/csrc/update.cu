@@ -129,7 +129,7 @@ __device__ __forceinline__ uint64_t voxel_address(const MapDev& map, uint32_t ix
 // The gathers use one useful element of every line they touch.  AMCL3D_LOAD_MODE selects the cache
 // operator: 0 ld.global.nc (L1-allocating), 1 ld.global.cg (L2 only), 2 ld.global.nc.L1::no_allocate,
 // 3 ld.global.L1::no_allocate.L2::evict_first, 4 ld.global.nc.L2::64B (the L2 fetches 64 instead of 128 bytes from DRAM
-// on a miss: profiles/r2_l2_prefetch_size_probe.txt).
+// on a miss: profiles/r2_l2_prefetch_size_probe.txt), 5 ld.global.nc.L2::256B.
 #ifndef AMCL3D_LOAD_MODE
 #define AMCL3D_LOAD_MODE 0
 #endif
@@ -141,6 +141,8 @@ __device__ __forceinline__ uint64_t voxel_address(const MapDev& map, uint32_t ix
 #define A3D_LD(suffix) "ld.global.L1::no_allocate." suffix
 #elif AMCL3D_LOAD_MODE == 4
 #define A3D_LD(suffix) "ld.global.nc.L2::64B." suffix
+#elif AMCL3D_LOAD_MODE == 5
+#define A3D_LD(suffix) "ld.global.nc.L2::256B." suffix
 #else
 #define A3D_LD(suffix) "ld.global.nc." suffix
 #endif

@@ -329,6 +329,14 @@ def gather_peaks(grid):
             ms, loads = grid.bench_gather(window_cells=win, blocks=148 * 8, iters=256, coherent=coh)
             best = max(best, loads / (ms * 1e-3))
         out[name] = best
+    # the same whole-grid random gather with the ".L2::64B" load qualifier (probe flavour 8): half the DRAM bytes per miss,
+    # nearly the same rate -- the random-access rate of the DRAM, not its bandwidth, bounds regime A
+    # (profiles/r2_l2_prefetch_size_probe.txt)
+    best = 0.0
+    for _ in range(3):
+        ms, loads = grid.bench_gather(window_cells=0, blocks=148 * 8, iters=256, coherent=8 << 1)
+        best = max(best, loads / (ms * 1e-3))
+    out["whole_grid_random_l2_64B_fetch"] = best
     return out
 
 

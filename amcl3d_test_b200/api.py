@@ -477,6 +477,14 @@ class ParticleFilter:
         return np.float32(wtp.value)
 
     @staticmethod
+    def shard_mean_exact_local(pfs) -> np.ndarray:
+        """getMean as one sequential f32 chain carried from rank to rank: the bits one GPU produces."""
+        arr = (C.c_void_p * len(pfs))(*[p._h.value for p in pfs])
+        out = np.zeros(7, np.float32)
+        check(capi.load().amcl3d_b200_pf_shard_mean_exact_local(arr, len(pfs), out.ctypes.data))
+        return out
+
+    @staticmethod
     def shard_mean_local(pfs) -> np.ndarray:
         arr = (C.c_void_p * len(pfs))(*[p._h.value for p in pfs])
         out = np.zeros(7, np.float32)

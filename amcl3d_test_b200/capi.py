@@ -19,7 +19,7 @@ SYMBOLS = [
     "amcl3d_b200_grid_set_edt_fast", "amcl3d_b200_grid_build_device", "amcl3d_b200_grid_last_build_ms",
     "amcl3d_b200_pf_last_phase_ms",
     "amcl3d_b200_pf_shard_init", "amcl3d_b200_pf_shard_init_capacity", "amcl3d_b200_pf_shard_resize",
-    "amcl3d_b200_pf_shard_gather_local", "amcl3d_b200_pf_shard_scatter_local", "amcl3d_b200_pf_shard_info", "amcl3d_b200_pf_shard_ipc_handle",
+    "amcl3d_b200_pf_shard_gather_local", "amcl3d_b200_pf_shard_scatter_local", "amcl3d_b200_pf_shard_mean_exact_local", "amcl3d_b200_pf_shard_info", "amcl3d_b200_pf_shard_ipc_handle",
     "amcl3d_b200_pf_shard_attach_ipc", "amcl3d_b200_pf_shard_attach_local", "amcl3d_b200_pf_shard_resample",
     "amcl3d_b200_pf_shard_mean", "amcl3d_b200_pf_shard_resample_local", "amcl3d_b200_pf_shard_mean_local",
     "amcl3d_b200_pf_shard_normalize", "amcl3d_b200_pf_shard_normalize_local", "amcl3d_b200_grid_clone",
@@ -112,6 +112,7 @@ def load():
         "amcl3d_b200_pf_shard_mean": (i, [vp, vp, vp]),
         "amcl3d_b200_pf_shard_resample_local": (i, [P(vp), i, f32, i, P(vp), f32]),
         "amcl3d_b200_pf_shard_mean_local": (i, [P(vp), i, vp]),
+        "amcl3d_b200_pf_shard_mean_exact_local": (i, [P(vp), i, vp]),
         "amcl3d_b200_set_l2_fetch_granularity": (i, [i, i]),
         "amcl3d_b200_get_l2_fetch_granularity": (i, [i, P(i)]),
         "amcl3d_b200_grid_create": (i, [i, P(vp)]),

@@ -147,7 +147,7 @@ struct amcl3d_b200_pf_s
   uint64_t idx_cap = 0;
   float* d_noise = nullptr;
   uint64_t noise_cap = 0;
-  float* d_scalars = nullptr;  // [0] total [1] total_r [2] max [8..14] out7
+  float* d_scalars = nullptr;  // [0] total [1] total_r [2] max [8..14] out7 [16..22] exact-mean chain state of this rank (sharded)
   unsigned long long* d_u64 = nullptr;  // [0] counter [1] argmax
   int* d_int = nullptr;
   double* d_delta = nullptr;
@@ -2247,6 +2247,42 @@ int amcl3d_b200_pf_shard_mean_local(amcl3d_b200_pf_t* pfs, int world, float out7
   if (int rc = use_device(pfs[0]->grid->device))
     return rc;
   CU(cudaMemcpy(out7, pfs[0]->d_scalars + 8, 7 * sizeof(float), cudaMemcpyDeviceToHost));
+  return AMCL3D_B200_OK;
+}
+
+// getMean as ONE sequential f32 chain over the global particle order (ParticleFilter.cpp:198-216), i.e. the bits one GPU
+// produces: rank r continues the six sums (and the running maximum) where rank r - 1 stopped -- its kernel waits for that
+// rank's event and reads its seven floats (peer memory).  Serial over the ranks by construction: N_total x one FADD latency.
+int amcl3d_b200_pf_shard_mean_exact_local(amcl3d_b200_pf_t* pfs, int world, float out7[7])
+{
+  NvtxRange nvtx_range("getMean (sharded, one process, exact chain)");
+  if (!pfs || !out7 || world < 1 || world > (int)kMaxShardWorld)
+    return fail(AMCL3D_B200_ERR_ARG, "bad argument");
+  for (int r = 0; r < world; ++r)
+  {
+    if (!pfs[r])
+      return fail(AMCL3D_B200_ERR_ARG, "NULL handle");
+    const amcl3d_b200_pf_s::Shard& S = pfs[r]->shard;
+    if (!S.on || !S.attached || S.world != (uint32_t)world || S.rank != (uint32_t)r)
+      return fail(AMCL3D_B200_ERR_STATE, "handles must be the attached ranks 0..world-1 of one set");
+  }
+  for (int r = 0; r < world; ++r)
+  {
+    amcl3d_b200_pf_t pf = pfs[r];
+    if (int rc = use_device(pf->grid->device))
+      return rc;
+    if (r > 0)
+      CU(cudaStreamWaitEvent(pf->stream, pfs[r - 1]->ev_sync, 0));
+    {
+      Timed t(pf);
+      CU(launch_mean_exact_carry(pf->d_p, pf->n, r > 0 ? pfs[r - 1]->d_scalars + 16 : nullptr, pf->d_scalars + 16, pf->stream));
+      pf->launches += 1;
+    }
+    CU(cudaEventRecord(pf->ev_sync, pf->stream));
+  }
+  amcl3d_b200_pf_t last = pfs[world - 1];
+  CU(cudaMemcpyAsync(out7, last->d_scalars + 16, 7 * sizeof(float), cudaMemcpyDeviceToHost, last->stream));
+  CU(cudaStreamSynchronize(last->stream));
   return AMCL3D_B200_OK;
 }
 

@@ -210,6 +210,8 @@ cudaError_t launch_count_emitted(const float* thr, int S, const float* prefix, u
 // mean: exact = sequential f32 chains (bit-exact), else f64 tree reduction. out7 device (7 floats)
 cudaError_t launch_mean(const float* particles, uint64_t n, int exact, float* out7, void* scratch,
                         cudaStream_t stream);
+// the exact (sequential f32) mean of a block that continues the chains of the blocks before it: carry7 = their state
+cudaError_t launch_mean_exact_carry(const float* particles, uint64_t n, const float* carry7, float* out7, cudaStream_t stream);
 size_t reduce_scratch_bytes();
 cudaError_t launch_predict(float* particles, uint64_t n, const double* delta6_dev, const float* noise6,
                            cudaStream_t stream);

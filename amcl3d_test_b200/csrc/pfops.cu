@@ -1219,7 +1219,7 @@ __global__ void count_emitted_kernel(const float* __restrict__ thr, int S, const
 constexpr int kMeanChunk = 384;        // particles per stage: 384 x 28 B = 10752 B (a multiple of 16, as TMA wants)
 constexpr int kMeanPitch = kMeanChunk + 4;  // floats between product rows: 16-byte aligned, 4 banks apart
 __global__ void __launch_bounds__(kChainThreads) mean_exact_kernel(const float* __restrict__ particles, uint64_t n,
-                                                                   float* __restrict__ out7)
+                                                                   const float* carry7, float* out7)
 {
   __shared__ __align__(128) float raw[2][kMeanChunk * 7];
   __shared__ __align__(16) float prod[2][7][kMeanPitch];
@@ -1245,7 +1245,9 @@ __global__ void __launch_bounds__(kChainThreads) mean_exact_kernel(const float* 
   if (tid == 0)
     for (uint64_t c = 0; c < nchunks && c < 2; ++c)
       issue(c);
-  float acc = 0.f;  // lanes 0..5: the sum; lane 6: the max
+  // lanes 0..5: the sum; lane 6: the max.  carry7: the state the chains had after the particles before this block (a set
+  // sharded over several handles: the previous rank's out7, possibly peer memory), NULL = start of the set
+  float acc = (carry7 != nullptr && tid < 7) ? carry7[tid] : 0.f;
   for (uint64_t c = 0; c < nchunks + 1; ++c)
   {
     if (tid >= 32)
@@ -1571,7 +1573,7 @@ cudaError_t launch_mean(const float* particles, uint64_t n, int exact, float* ou
 {
   if (exact)
   {
-    mean_exact_kernel<<<1, kChainThreads, 0, stream>>>(particles, n, out7);
+    mean_exact_kernel<<<1, kChainThreads, 0, stream>>>(particles, n, nullptr, out7);
     return cudaGetLastError();
   }
   double* part = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + 16384);
@@ -1580,6 +1582,12 @@ cudaError_t launch_mean(const float* particles, uint64_t n, int exact, float* ou
     nb = kRedBlocks;
   mean_pass1<<<nb, kRedThreads, 0, stream>>>(particles, n, part);
   mean_pass2<<<1, 7 * 32, 0, stream>>>(part, nb, out7);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mean_exact_carry(const float* particles, uint64_t n, const float* carry7, float* out7, cudaStream_t stream)
+{
+  mean_exact_kernel<<<1, kChainThreads, 0, stream>>>(particles, n, carry7, out7);
   return cudaGetLastError();
 }
 

@@ -425,10 +425,13 @@ Particle ParticleFilter::getMean()
   Particle m;
   if (sharded())
   {
-    // partial sums per device, combined in rank order in f64 (the one step of the sharded path that is not the
-    // reference's sequential f32 chain: differs from one GPU in the last ulps)
+    // exact (default): ONE sequential f32 chain carried from rank to rank, the bits one device produces (serial over the
+    // ranks); fast (setExactMean(false)): partial sums per device combined in rank order in f64, last-ulp differences
     syncShards();
-    check(amcl3d_b200_pf_shard_mean_local(shard_.data(), static_cast<int>(shard_.size()), &m.x), "getMean (sharded)");
+    if (exact_mean_)
+      check(amcl3d_b200_pf_shard_mean_exact_local(shard_.data(), static_cast<int>(shard_.size()), &m.x), "getMean (sharded, exact)");
+    else
+      check(amcl3d_b200_pf_shard_mean_local(shard_.data(), static_cast<int>(shard_.size()), &m.x), "getMean (sharded)");
     mean_ = m;
     return m;
   }

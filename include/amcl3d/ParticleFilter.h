@@ -16,7 +16,7 @@
 // addParticleWeight, getBestParticle, the MonteCarloLocalization steps) runs on the first device, and the set moves there
 // and back DEVICE TO DEVICE over NVLink (amcl3d_b200_pf_shard_gather_local / _scatter_local), never through the host; the
 // shards are sized for max(max_resamp_num_, the current count), so a changing particle count re-draws the partition
-// without remaking them.  Host RNG (std::mt19937) as in the reference; setSeed() makes runs reproducible (the reference seeds
+// without remaking them.  getMean of a sharded set is one f32 chain carried from device to device (setExactMean).  Host RNG (std::mt19937) as in the reference; setSeed() makes runs reproducible (the reference seeds
 // from std::random_device).
 #pragma once
 
@@ -278,6 +278,10 @@ public:
    *  the plain path.  Also read from AMCL3D_B200_DEVICES at construction.  The first device must be grid3d_'s. */
   void setDevices(const std::vector<int>& devices);
   const std::vector<int>& devices() const { return devices_; }
+  /*! getMean() of a sharded set: true (default) = one sequential f32 chain carried from device to device, bit-identical to
+   *  one device (serial over the devices: about 3 us per 1000 particles in total); false = per-device partial sums combined
+   *  in f64 (tens of microseconds, last-ulp differences).  One device always runs the exact chain. */
+  void setExactMean(bool exact) { exact_mean_ = exact; }
   /*! Device-to-device moves of the whole set between the shards and the first device's handle so far (tests). */
   uint64_t deviceGathers() const { return gathers_; }
   uint64_t deviceScatters() const { return scatters_; }
@@ -319,6 +323,7 @@ private:
   std::vector<amcl3d_b200_grid_t> replicas_;
   uint64_t shard_n_{ 0 }, shard_cap_{ 0 }, replica_generation_{ 0 };
   uint64_t gathers_{ 0 }, scatters_{ 0 };
+  bool exact_mean_{ true };
   enum Where { kNowhere, kSingle, kSharded };
   Where where_{ kNowhere };  // which device-side home holds the set when p_.dev_fresh_
 };

@@ -334,6 +334,9 @@ int amcl3d_b200_pf_shard_normalize_local(amcl3d_b200_pf_t* pfs, int world);
 int amcl3d_b200_pf_shard_resample_local(amcl3d_b200_pf_t* pfs, int world, float u01, int normalize, const void* const* d_wr_local,
                                         float alpha);
 int amcl3d_b200_pf_shard_mean_local(amcl3d_b200_pf_t* pfs, int world, float out7[7]);
+/* the same as ONE sequential f32 chain over the global order -- bit-identical to getMean of one GPU (ParticleFilter.cpp:198-216):
+ * rank r continues the sums where rank r - 1 stopped (its seven floats read from peer memory).  Serial over the ranks. */
+int amcl3d_b200_pf_shard_mean_exact_local(amcl3d_b200_pf_t* pfs, int world, float out7[7]);
 /* Steps of the reference that have no sharded form (uniformSample, addParticleWeight, computeSampleNum, updateSampleHeight,
  * getBestParticle: their exact f32 chains run over the whole set anyway) on a set that lives in shards, without the host:
  * gather_local copies the blocks of all ranks into p_ of the plain handle `dst` (any device of the box) device to device

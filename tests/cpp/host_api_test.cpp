@@ -371,8 +371,12 @@ int main(int argc, char** argv)
       dump_particles((tag + "_after_update").c_str(), pf.p_);
       pf.particleNormalize();
       dump_particles((tag + "_after_normalize").c_str(), pf.p_);
-      Particle mm = pf.getMean();
+      Particle mm = pf.getMean();  // one f32 chain carried from rank to rank
       dump((tag + "_mean").c_str(), &mm.x, 1, 7);
+      pf.setExactMean(false);
+      mm = pf.getMean();  // per-rank partial sums combined in f64
+      dump((tag + "_mean_fast").c_str(), &mm.x, 1, 7);
+      pf.setExactMean(true);
       pf.setSeed(seed);
       pf.resample();
       dump_particles((tag + "_after_resample").c_str(), pf.p_);

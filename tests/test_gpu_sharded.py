@@ -51,7 +51,7 @@ def _one_gpu(g, P, clouds, u01s, beacons=None):
         W = pf.p_
         pf.particleNormalize()
         idx = pf.resample(u01, want_idx=True)
-        out.append((W, pf.p_, idx, pf.getMean()))
+        out.append((W, pf.p_, idx, pf.getMean(), pf.getMean(exact=True)))
     return out
 
 
@@ -155,6 +155,8 @@ def test_ranks_in_one_process(layout):
         assert np.array_equal(bits(out), bits(ref[k][1]))
         mean = ParticleFilter.shard_mean_local(pfs)
         assert np.allclose(mean[:6], ref[k][3][:6], rtol=1e-5, atol=1e-6) and mean[6] == ref[k][3][6]
+        exact = ParticleFilter.shard_mean_exact_local(pfs)  # one f32 chain carried from rank to rank
+        assert np.array_equal(bits(exact), bits(ref[k][4]))
 
 
 @pytest.mark.parametrize("layout", list(LAYOUTS))
